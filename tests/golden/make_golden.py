@@ -1,0 +1,184 @@
+"""Generate the golden vectors under tests/golden/ by running the REFERENCE code.
+
+Runs only in the build container (needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+It imports the reference's own `movedepth.layers`, `movedepth.networks` and `movedepth.trainer`
+with the import shims of SURVEY.md §8(c) (stub tensorboardX/matplotlib/skimage/pykitti, PIL
+ANTIALIAS alias, no-op torch.cuda.set_device, out-of-place residual in UncertNet.forward), gives
+every sub-model the deterministic weights of tests/_weights.py, and records reference outputs
+for (A) each operator on small seeded inputs and (B) whole `Trainer.process_batch` + backward
+steps on a small configuration.  The inputs are regenerated from seeds by the tests
+(tests/_cases.py), only outputs are stored.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+REF = os.environ.get("MOVEDEPTH_REFERENCE", "/root/reference")
+
+
+def import_reference():
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    class _Writer:
+        def __init__(self, *a, **k):
+            pass
+
+        def __getattr__(self, _):
+            return lambda *a, **k: None
+
+    stub("tensorboardX", SummaryWriter=_Writer)
+    plt = stub("matplotlib.pyplot", get_cmap=lambda *a, **k: None)
+    stub("matplotlib", pyplot=plt)
+    stub("skimage.transform")
+    stub("skimage", transform=sys.modules["skimage.transform"])
+    stub("pykitti")
+    from PIL import Image
+    if not hasattr(Image, "ANTIALIAS"):
+        Image.ANTIALIAS = Image.LANCZOS
+    torch.cuda.set_device = lambda *_: None
+    sys.path.insert(0, REF)
+    import movedepth.layers as rl
+    import movedepth.networks as rn
+    import movedepth.trainer as rt
+    from movedepth.options import MonodepthOptions
+
+    def uncert_forward(self, x):       # same values as depth_decoder.py:387-393, residual out of place
+        out = self.conv2(self.conv1(x))
+        out = out + x
+        return torch.sigmoid(self.head_convs(out))
+    rn.UncertNet.forward = uncert_forward
+    return rl, rn, rt, MonodepthOptions
+
+
+def np32(t):
+    return t.detach().cpu().numpy().astype(np.float32)
+
+
+def op_vectors(rl):
+    import _cases as C
+    g = {}
+    # A1: depth hypotheses
+    c = C.case_hypotheses()
+    g["hyp_v2"] = np32(rl.schedule_depth_rangev2(c["prior"], c["D"], c["fac"]))
+    g["hyp_zv2"] = np32(rl.schedule_depth_range_zv2(c["prior"], c["D"], c["fac"], c["z_trans"]))
+    g["hyp_v2_linear"] = np32(rl.schedule_depth_rangev2(c["prior"], c["D"], c["fac"], type="linear"))
+    # A2: cost volume (reference layout [B,D,C,h,w]) for each pose case
+    for name in C.COSTVOL_CASES:
+        c = C.case_costvol(name)
+        bp = rl.BackprojectDepth(c["D"], c["h"], c["w"])
+        pj = rl.Project3D(c["D"], c["h"], c["w"])
+        ref, src = c["ref"].clone().requires_grad_(True), c["src"].clone().requires_grad_(True)
+        vol = rl.generate_costvol(ref, src, c["K"], c["invK"], c["hyps"], c["pose"], c["D"], bp, pj)
+        g["costvol_%s" % name] = np32(vol)
+        (vol * c["gvol"]).sum().backward()
+        g["costvol_%s_gref" % name] = np32(ref.grad)
+        g["costvol_%s_gsrc" % name] = np32(src.grad)
+    # A3: entropy + localmax
+    c = C.case_localmax()
+    g["entropy"] = np32(rl.entropy(c["prob"], dim=1, keepdim=True))
+    for r in (1, 2):
+        g["localmax_r%d" % r] = np32(rl.localmax(c["prob"], r, c["D"], c["inv_a"], c["inv_b"]))
+    g["localmax_onehot"] = np32(rl.localmax(c["onehot"], 1, c["D"], c["inv_a"], c["inv_b"]))
+    # A4: convex upsample
+    c = C.case_convex()
+    g["convex_up"] = np32(rl.convex_upsample(c["depth"], c["mask"], 2))
+    # A5: SSIM, reprojection pieces, smoothness
+    c = C.case_images()
+    g["ssim"] = np32(rl.SSIM()(c["x"], c["y"]))
+    g["smooth"] = np32(rl.get_smooth_loss(c["disp"], c["x"]))
+    # A6: pose matrices
+    c = C.case_pose()
+    g["T_fwd"] = np32(rl.transformation_from_parameters(c["aa"], c["tr"], invert=False))
+    g["T_inv"] = np32(rl.transformation_from_parameters(c["aa"], c["tr"], invert=True))
+    # A7: full-res border warp
+    c = C.case_warp()
+    bp = rl.BackprojectDepth(c["B"], c["H"], c["W"])
+    pj = rl.Project3D(c["B"], c["H"], c["W"])
+    grid = pj(bp(c["depth"], c["invK"]), c["K"], c["T"])
+    g["warp_grid"] = np32(grid)
+    g["warp_img"] = np32(torch.nn.functional.grid_sample(c["img"], grid, padding_mode="border", align_corners=True))
+    np.savez_compressed(os.path.join(HERE, "ops.npz"), **g)
+    print("ops.npz:", {k: v.shape for k, v in g.items()})
+
+
+def step_vectors(rl, rn, rt, Options):
+    import _cases as C
+    from _weights import fill_deterministic
+    for name, cfg in C.STEP_CASES.items():
+        argv = ["--no_cuda", "--weights_init", "scratch", "--num_workers", "0", "--data_path", "/nonexistent",
+                "--png", "--log_dir", "/tmp/mvd_golden", "--prior_scale", "2", "--convex_up",
+                "--height", str(cfg["H"]), "--width", str(cfg["W"]), "--num_depth_bins", str(cfg["D"]),
+                "--batch_size", str(cfg["B"]), "--res_arch", str(cfg.get("arch", 18)), "--learning_rate", "2e-4",
+                "--frame_ids"] + [str(f) for f in cfg["frame_ids"]]
+        opt = Options().parser.parse_args(argv)
+        tr = rt.Trainer(opt)
+        for k, m in tr.models.items():
+            fill_deterministic(m, salt=k + "/")
+        tr.set_train()
+        tr.epoch, tr.step = cfg["epoch"], 0
+        inputs, noise, mask_xy = C.step_inputs(cfg)
+        # the reference draws its own noise / box: feed it ours through the same RNG entry points
+        noise_q = [n.clone() for n in noise]
+        orig_randn = torch.randn
+        torch.randn = lambda *a, **k: noise_q.pop(0) if (len(a) == 1 and isinstance(a[0], torch.Size)) else orig_randn(*a, **k)
+        xy_q = list(mask_xy)
+        orig_ri = np.random.randint
+        np.random.randint = lambda *a, **k: xy_q.pop(0)
+        captured = {}
+        def grab(_m, args):                     # first call = un-augmented reference frame
+            captured.setdefault("vol", args[0].detach().clone())
+        h1 = tr.models["reg3d"].register_forward_pre_hook(grab)
+        try:
+            outputs, losses = tr.process_batch(dict(inputs), is_train=True)
+        finally:
+            torch.randn, np.random.randint = orig_randn, orig_ri
+            h1.remove()
+        tr.model_optimizer.zero_grad()
+        losses["loss"].backward()
+        g = {"loss/" + k: np32(v) for k, v in losses.items()}
+        for s in range(4):
+            g["disp%d" % s] = np32(outputs[("disp", s)])
+        g["depth_mvs"] = np32(outputs["depth_mvs"])
+        g["masked_depth"] = np32(outputs["masked_depth"])
+        g["fused_depth"] = np32(outputs["fused_depth"])
+        g["trust_mono_mask"] = np32(outputs["trust_mono_mask"])
+        g["mono_reproj_loss"] = np32(outputs["mono_reproj_loss"])
+        g["mvs_reprojection_loss"] = np32(outputs["mvs_reprojection_loss"])
+        g["cost_volume"] = np32(captured["vol"])
+        for f in cfg["frame_ids"][1:]:
+            g["cam_T_cam_%d" % f] = np32(outputs[("cam_T_cam", 0, f)])
+            g["warped_%d_s0" % f] = np32(outputs[("color", f, 0)])
+        for k, m in tr.models.items():
+            sq = sum(float((p.grad.double() ** 2).sum()) for p in m.parameters() if p.grad is not None)
+            g["gradnorm/" + k] = np.float64(sq ** 0.5)
+        sd = {k: dict(m.named_parameters()) for k, m in tr.models.items()}
+        for mk, pk in C.GRAD_PROBES:
+            g["grad/%s/%s" % (mk, pk)] = np32(sd[mk][pk].grad)
+        # one Adam step, then probe a few updated parameters
+        tr.model_optimizer.step()
+        for mk, pk in C.GRAD_PROBES:
+            g["adam/%s/%s" % (mk, pk)] = np32(sd[mk][pk])
+        np.savez_compressed(os.path.join(HERE, "step_%s.npz" % name), **g)
+        print("step_%s.npz: loss=%.6f" % (name, float(losses["loss"])),
+              {k: float(v) for k, v in g.items() if k.startswith("loss/")})
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    rl, rn, rt, Options = import_reference()
+    op_vectors(rl)
+    step_vectors(rl, rn, rt, Options)
