@@ -1,0 +1,226 @@
+#!/usr/bin/env python
+"""Benchmark of the MOVEDepth dense hot path (BASELINE.json metric: training frames/sec at
+192x640, D=96; cost-volume kernel HBM GB/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Own arm: one process per GPU (launched by torchrun for N>1).  A step = Trainer.process_batch +
+backward + fused Adam on one synthetic batch of BASELINE configs[1] (ResNet18, 2-frame, 192x640,
+D=96, batch 6 per GPU).  Prints ONE JSON line on rank 0.
+Reference arm (`--impl reference`): the CPU oracle port of the reference's own step
+(oracle/step.py; the Python reference cannot travel to the GPU box) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "training frames/sec (192x640, D=96)"
+H, W, D, BATCH, C, G = 192, 640, 96, 6, 32, 16
+WORKLOAD = "ResNet18 2-frame 192x640 D=96 batch 6/GPU, fwd+bwd+Adam (BASELINE configs[1])"
+
+
+def costvol_bytes(batch):
+    """Algorithmic bytes of one fused cost-volume launch: ref + src + prior in, grouped volume out
+    = 4*B*h*w*(2C + 1 + D*G)  (SURVEY section 8d)."""
+    return 4 * batch * (H // 4) * (W // 4) * (2 * C + 1 + D * G)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                     "hw_power_brake_slowdown": 0x80, "sync_boost": 0x10, "applications_clocks_setting": 0x2}
+            while not self.stop_flag:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+                time.sleep(0.05)
+        except Exception as e:                       # NVML missing: report that rather than inventing clocks
+            self.reasons.add("nvml_unavailable:%s" % type(e).__name__)
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "samples": len(self.sm), "reasons": sorted(self.reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+def oracle_options(batch):
+    from oracle.step import default_options
+    return default_options(height=H, width=W, num_depth_bins=D, batch_size=batch, frame_ids=[0, -1], matching_ids=[0, -1],
+                           res_arch=18, learning_rate=2e-4)
+
+
+def time_oracle(steps, warmup, batch=1):
+    """frames/s of the oracle port's full train step on the host cores (bounded sample: `batch`
+    frames of the benchmark workload per step)."""
+    import torch
+    from oracle.step import OracleStep, synthetic_inputs
+    torch.set_num_threads(os.cpu_count() or 1)
+    opt = oracle_options(batch)
+    torch.manual_seed(0)
+    st = OracleStep(opt)
+    inputs = synthetic_inputs(opt, batch, seed=1)
+    for _ in range(warmup):
+        st.train_step(dict(inputs), epoch=0)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        st.train_step(dict(inputs), epoch=0)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    fps, sec, cores = time_oracle(args.steps, max(1, args.warmup), batch=1)
+    sample = "1 frame of the workload per step (same shapes, D=96), %d timed steps after %d warm-up" % (args.steps, max(1, args.warmup))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "host": "CPU, torch %d threads" % cores},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def run_own(args):
+    import torch
+    import torch.distributed as dist
+    from movedepth_b200 import ops
+    from movedepth_b200.options import MonodepthOptions
+    from movedepth_b200.trainer import Trainer, SyntheticKITTI
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    argv = ["--height", str(H), "--width", str(W), "--num_depth_bins", str(D), "--batch_size", str(BATCH), "--frame_ids", "0", "-1",
+            "--matching_ids", "0", "-1", "--res_arch", "18", "--weights_init", "scratch", "--prior_scale", "2", "--convex_up",
+            "--learning_rate", "2e-4", "--b200_conv_precision", args.precision, "--log_dir", "/tmp/mvd_bench"]
+    if world > 1:
+        argv.append("--ddp")
+    opt = MonodepthOptions().parse(argv)
+    torch.manual_seed(0)
+    tr = Trainer(opt)
+    tr.epoch = 9 if args.velocity else 0        # epoch > ztrans_start_epc switches to the velocity-guided range
+    host_batches = list(SyntheticKITTI(opt, BATCH, 4, seed=1 + rank))
+    dev_batches = [{k: v.cuda(non_blocking=True) for k, v in b.items()} for b in host_batches]
+    h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(batches, steps, read_loss):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            flush.fill_(i & 1)                                            # L2 flush between iterations
+            _, losses = tr.train_step(batches[i % len(batches)])
+            if read_loss:
+                float(losses["loss"])                                     # device -> host read of the step result
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for i in range(max(3, args.warmup)):
+        tr.train_step(dev_batches[i % 4])
+    sampler = ClockSampler(local)
+    sampler.start()
+    ops.costvol_events = []
+    n0 = ops.launch_counter["n"]
+    ms = timed(dev_batches, args.steps, read_loss=False)
+    launches = ops.launch_counter["n"] - n0
+    cv = [a.elapsed_time(b) for a, b in ops.costvol_events]
+    ops.costvol_events = None
+    ms_e2e = timed(host_batches, args.steps, read_loss=True)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank != 0:
+        return
+    frames = BATCH * world * args.steps
+    pk, pk_src = peaks()
+    cv_ms = sum(cv) / len(cv)
+    achieved = costvol_bytes(BATCH) / (cv_ms * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "precision": {"mixed": "fp32 on the cost-volume branch; cuDNN TF32 (PyTorch's default "
+                   "conv policy) on the mono/pose branch", "fp32": "fp32 everywhere", "tf32": "cuDNN TF32 everywhere"}[args.precision],
+                   "schedule": "velocity-guided (epoch 9)" if args.velocity else "fixed range (epoch 0)",
+                   "l2": "256 MiB buffer written between timed steps (L2 flush); per-step activations also exceed L2",
+                   "parallelism": "dp%d, flat-arena gradient all-reduce over NCCL" % world},
+        "roofline": {"kernel": "costvol_grouped_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / pk["hbm_gbs"], "traffic": args.traffic, "peak_source": pk_src,
+                     "algorithmic_bytes": costvol_bytes(BATCH), "avg_launch_us": cv_ms * 1e3, "launches_timed": len(cv)},
+        "clocks": sampler.summary(),
+        "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        fps, sec, cores = time_oracle(3, 1, batch=1)
+        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                                "sample": "1 frame of the workload per step (same shapes, D=96), 3 timed steps after 1 warm-up"}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--precision", default="mixed", choices=["mixed", "fp32", "tf32"])
+    ap.add_argument("--velocity", action="store_true", help="use the velocity-guided hypothesis range (epoch > 8)")
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from the committed ncu capture")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_own(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,121 @@
+/*
+ * movedepth_b200 -- C ABI of the B200-native MOVEDepth dense hot path.
+ *
+ * The reference (JeffWang987/MOVEDepth) has no FFI layer: its hot path is plain PyTorch
+ * (SURVEY.md section 8b).  This header is the boundary a maintainer binds instead of the
+ * ATen call sites cited on each entry point (file:line relative to the reference root).
+ * INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer on the current CUDA device, fp32, 16-byte aligned,
+ *     dense in the layout stated; the caller owns all buffers; nothing is allocated, freed
+ *     or synchronised inside the library;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); every call
+ *     only enqueues work on it, so calls are CUDA-graph capturable;
+ *   - return 0 on success, <0 for an argument error detected before any launch,
+ *     >0 = the cudaError_t of a failed launch.  mvd_last_error_string() returns a
+ *     thread-local description of the last failure on the calling thread;
+ *   - no C++ exception crosses the boundary; functions are re-entrant.
+ */
+#ifndef MOVEDEPTH_B200_H_
+#define MOVEDEPTH_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVD_ABI_VERSION 1
+
+/* cost-volume output layouts (grouped volume, G correlation groups) */
+#define MVD_LAYOUT_BGDHW 0 /* [B,G,D,h,w] : what reg3d's first Conv3d consumes (NCDHW)       */
+#define MVD_LAYOUT_BDHWG 1 /* [B,D,h,w,G] : channels-last-3d view of the same logical tensor */
+
+/* flags */
+#define MVD_FLAG_NO_TMA 1 /* force the global-gather route (debug / parity isolation) */
+
+int mvd_version(void);
+const char* mvd_last_error_string(void);
+/* number of SMs the persistent grids were sized for (0 before the first launch) */
+int mvd_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * K1  fused homography-warp cost volume, group correlation folded in.
+ * Replaces: movedepth/layers.py:778-794 (generate_costvol: BackprojectDepth 581-586,
+ * Project3D 601-621, F.grid_sample zeros/bilinear/align_corners=True at 791, product 792)
+ * followed by the group mean movedepth/trainer.py:359 (reshape(B,D,C/G,G,h,w).mean(2)).
+ *
+ *   ref, src : [B,h,w,C] channels-last matching features (C == 32)
+ *   prior    : [B,h,w]   mono depth prior, used with `ratio` when hyps == NULL
+ *   ratio    : [B,D]     hypothesis d = prior * ratio[b,d]  (separable form of
+ *                        schedule_depth_rangev2 / _zv2, layers.py:256-284 / 370-398)
+ *   hyps     : [B,D,h,w] explicit hypotheses, or NULL
+ *   K, invK, T : [B,4,4] row-major; K/invK at the volume's resolution, T = ref->src pose
+ *   out      : grouped volume, G == 16 groups, group g = mean of channels {g, g+G},
+ *              laid out per `out_layout`
+ * ------------------------------------------------------------------------------------- */
+int mvd_costvol_grouped_fwd(const float* ref, const float* src, const float* prior,
+                            const float* ratio, const float* hyps, const float* K,
+                            const float* invK, const float* T, float* out, int B, int C, int G,
+                            int h, int w, int D, int out_layout, int flags, void* stream);
+
+/* Backward of the above (autograd of grid_sample + product + group mean; the sampling grid
+ * is built under no_grad in the reference, layers.py:784-790, so only ref/src get gradients).
+ *   gout : same layout as `out`;  gref, gsrc : [B,h,w,C], OVERWRITTEN (zeroed inside). */
+int mvd_costvol_grouped_bwd(const float* gout, const float* ref, const float* src,
+                            const float* prior, const float* ratio, const float* hyps,
+                            const float* K, const float* invK, const float* T, float* gref,
+                            float* gsrc, int B, int C, int G, int h, int w, int D, int out_layout,
+                            int flags, void* stream);
+
+/* Reference-layout volume (public generate_costvol signature, layers.py:778-794):
+ *   ref, src : [B,C,h,w] (NCHW, any C);  hyps : [B,D,h,w];  out : [B,D,C,h,w]. */
+int mvd_costvol_full_fwd(const float* ref, const float* src, const float* hyps, const float* K,
+                         const float* invK, const float* T, float* out, int B, int C, int h, int w,
+                         int D, void* stream);
+/*   gout : [B,D,C,h,w];  gref, gsrc : [B,C,h,w], OVERWRITTEN (zeroed inside). */
+int mvd_costvol_full_bwd(const float* gout, const float* ref, const float* src, const float* hyps,
+                         const float* K, const float* invK, const float* T, float* gref,
+                         float* gsrc, int B, int C, int h, int w, int D, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K3  softmax over D + entropy + local-max depth regression, one pass over the logits.
+ * Replaces: F.softmax(cost,1) movedepth/trainer.py:367,395; entropy layers.py:862-863;
+ * localmax layers.py:796-812 (argmax, clamped +-radius window counted with duplicates,
+ * soft index / (D-1), depth = 1/(inv_a + n*(inv_b-inv_a))).
+ *   logits : [B,D,h,w];  inv_a, inv_b : [B,h,w] (1/hyps[:, -1], 1/hyps[:, 0])
+ *   prob (nullable) : [B,D,h,w];  entropy : [B,h,w];  depth : [B,h,w];  amax : [B,h,w] int32
+ * ------------------------------------------------------------------------------------- */
+int mvd_regress_fwd(const float* logits, const float* inv_a, const float* inv_b, float* prob,
+                    float* entropy, float* depth, int* amax, int B, int D, int hw, int radius,
+                    void* stream);
+/* Backward: glogits = d(entropy)/dlogits * g_entropy + d(depth)/dlogits * g_depth
+ * (the argmax index is a constant, as in autograd).  Recomputes the softmax from logits. */
+int mvd_regress_bwd(const float* logits, const float* inv_a, const float* inv_b, const int* amax,
+                    const float* g_entropy, const float* g_depth, float* glogits, int B, int D,
+                    int hw, int radius, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K4  convex upsampling.  Replaces: convex_upsample movedepth/layers.py:200-214
+ * (softmax over the 9 taps of mask.view(B,9,f,f,h,w), zero-padded 3x3 unfold of depth,
+ * weighted sum, pixel shuffle).  f = 2**scale.
+ *   depth : [B,h,w];  mask : [B,9*f*f,h,w];  out : [B,f*h,f*w]
+ * ------------------------------------------------------------------------------------- */
+int mvd_convex_up_fwd(const float* depth, const float* mask, float* out, int B, int h, int w, int f,
+                      void* stream);
+/*   gdepth : [B,h,w] OVERWRITTEN;  gmask : [B,9*f*f,h,w] OVERWRITTEN */
+int mvd_convex_up_bwd(const float* depth, const float* mask, const float* gout, float* gdepth,
+                      float* gmask, int B, int h, int w, int f, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused multi-tensor Adam on a flat fp32 arena (torch.optim.Adam semantics, no amsgrad, no
+ * weight decay; replaces optimizer.step() movedepth/trainer.py:137-141, 272).
+ *   step_size = lr / (1 - beta1^t);  bias2 = sqrt(1 - beta2^t)
+ * ------------------------------------------------------------------------------------- */
+int mvd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                  float beta1, float beta2, float eps, float step_size, float bias2,
+                  float grad_scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOVEDEPTH_B200_H_ */

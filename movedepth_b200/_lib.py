@@ -1,0 +1,72 @@
+"""ctypes binding of libmovedepth_b200.so (the C ABI declared in include/movedepth_b200.h).
+
+There is no fallback: if the shared library is missing or a symbol of the header is not
+exported, importing the ops raises.  Build with `python -m movedepth_b200.build`.
+"""
+import ctypes
+import os
+import re
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB_PATH = os.path.join(HERE, "libmovedepth_b200.so")
+HEADER = os.path.join(ROOT, "include", "movedepth_b200.h")
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_F = ctypes.c_float
+_LL = ctypes.c_longlong
+
+# argument types per entry point, in header order
+SIGNATURES = {
+    "mvd_version": ([], _I),
+    "mvd_last_error_string": ([], ctypes.c_char_p),
+    "mvd_sm_count": ([], _I),
+    "mvd_costvol_grouped_fwd": ([_P] * 9 + [_I] * 8 + [_P], _I),
+    "mvd_costvol_grouped_bwd": ([_P] * 11 + [_I] * 8 + [_P], _I),
+    "mvd_costvol_full_fwd": ([_P] * 7 + [_I] * 5 + [_P], _I),
+    "mvd_costvol_full_bwd": ([_P] * 9 + [_I] * 5 + [_P], _I),
+    "mvd_regress_fwd": ([_P] * 7 + [_I] * 4 + [_P], _I),
+    "mvd_regress_bwd": ([_P] * 7 + [_I] * 4 + [_P], _I),
+    "mvd_convex_up_fwd": ([_P] * 3 + [_I] * 4 + [_P], _I),
+    "mvd_convex_up_bwd": ([_P] * 5 + [_I] * 4 + [_P], _I),
+    "mvd_photometric_fwd": ([_P] * 8 + [_I] * 3 + [_F, _I, _P], _I),
+    "mvd_photometric_bwd": ([_P] * 10 + [_I] * 3 + [_F, _I, _P], _I),
+    "mvd_adam_step": ([_P] * 4 + [_LL] + [_F] * 6 + [_P], _I),
+}
+
+
+def declared_symbols(header=HEADER):
+    """Every function the header declares (used by the symbol-export test)."""
+    text = re.sub(r"/\*.*?\*/", "", open(header).read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(mvd_[a-z0-9_]+)\s*\(", text)))
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "movedepth_b200: %s is missing -- the CUDA extension is required (no CPU/eager "
+                "fallback exists). Build it with `python -m movedepth_b200.build`." % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name in declared_symbols():
+            if not hasattr(handle, name):
+                raise RuntimeError("movedepth_b200: %s does not export %s" % (LIB_PATH, name))
+            fn = getattr(handle, name)
+            args, res = SIGNATURES[name]
+            fn.argtypes = args
+            fn.restype = res
+        if handle.mvd_version() != 1:
+            raise RuntimeError("movedepth_b200: ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().mvd_last_error_string()
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))

@@ -1,0 +1,80 @@
+// Library plumbing: version, thread-local error string, SM count, TMA descriptor encoding.
+#include "common.cuh"
+#include "../../include/movedepth_b200.h"
+
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace mvd {
+
+static thread_local char g_err[512] = "";
+static int g_sms = 0;
+
+char* err_buf() { return g_err; }
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "%s: %s", what, cudaGetErrorString(e));
+    return 0;
+}
+
+int sm_count() {
+    if (g_sms == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            g_sms = n;
+        else
+            return 148;
+    }
+    return g_sms;
+}
+
+cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// cuTensorMapEncodeTiled is a driver entry point; fetch it through the runtime so the library
+// does not link libcuda directly (it must load, and export its symbols, on a GPU-less host).
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    });
+    return fn;
+}
+
+int make_nhwc32_tensor_map(CUtensorMap* map, const float* base, int B, int h, int w, int box_w, int box_h) {
+    auto fn = encode_fn();
+    if (!fn) return fail(-2, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t gdim[4] = {32u, static_cast<cuuint64_t>(w), static_cast<cuuint64_t>(h), static_cast<cuuint64_t>(B)};
+    cuuint64_t gstr[3] = {128u, static_cast<cuuint64_t>(w) * 128u, static_cast<cuuint64_t>(w) * h * 128u};
+    cuuint32_t box[4] = {32u, static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1u};
+    cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
+    return 0;
+}
+
+}  // namespace mvd
+
+extern "C" {
+
+int mvd_version(void) { return MVD_ABI_VERSION; }
+const char* mvd_last_error_string(void) { return mvd::err_buf(); }
+int mvd_sm_count(void) { return mvd::sm_count(); }
+
+}

@@ -1,0 +1,681 @@
+// K1 / K1b -- fused homography-warp cost volume with group correlation (sm_100a).
+//
+// What the reference does (movedepth/layers.py:778-794 + movedepth/trainer.py:359): per batch item
+// repeat the source feature map D times, back-project D depth maps, project, grid_sample
+// (bilinear, zeros, align_corners=True), multiply by the reference feature, stack to
+// [B,D,C,h,w] (566 MB at B=6, D=96) and only then average channel pairs into G groups.
+//
+// What this kernel does instead: one persistent CTA per tile of R x 32 reference pixels.
+//   * the bounding box of all source positions the tile can touch (over every hypothesis) is
+//     found with a warp-shuffle min/max reduction of the projected segment end points;
+//   * that source box is staged once into shared memory by TMA (channels-last, 128B swizzle,
+//     out-of-bounds zero fill == padding_mode='zeros'), the reference tile likewise;
+//   * every thread owns one pixel and a contiguous chunk of hypotheses.  Because consecutive
+//     hypotheses fall into the same bilinear cell most of the time, the thread keeps the
+//     per-tap group correlations  P_tap[g] = 1/2 * sum_{c in group g} ref[c] * src_tap[c]  of its
+//     current cell in registers; a hypothesis then costs 64 FMAs and 16 coalesced stores, and
+//     shared memory is only read when the cell changes;
+//   * tiles whose box does not fit (degenerate poses) gather straight from global/L2.
+// The C-channel volume is never materialised: HBM traffic is ref + src + prior in, the grouped
+// volume out (4*B*h*w*(2C + 1 + D*G) bytes).
+//
+// Backward mirrors it: Q_tap[g] += w_tap * gout[g] is accumulated per cell in registers and
+// flushed with vector atomics when the cell changes.
+#include "common.cuh"
+#include "../../include/movedepth_b200.h"
+
+#include <limits.h>
+
+namespace mvd {
+
+constexpr int CV_C = 32;
+constexpr int CV_G = 16;
+constexpr int CV_TW = 32;   // tile width  (one lane per pixel column)
+constexpr int CV_R = 2;     // tile rows
+constexpr int CV_NCH = 4;   // hypothesis chunks per CTA
+constexpr int CV_WARPS = CV_R * CV_NCH;
+constexpr int CV_THREADS = 32 * CV_WARPS;
+constexpr int CV_BOX_W = 48;          // staged source box (pixels)
+constexpr int CV_BOX_H = CV_R + 8;
+constexpr int CV_MAXD = 1024;
+
+struct CvArgs {
+    const float* ref;
+    const float* src;
+    const float* prior;
+    const float* ratio;
+    const float* hyps;
+    const float* K;
+    const float* invK;
+    const float* T;
+    float* out;          // fwd
+    const float* gout;   // bwd
+    float* gref;
+    float* gsrc;
+    int B, h, w, D;
+    int layout;
+    int use_tma;
+    int tiles_x, tiles_y, num_tiles;
+    int DC;              // hypotheses per chunk
+};
+
+struct CvSmem {
+    // offsets into dynamic shared memory (base aligned to 1024 B for the 128B swizzle)
+    static constexpr int SRC_BYTES = CV_BOX_W * CV_BOX_H * 128;
+    static constexpr int REF_BYTES = CV_R * CV_TW * 128;
+    static constexpr int OFF_SRC = 0;
+    static constexpr int OFF_REF = (SRC_BYTES + 1023) / 1024 * 1024;
+    static constexpr int OFF_RATIO = OFF_REF + REF_BYTES;
+    static constexpr int OFF_GEO = OFF_RATIO + CV_MAXD * 4;
+    static constexpr int OFF_RED = OFF_GEO + 32 * 4;
+    static constexpr int OFF_BAR = OFF_RED + 2 * CV_WARPS * 4 * 4;
+    static constexpr int TOTAL = OFF_BAR + 16;
+    static constexpr int ALLOC = TOTAL + 1024;   // slack for manual 1024 B alignment
+};
+
+struct PixelCtx {
+    float mrx, mry, mrz, tx, ty, tz;   // p(depth) = depth * mr + t
+    int b, x, y, d0, d1;
+    bool active;
+    bool boxed;         // source box staged in shared memory for this tile
+    int ox, oy;         // box origin in source pixels
+};
+
+__device__ __forceinline__ void project_uv(const PixelCtx& c, float depth, float& u, float& v, float& pz) {
+    pz = fmaf(depth, c.mrz, c.tz) + 1e-7f;
+    const float inv = __frcp_rn(pz);
+    u = fmaf(depth, c.mrx, c.tx) * inv;
+    v = fmaf(depth, c.mry, c.ty) * inv;
+}
+
+__device__ __forceinline__ float4 lds128(const unsigned char* base, int pix, int j) {
+    return *reinterpret_cast<const float4*>(base + pix * 128 + ((j ^ (pix & 7)) << 4));
+}
+
+// Fetch channels [4j,4j+4) and [16+4j,16+4j+4) of source pixel (px,py); zero outside the image.
+__device__ __forceinline__ void fetch_tap(const CvArgs& a, const PixelCtx& c, const unsigned char* sbox, bool in_box,
+                                          int rel_pix, int px, int py, int j, float4& lo, float4& hi) {
+    if (in_box) {
+        lo = lds128(sbox, rel_pix, j);
+        hi = lds128(sbox, rel_pix, j + 4);
+    } else if (px >= 0 && px < a.w && py >= 0 && py < a.h) {
+        const float4* g = reinterpret_cast<const float4*>(a.src + (static_cast<size_t>(c.b * a.h + py) * a.w + px) * CV_C);
+        lo = __ldg(g + j);
+        hi = __ldg(g + j + 4);
+    } else {
+        lo = make_float4(0.f, 0.f, 0.f, 0.f);
+        hi = lo;
+    }
+}
+
+// Per-tile prologue shared by forward and backward.  Returns the pixel context; leaves the
+// reference tile (and, when it fits, the source box) in shared memory.
+__device__ __forceinline__ void tile_prologue(const CvArgs& a, const CUtensorMap* map_src, const CUtensorMap* map_ref,
+                                              unsigned char* smem, int tile, int iter, uint32_t& phase, PixelCtx& c) {
+    float* ratio_s = reinterpret_cast<float*>(smem + CvSmem::OFF_RATIO);
+    float* geo = reinterpret_cast<float*>(smem + CvSmem::OFF_GEO);
+    float* red = reinterpret_cast<float*>(smem + CvSmem::OFF_RED) + (iter & 1) * CV_WARPS * 4;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + CvSmem::OFF_BAR);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per_b = a.tiles_x * a.tiles_y;
+    const int b = tile / per_b;
+    const int trem = tile - b * per_b;
+    const int tyi = trem / a.tiles_x, txi = trem - tyi * a.tiles_x;
+
+    __syncthreads();   // everyone is done with the previous tile's shared data
+    if (tid < 12) {    // P = (K @ T)[:3, :]   (movedepth/layers.py:609)
+        const int i = tid >> 2, j = tid & 3;
+        const float* Kb = a.K + b * 16;
+        const float* Tb = a.T + b * 16;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s = fmaf(Kb[i * 4 + k], Tb[k * 4 + j], s);
+        geo[tid] = s;
+    } else if (tid < 21) {   // inv_K[:3,:3]   (movedepth/layers.py:582)
+        const int q = tid - 12;
+        geo[12 + q] = a.invK[b * 16 + (q / 3) * 4 + (q % 3)];
+    }
+    if (a.ratio != nullptr)
+        for (int d = tid; d < a.D; d += CV_THREADS) ratio_s[d] = a.ratio[b * a.D + d];
+    __syncthreads();
+
+    const int row = warp % CV_R, chunk = warp / CV_R;
+    c.b = b;
+    c.x = txi * CV_TW + lane;
+    c.y = tyi * CV_R + row;
+    c.d0 = chunk * a.DC;
+    c.d1 = min(a.D, c.d0 + a.DC);
+    c.active = (c.x < a.w) && (c.y < a.h) && (c.d0 < c.d1);
+    {
+        const float xf = static_cast<float>(c.x), yf = static_cast<float>(c.y);
+        const float rx = fmaf(geo[12], xf, fmaf(geo[13], yf, geo[14]));
+        const float ry = fmaf(geo[15], xf, fmaf(geo[16], yf, geo[17]));
+        const float rz = fmaf(geo[18], xf, fmaf(geo[19], yf, geo[20]));
+        c.mrx = fmaf(geo[0], rx, fmaf(geo[1], ry, geo[2] * rz));
+        c.mry = fmaf(geo[4], rx, fmaf(geo[5], ry, geo[6] * rz));
+        c.mrz = fmaf(geo[8], rx, fmaf(geo[9], ry, geo[10] * rz));
+        c.tx = geo[3];
+        c.ty = geo[7];
+        c.tz = geo[11];
+    }
+
+    // ---- bounding box of the source footprint: the projection of a depth interval is the
+    // segment between the projections of its end points as long as z stays positive.
+    float lo_u = 3.0e38f, hi_u = -3.0e38f, lo_v = 3.0e38f, hi_v = -3.0e38f;
+    int bad = 0;
+    if (c.active && a.use_tma) {
+        float dmin, dmax;
+        if (a.hyps != nullptr) {
+            dmin = 3.0e38f;
+            dmax = -3.0e38f;
+            const float* hp = a.hyps + (static_cast<size_t>(b) * a.D * a.h + c.y) * a.w + c.x;
+            for (int d = c.d0; d < c.d1; ++d) {
+                const float dv = __ldg(hp + static_cast<size_t>(d) * a.h * a.w);
+                dmin = fminf(dmin, dv);
+                dmax = fmaxf(dmax, dv);
+            }
+        } else {
+            const float pr = __ldg(a.prior + static_cast<size_t>(b * a.h + c.y) * a.w + c.x);
+            const float d_a = pr * ratio_s[c.d0], d_b = pr * ratio_s[c.d1 - 1];
+            dmin = fminf(d_a, d_b);
+            dmax = fmaxf(d_a, d_b);
+        }
+        float u0, v0, z0, u1, v1, z1;
+        project_uv(c, dmin, u0, v0, z0);
+        project_uv(c, dmax, u1, v1, z1);
+        if (!(z0 > 1e-6f) || !(z1 > 1e-6f) || !(fabsf(u0) < 1e8f) || !(fabsf(u1) < 1e8f) || !(fabsf(v0) < 1e8f) ||
+            !(fabsf(v1) < 1e8f)) {
+            bad = 1;
+        } else {
+            const float wf = static_cast<float>(a.w), hf = static_cast<float>(a.h);
+            const float mnu = fminf(u0, u1), mxu = fmaxf(u0, u1), mnv = fminf(v0, v1), mxv = fmaxf(v0, v1);
+            if (mxu > -1.f && mnu < wf && mxv > -1.f && mnv < hf) {   // segment touches the image
+                lo_u = fmaxf(mnu, -1.f);
+                hi_u = fminf(mxu, wf);
+                lo_v = fmaxf(mnv, -1.f);
+                hi_v = fminf(mxv, hf);
+            }
+        }
+    }
+    lo_u = warp_min(lo_u);
+    hi_u = warp_max(hi_u);
+    lo_v = warp_min(lo_v);
+    hi_v = warp_max(hi_v);
+    if (lane == 0) {
+        red[warp * 4 + 0] = lo_u;
+        red[warp * 4 + 1] = hi_u;
+        red[warp * 4 + 2] = lo_v;
+        red[warp * 4 + 3] = hi_v;
+    }
+    const int any_bad = __syncthreads_or(bad);
+#pragma unroll
+    for (int wi = 0; wi < CV_WARPS; ++wi) {
+        lo_u = fminf(lo_u, red[wi * 4 + 0]);
+        hi_u = fmaxf(hi_u, red[wi * 4 + 1]);
+        lo_v = fminf(lo_v, red[wi * 4 + 2]);
+        hi_v = fmaxf(hi_v, red[wi * 4 + 3]);
+    }
+    c.boxed = false;
+    c.ox = 0;
+    c.oy = 0;
+    if (a.use_tma && !any_bad) {
+        if (hi_u < lo_u) {   // nothing of this tile lands inside the image: empty box is fine
+            c.boxed = true;
+        } else {
+            const int ix0 = static_cast<int>(floorf(lo_u)), ix1 = min(static_cast<int>(floorf(hi_u)), a.w - 1);
+            const int iy0 = static_cast<int>(floorf(lo_v)), iy1 = min(static_cast<int>(floorf(hi_v)), a.h - 1);
+            c.ox = ix0 - 1;
+            c.oy = iy0 - 1;
+            c.boxed = (ix1 + 2 - c.ox + 1 <= CV_BOX_W) && (iy1 + 2 - c.oy + 1 <= CV_BOX_H);
+        }
+    }
+    if (tid == 0) {
+        const uint32_t bytes = CvSmem::REF_BYTES + (c.boxed ? CvSmem::SRC_BYTES : 0);
+        mbar_expect_tx(bar, bytes);
+        tma_load_4d(smem + CvSmem::OFF_REF, map_ref, bar, 0, txi * CV_TW, tyi * CV_R, b);
+        if (c.boxed) tma_load_4d(smem + CvSmem::OFF_SRC, map_src, bar, 0, c.ox, c.oy, b);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+}
+
+__device__ __forceinline__ void load_half_ref(const unsigned char* smem, int warp, int lane, float (&rh)[CV_C]) {
+    const unsigned char* rbox = smem + CvSmem::OFF_REF;
+    const int pr = (warp % CV_R) * CV_TW + lane;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 v = lds128(rbox, pr, j);
+        rh[4 * j + 0] = 0.5f * v.x;
+        rh[4 * j + 1] = 0.5f * v.y;
+        rh[4 * j + 2] = 0.5f * v.z;
+        rh[4 * j + 3] = 0.5f * v.w;
+    }
+}
+
+struct Bilinear {
+    float w00, w01, w10, w11;
+    int ix, iy;
+    bool ok;
+};
+
+// ATen grid_sampler_2d (bilinear, align_corners=True, zeros): nw=(x1-u)(y1-v), ne=(u-x0)(y1-v), ...
+__device__ __forceinline__ Bilinear bilinear_at(const CvArgs& a, float u, float v) {
+    Bilinear s;
+    s.ok = (u > -1.f) && (u < static_cast<float>(a.w)) && (v > -1.f) && (v < static_cast<float>(a.h));
+    s.w00 = s.w01 = s.w10 = s.w11 = 0.f;
+    s.ix = 0;
+    s.iy = 0;
+    if (s.ok) {
+        const float x0 = floorf(u), y0 = floorf(v);
+        const float fx1 = u - x0, fx0 = (x0 + 1.f) - u;
+        const float fy1 = v - y0, fy0 = (y0 + 1.f) - v;
+        s.w00 = fx0 * fy0;
+        s.w01 = fx1 * fy0;
+        s.w10 = fx0 * fy1;
+        s.w11 = fx1 * fy1;
+        s.ix = static_cast<int>(x0);
+        s.iy = static_cast<int>(y0);
+    }
+    return s;
+}
+
+__device__ __forceinline__ bool cell_in_box(const PixelCtx& c, int ix, int iy, int& rel) {
+    const int rx = ix - c.ox, ry = iy - c.oy;
+    rel = ry * CV_BOX_W + rx;
+    return c.boxed && rx >= 0 && rx <= CV_BOX_W - 2 && ry >= 0 && ry <= CV_BOX_H - 2;
+}
+
+// ------------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(CV_THREADS, 2)
+costvol_grouped_fwd_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_ref,
+                           const CvArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + CvSmem::OFF_BAR);
+    const float* ratio_s = reinterpret_cast<const float*>(smem + CvSmem::OFF_RATIO);
+    const unsigned char* sbox = smem + CvSmem::OFF_SRC;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        tma_prefetch_desc(&map_src);
+        tma_prefetch_desc(&map_ref);
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    uint32_t phase = 0;
+    const size_t hw = static_cast<size_t>(a.h) * a.w;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++iter) {
+        PixelCtx c;
+        tile_prologue(a, &map_src, &map_ref, smem, tile, iter, phase, c);
+        if (!c.active) continue;
+
+        float rh[CV_C];
+        load_half_ref(smem, warp, lane, rh);
+        float P[4][CV_G];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int g = 0; g < CV_G; ++g) P[t][g] = 0.f;
+        int cx = INT_MIN, cy = INT_MIN;
+
+        const size_t pix = static_cast<size_t>(c.y) * a.w + c.x;
+        const float prior_v = (a.hyps == nullptr) ? __ldg(a.prior + c.b * hw + pix) : 0.f;
+        const float* hp = (a.hyps != nullptr) ? a.hyps + static_cast<size_t>(c.b) * a.D * hw + pix : nullptr;
+
+        for (int d = c.d0; d < c.d1; ++d) {
+            const float depth = hp ? __ldg(hp + d * hw) : prior_v * ratio_s[d];
+            float u, v, pz;
+            project_uv(c, depth, u, v, pz);
+            const Bilinear s = bilinear_at(a, u, v);
+            if (s.ok && (s.ix != cx || s.iy != cy)) {
+                cx = s.ix;
+                cy = s.iy;
+                int rel;
+                const bool in_box = cell_in_box(c, cx, cy, rel);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int px = cx + (t & 1), py = cy + (t >> 1);
+                    const int rp = rel + (t & 1) + (t >> 1) * CV_BOX_W;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float4 lo, hi;
+                        fetch_tap(a, c, sbox, in_box, rp, px, py, j, lo, hi);
+                        P[t][4 * j + 0] = fmaf(rh[4 * j + 0], lo.x, rh[16 + 4 * j + 0] * hi.x);
+                        P[t][4 * j + 1] = fmaf(rh[4 * j + 1], lo.y, rh[16 + 4 * j + 1] * hi.y);
+                        P[t][4 * j + 2] = fmaf(rh[4 * j + 2], lo.z, rh[16 + 4 * j + 2] * hi.z);
+                        P[t][4 * j + 3] = fmaf(rh[4 * j + 3], lo.w, rh[16 + 4 * j + 3] * hi.w);
+                    }
+                }
+            }
+            float o[CV_G];
+#pragma unroll
+            for (int g = 0; g < CV_G; ++g)
+                o[g] = fmaf(s.w11, P[3][g], fmaf(s.w10, P[2][g], fmaf(s.w01, P[1][g], s.w00 * P[0][g])));
+            if (a.layout == MVD_LAYOUT_BGDHW) {
+                float* op = a.out + (static_cast<size_t>(c.b) * CV_G * a.D + d) * hw + pix;
+                const size_t gs = static_cast<size_t>(a.D) * hw;
+#pragma unroll
+                for (int g = 0; g < CV_G; ++g) op[g * gs] = o[g];
+            } else {
+                float4* op = reinterpret_cast<float4*>(a.out + ((static_cast<size_t>(c.b) * a.D + d) * hw + pix) * CV_G);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) op[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ backward
+__device__ __forceinline__ void flush_cell(const CvArgs& a, const PixelCtx& c, const unsigned char* sbox,
+                                           const float (&rh)[CV_C], float (&Q)[4][CV_G], float (&gr)[CV_C], int cx,
+                                           int cy) {
+    int rel;
+    const bool in_box = cell_in_box(c, cx, cy, rel);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int px = cx + (t & 1), py = cy + (t >> 1);
+        const int rp = rel + (t & 1) + (t >> 1) * CV_BOX_W;
+        if (px >= 0 && px < a.w && py >= 0 && py < a.h) {
+            float4* gs = reinterpret_cast<float4*>(a.gsrc + (static_cast<size_t>(c.b * a.h + py) * a.w + px) * CV_C);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float4 lo, hi;
+                fetch_tap(a, c, sbox, in_box, rp, px, py, j, lo, hi);
+                const float q0 = Q[t][4 * j + 0], q1 = Q[t][4 * j + 1], q2 = Q[t][4 * j + 2], q3 = Q[t][4 * j + 3];
+                gr[4 * j + 0] = fmaf(q0, lo.x, gr[4 * j + 0]);
+                gr[4 * j + 1] = fmaf(q1, lo.y, gr[4 * j + 1]);
+                gr[4 * j + 2] = fmaf(q2, lo.z, gr[4 * j + 2]);
+                gr[4 * j + 3] = fmaf(q3, lo.w, gr[4 * j + 3]);
+                gr[16 + 4 * j + 0] = fmaf(q0, hi.x, gr[16 + 4 * j + 0]);
+                gr[16 + 4 * j + 1] = fmaf(q1, hi.y, gr[16 + 4 * j + 1]);
+                gr[16 + 4 * j + 2] = fmaf(q2, hi.z, gr[16 + 4 * j + 2]);
+                gr[16 + 4 * j + 3] = fmaf(q3, hi.w, gr[16 + 4 * j + 3]);
+                atomicAdd(gs + j, make_float4(q0 * rh[4 * j + 0], q1 * rh[4 * j + 1], q2 * rh[4 * j + 2], q3 * rh[4 * j + 3]));
+                atomicAdd(gs + j + 4, make_float4(q0 * rh[16 + 4 * j + 0], q1 * rh[16 + 4 * j + 1],
+                                                  q2 * rh[16 + 4 * j + 2], q3 * rh[16 + 4 * j + 3]));
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < CV_G; ++g) Q[t][g] = 0.f;
+    }
+}
+
+__global__ void __launch_bounds__(CV_THREADS, 1)
+costvol_grouped_bwd_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_ref,
+                           const CvArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + CvSmem::OFF_BAR);
+    const float* ratio_s = reinterpret_cast<const float*>(smem + CvSmem::OFF_RATIO);
+    const unsigned char* sbox = smem + CvSmem::OFF_SRC;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        tma_prefetch_desc(&map_src);
+        tma_prefetch_desc(&map_ref);
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    uint32_t phase = 0;
+    const size_t hw = static_cast<size_t>(a.h) * a.w;
+    int iter = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++iter) {
+        PixelCtx c;
+        tile_prologue(a, &map_src, &map_ref, smem, tile, iter, phase, c);
+        if (!c.active) continue;
+
+        float rh[CV_C], gr[CV_C];
+        load_half_ref(smem, warp, lane, rh);
+#pragma unroll
+        for (int k = 0; k < CV_C; ++k) gr[k] = 0.f;
+        float Q[4][CV_G];
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+#pragma unroll
+            for (int g = 0; g < CV_G; ++g) Q[t][g] = 0.f;
+        int cx = INT_MIN, cy = INT_MIN;
+
+        const size_t pix = static_cast<size_t>(c.y) * a.w + c.x;
+        const float prior_v = (a.hyps == nullptr) ? __ldg(a.prior + c.b * hw + pix) : 0.f;
+        const float* hp = (a.hyps != nullptr) ? a.hyps + static_cast<size_t>(c.b) * a.D * hw + pix : nullptr;
+
+        for (int d = c.d0; d < c.d1; ++d) {
+            float go[CV_G];
+            if (a.layout == MVD_LAYOUT_BGDHW) {
+                const float* gp = a.gout + (static_cast<size_t>(c.b) * CV_G * a.D + d) * hw + pix;
+                const size_t gs = static_cast<size_t>(a.D) * hw;
+#pragma unroll
+                for (int g = 0; g < CV_G; ++g) go[g] = __ldg(gp + g * gs);
+            } else {
+                const float4* gp = reinterpret_cast<const float4*>(a.gout + ((static_cast<size_t>(c.b) * a.D + d) * hw + pix) * CV_G);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 t4 = __ldg(gp + q);
+                    go[4 * q] = t4.x;
+                    go[4 * q + 1] = t4.y;
+                    go[4 * q + 2] = t4.z;
+                    go[4 * q + 3] = t4.w;
+                }
+            }
+            const float depth = hp ? __ldg(hp + d * hw) : prior_v * ratio_s[d];
+            float u, v, pz;
+            project_uv(c, depth, u, v, pz);
+            const Bilinear s = bilinear_at(a, u, v);
+            if (!s.ok) continue;
+            if (s.ix != cx || s.iy != cy) {
+                if (cx != INT_MIN) flush_cell(a, c, sbox, rh, Q, gr, cx, cy);
+                cx = s.ix;
+                cy = s.iy;
+            }
+#pragma unroll
+            for (int g = 0; g < CV_G; ++g) {
+                Q[0][g] = fmaf(s.w00, go[g], Q[0][g]);
+                Q[1][g] = fmaf(s.w01, go[g], Q[1][g]);
+                Q[2][g] = fmaf(s.w10, go[g], Q[2][g]);
+                Q[3][g] = fmaf(s.w11, go[g], Q[3][g]);
+            }
+        }
+        if (cx != INT_MIN) flush_cell(a, c, sbox, rh, Q, gr, cx, cy);
+        // d out / d ref_c = 1/2 * sum_t w_t * src_tap_c ; chunks of the same pixel meet in global memory
+        float4* grp = reinterpret_cast<float4*>(a.gref + (c.b * hw + pix) * CV_C);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            atomicAdd(grp + j, make_float4(0.5f * gr[4 * j], 0.5f * gr[4 * j + 1], 0.5f * gr[4 * j + 2], 0.5f * gr[4 * j + 3]));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host
+static int costvol_grouped_launch(bool bwd, CvArgs a, int C, int G, int flags, cudaStream_t st) {
+    MVD_REQUIRE(C == CV_C && G == CV_G, "grouped cost volume is built for C=32, G=16 (got C=%d, G=%d)", C, G);
+    MVD_REQUIRE(a.B > 0 && a.h > 0 && a.w > 0 && a.D > 0, "empty shape B=%d h=%d w=%d D=%d", a.B, a.h, a.w, a.D);
+    MVD_REQUIRE(a.D <= CV_MAXD, "D=%d exceeds the supported maximum %d", a.D, CV_MAXD);
+    MVD_REQUIRE(a.layout == MVD_LAYOUT_BGDHW || a.layout == MVD_LAYOUT_BDHWG, "unknown out_layout %d", a.layout);
+    MVD_REQUIRE(a.hyps != nullptr || (a.prior != nullptr && a.ratio != nullptr), "need hyps or (prior, ratio)");
+    MVD_REQUIRE(aligned16(a.ref) && aligned16(a.src) && aligned16(a.out) && aligned16(a.gout) && aligned16(a.gref) &&
+                    aligned16(a.gsrc),
+                "feature / volume pointers must be 16-byte aligned");
+    a.use_tma = (flags & MVD_FLAG_NO_TMA) ? 0 : 1;
+    a.tiles_x = (a.w + CV_TW - 1) / CV_TW;
+    a.tiles_y = (a.h + CV_R - 1) / CV_R;
+    a.num_tiles = a.tiles_x * a.tiles_y * a.B;
+    a.DC = (a.D + CV_NCH - 1) / CV_NCH;
+
+    CUtensorMap map_src, map_ref;
+    int rc = make_nhwc32_tensor_map(&map_src, a.src, a.B, a.h, a.w, CV_BOX_W, CV_BOX_H);
+    if (rc) return rc;
+    rc = make_nhwc32_tensor_map(&map_ref, a.ref, a.B, a.h, a.w, CV_TW, CV_R);
+    if (rc) return rc;
+
+    const int smem = CvSmem::ALLOC;
+    const int per_sm = bwd ? 1 : 2;
+    const int grid = min(a.num_tiles, sm_count() * per_sm);
+    if (bwd) {
+        cudaError_t e = cudaMemsetAsync(a.gref, 0, sizeof(float) * a.B * a.h * a.w * CV_C, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(a.gsrc, 0, sizeof(float) * a.B * a.h * a.w * CV_C, st);
+        if (e != cudaSuccess) return fail(static_cast<int>(e), "costvol bwd memset: %s", cudaGetErrorString(e));
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(costvol_grouped_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            attr_done = true;
+        }
+        costvol_grouped_bwd_kernel<<<grid, CV_THREADS, smem, st>>>(map_src, map_ref, a);
+        return check_launch("costvol_grouped_bwd");
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(costvol_grouped_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        attr_done = true;
+    }
+    costvol_grouped_fwd_kernel<<<grid, CV_THREADS, smem, st>>>(map_src, map_ref, a);
+    return check_launch("costvol_grouped_fwd");
+}
+
+// ---- reference-layout volume [B,D,C,h,w] (public generate_costvol API; any C, NCHW) ---------
+struct FullGeom {
+    float mrx, mry, mrz, tx, ty, tz;
+};
+__device__ __forceinline__ FullGeom full_geom(const float* K, const float* invK, const float* T, int b, int x, int y) {
+    const float* Kb = K + b * 16;
+    const float* Tb = T + b * 16;
+    const float* Ib = invK + b * 16;
+    float P[12];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s = fmaf(Kb[i * 4 + k], Tb[k * 4 + j], s);
+            P[i * 4 + j] = s;
+        }
+    const float xf = static_cast<float>(x), yf = static_cast<float>(y);
+    const float rx = fmaf(Ib[0], xf, fmaf(Ib[1], yf, Ib[2]));
+    const float ry = fmaf(Ib[4], xf, fmaf(Ib[5], yf, Ib[6]));
+    const float rz = fmaf(Ib[8], xf, fmaf(Ib[9], yf, Ib[10]));
+    FullGeom g;
+    g.mrx = fmaf(P[0], rx, fmaf(P[1], ry, P[2] * rz));
+    g.mry = fmaf(P[4], rx, fmaf(P[5], ry, P[6] * rz));
+    g.mrz = fmaf(P[8], rx, fmaf(P[9], ry, P[10] * rz));
+    g.tx = P[3];
+    g.ty = P[7];
+    g.tz = P[11];
+    return g;
+}
+
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+costvol_full_kernel(const float* __restrict__ ref, const float* __restrict__ src, const float* __restrict__ hyps,
+                    const float* __restrict__ K, const float* __restrict__ invK, const float* __restrict__ T,
+                    float* __restrict__ out, const float* __restrict__ gout, float* __restrict__ gref,
+                    float* __restrict__ gsrc, int B, int C, int h, int w, int D) {
+    const size_t hw = static_cast<size_t>(h) * w;
+    const size_t total = static_cast<size_t>(B) * D * hw;
+    for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(idx % w);
+        const int y = static_cast<int>((idx / w) % h);
+        const int d = static_cast<int>((idx / hw) % D);
+        const int b = static_cast<int>(idx / (hw * D));
+        const FullGeom g = full_geom(K, invK, T, b, x, y);
+        const float depth = __ldg(hyps + idx);
+        const float pz = fmaf(depth, g.mrz, g.tz) + 1e-7f;
+        const float inv = __frcp_rn(pz);
+        const float u = fmaf(depth, g.mrx, g.tx) * inv, v = fmaf(depth, g.mry, g.ty) * inv;
+        const bool ok = (u > -1.f) && (u < static_cast<float>(w)) && (v > -1.f) && (v < static_cast<float>(h));
+        float wt[4] = {0.f, 0.f, 0.f, 0.f};
+        int off[4] = {0, 0, 0, 0};
+        bool inb[4] = {false, false, false, false};
+        if (ok) {
+            const float x0 = floorf(u), y0 = floorf(v);
+            const float fx1 = u - x0, fx0 = (x0 + 1.f) - u, fy1 = v - y0, fy0 = (y0 + 1.f) - v;
+            wt[0] = fx0 * fy0;
+            wt[1] = fx1 * fy0;
+            wt[2] = fx0 * fy1;
+            wt[3] = fx1 * fy1;
+            const int ix = static_cast<int>(x0), iy = static_cast<int>(y0);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int px = ix + (t & 1), py = iy + (t >> 1);
+                inb[t] = px >= 0 && px < w && py >= 0 && py < h;
+                off[t] = py * w + px;
+            }
+        }
+        const size_t pix = static_cast<size_t>(y) * w + x;
+        for (int c = 0; c < C; ++c) {
+            const float* sp = src + (static_cast<size_t>(b) * C + c) * hw;
+            float tap[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) tap[t] = inb[t] ? __ldg(sp + off[t]) : 0.f;
+            const float warped = fmaf(tap[3], wt[3], fmaf(tap[2], wt[2], fmaf(tap[1], wt[1], tap[0] * wt[0])));
+            const size_t rix = (static_cast<size_t>(b) * C + c) * hw + pix;
+            const size_t oix = ((static_cast<size_t>(b) * D + d) * C + c) * hw + pix;
+            if (!BWD) {
+                out[oix] = warped * __ldg(ref + rix);
+            } else {
+                const float go = __ldg(gout + oix);
+                atomicAdd(gref + rix, go * warped);
+                const float gw = go * __ldg(ref + rix);
+                float* gp = gsrc + (static_cast<size_t>(b) * C + c) * hw;
+#pragma unroll
+                for (int t = 0; t < 4; ++t)
+                    if (inb[t]) atomicAdd(gp + off[t], gw * wt[t]);
+            }
+        }
+    }
+}
+
+}  // namespace mvd
+
+extern "C" {
+
+int mvd_costvol_grouped_fwd(const float* ref, const float* src, const float* prior, const float* ratio,
+                            const float* hyps, const float* K, const float* invK, const float* T, float* out, int B,
+                            int C, int G, int h, int w, int D, int out_layout, int flags, void* stream) {
+    MVD_REQUIRE(ref && src && K && invK && T && out, "null pointer argument");
+    mvd::CvArgs a{};
+    a.ref = ref; a.src = src; a.prior = prior; a.ratio = ratio; a.hyps = hyps;
+    a.K = K; a.invK = invK; a.T = T; a.out = out;
+    a.B = B; a.h = h; a.w = w; a.D = D; a.layout = out_layout;
+    return mvd::costvol_grouped_launch(false, a, C, G, flags, mvd::as_stream(stream));
+}
+
+int mvd_costvol_grouped_bwd(const float* gout, const float* ref, const float* src, const float* prior,
+                            const float* ratio, const float* hyps, const float* K, const float* invK, const float* T,
+                            float* gref, float* gsrc, int B, int C, int G, int h, int w, int D, int out_layout,
+                            int flags, void* stream) {
+    MVD_REQUIRE(gout && ref && src && K && invK && T && gref && gsrc, "null pointer argument");
+    mvd::CvArgs a{};
+    a.ref = ref; a.src = src; a.prior = prior; a.ratio = ratio; a.hyps = hyps;
+    a.K = K; a.invK = invK; a.T = T; a.gout = gout; a.gref = gref; a.gsrc = gsrc;
+    a.B = B; a.h = h; a.w = w; a.D = D; a.layout = out_layout;
+    return mvd::costvol_grouped_launch(true, a, C, G, flags, mvd::as_stream(stream));
+}
+
+int mvd_costvol_full_fwd(const float* ref, const float* src, const float* hyps, const float* K, const float* invK,
+                         const float* T, float* out, int B, int C, int h, int w, int D, void* stream) {
+    MVD_REQUIRE(ref && src && hyps && K && invK && T && out, "null pointer argument");
+    MVD_REQUIRE(B > 0 && C > 0 && h > 0 && w > 0 && D > 0, "empty shape");
+    const size_t total = static_cast<size_t>(B) * D * h * w;
+    const int grid = static_cast<int>(min(static_cast<size_t>(mvd::sm_count()) * 8, (total + 255) / 256));
+    mvd::costvol_full_kernel<false><<<grid, 256, 0, mvd::as_stream(stream)>>>(ref, src, hyps, K, invK, T, out, nullptr,
+                                                                               nullptr, nullptr, B, C, h, w, D);
+    return mvd::check_launch("costvol_full_fwd");
+}
+
+int mvd_costvol_full_bwd(const float* gout, const float* ref, const float* src, const float* hyps, const float* K,
+                         const float* invK, const float* T, float* gref, float* gsrc, int B, int C, int h, int w, int D,
+                         void* stream) {
+    MVD_REQUIRE(gout && ref && src && hyps && K && invK && T && gref && gsrc, "null pointer argument");
+    MVD_REQUIRE(B > 0 && C > 0 && h > 0 && w > 0 && D > 0, "empty shape");
+    cudaStream_t st = mvd::as_stream(stream);
+    const size_t fbytes = sizeof(float) * B * C * h * w;
+    cudaError_t e = cudaMemsetAsync(gref, 0, fbytes, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(gsrc, 0, fbytes, st);
+    if (e != cudaSuccess) return mvd::fail(static_cast<int>(e), "costvol_full_bwd memset: %s", cudaGetErrorString(e));
+    const size_t total = static_cast<size_t>(B) * D * h * w;
+    const int grid = static_cast<int>(min(static_cast<size_t>(mvd::sm_count()) * 8, (total + 255) / 256));
+    mvd::costvol_full_kernel<true><<<grid, 256, 0, st>>>(ref, src, hyps, K, invK, T, nullptr, gout, gref, gsrc, B, C, h,
+                                                          w, D);
+    return mvd::check_launch("costvol_full_bwd");
+}
+
+}

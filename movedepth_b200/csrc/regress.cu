@@ -1,0 +1,260 @@
+// K3 -- softmax over the depth axis + entropy + local-max depth regression, and K4 -- convex
+// upsampling.  Both are small HBM-bound passes; one thread per low-resolution pixel keeps every
+// access coalesced along x (the depth/mask-channel stride is h*w).
+#include "common.cuh"
+#include "../../include/movedepth_b200.h"
+
+namespace mvd {
+
+// ------------------------------------------------------------------------------------------ K3
+// movedepth/trainer.py:367 (softmax), layers.py:862-863 (entropy), layers.py:796-812 (localmax)
+__global__ void __launch_bounds__(128)
+regress_fwd_kernel(const float* __restrict__ logits, const float* __restrict__ inv_a, const float* __restrict__ inv_b,
+                   float* __restrict__ prob, float* __restrict__ entropy, float* __restrict__ depth,
+                   int* __restrict__ amax, int B, int D, int hw, int radius) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * hw) return;
+    const int b = idx / hw, p = idx - b * hw;
+    const float* lp = logits + static_cast<size_t>(b) * D * hw + p;
+    float m = -INFINITY;
+    int im = 0;
+    for (int d = 0; d < D; ++d) {
+        const float v = __ldg(lp + static_cast<size_t>(d) * hw);
+        if (v > m) {
+            m = v;
+            im = d;
+        }
+    }
+    float s = 0.f;
+    for (int d = 0; d < D; ++d) s += expf(__ldg(lp + static_cast<size_t>(d) * hw) - m);
+    const float inv_s = 1.f / s;
+    float ent = 0.f;
+    float* pp = prob ? prob + static_cast<size_t>(b) * D * hw + p : nullptr;
+    for (int d = 0; d < D; ++d) {
+        const float q = expf(__ldg(lp + static_cast<size_t>(d) * hw) - m) * inv_s;
+        if (pp) pp[static_cast<size_t>(d) * hw] = q;
+        ent -= q * logf(fminf(fmaxf(q, 1e-9f), 1.f));
+    }
+    float num = 0.f, den = 1e-6f;
+    for (int k = -radius; k <= radius; ++k) {
+        const int j = min(max(im + k, 0), D - 1);
+        const float q = expf(__ldg(lp + static_cast<size_t>(j) * hw) - m) * inv_s;
+        num += static_cast<float>(j) * q;
+        den += q;
+    }
+    const float n = (num / den) / static_cast<float>(D - 1);
+    const float a = __ldg(inv_a + idx), bv = __ldg(inv_b + idx);
+    entropy[idx] = ent;
+    depth[idx] = 1.f / (a + n * (bv - a));
+    amax[idx] = im;
+}
+
+__global__ void __launch_bounds__(128)
+regress_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ inv_a, const float* __restrict__ inv_b,
+                   const int* __restrict__ amax, const float* __restrict__ g_entropy,
+                   const float* __restrict__ g_depth, float* __restrict__ glogits, int B, int D, int hw, int radius) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * hw) return;
+    const int b = idx / hw, p = idx - b * hw;
+    const float* lp = logits + static_cast<size_t>(b) * D * hw + p;
+    float m = -INFINITY;
+    for (int d = 0; d < D; ++d) m = fmaxf(m, __ldg(lp + static_cast<size_t>(d) * hw));
+    float s = 0.f;
+    for (int d = 0; d < D; ++d) s += expf(__ldg(lp + static_cast<size_t>(d) * hw) - m);
+    const float inv_s = 1.f / s;
+
+    // local soft-argmax pieces (window indices are constants of the backward, like autograd)
+    const int im = amax[idx];
+    float num = 0.f, den = 1e-6f;
+    for (int k = -radius; k <= radius; ++k) {
+        const int j = min(max(im + k, 0), D - 1);
+        const float q = expf(__ldg(lp + static_cast<size_t>(j) * hw) - m) * inv_s;
+        num += static_cast<float>(j) * q;
+        den += q;
+    }
+    const float soft = num / den;
+    const float a = __ldg(inv_a + idx), bv = __ldg(inv_b + idx);
+    const float dep = 1.f / (a + (soft / static_cast<float>(D - 1)) * (bv - a));
+    const float gd = g_depth ? __ldg(g_depth + idx) : 0.f;
+    const float ge = g_entropy ? __ldg(g_entropy + idx) : 0.f;
+    const float gsoft = -gd * dep * dep * (bv - a) / static_cast<float>(D - 1);
+    const int lo = im - radius, hi = im + radius;
+
+    auto grad_p = [&](int d, float q) {
+        float g = 0.f;
+        if (ge != 0.f) g = ge * (-logf(fminf(fmaxf(q, 1e-9f), 1.f)) - ((q >= 1e-9f && q <= 1.f) ? 1.f : 0.f));
+        // multiplicity of d in the clamped window
+        int cnt = 0;
+        if (d >= lo && d <= hi) cnt = 1;
+        if (d == 0 && lo < 0) cnt = 1 - lo;               // indices lo..0 all clamp to 0
+        if (d == D - 1 && hi > D - 1) cnt = hi - (D - 1) + 1;
+        if (cnt) g += gsoft * static_cast<float>(cnt) * (static_cast<float>(d) - soft) / den;
+        return g;
+    };
+    float dot = 0.f;
+    for (int d = 0; d < D; ++d) {
+        const float q = expf(__ldg(lp + static_cast<size_t>(d) * hw) - m) * inv_s;
+        dot = fmaf(q, grad_p(d, q), dot);
+    }
+    float* gp = glogits + static_cast<size_t>(b) * D * hw + p;
+    for (int d = 0; d < D; ++d) {
+        const float q = expf(__ldg(lp + static_cast<size_t>(d) * hw) - m) * inv_s;
+        gp[static_cast<size_t>(d) * hw] = q * (grad_p(d, q) - dot);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K4
+// movedepth/layers.py:200-214: mask.view(B,9,f,f,h,w) softmax over 9; unfold(depth,3,pad=1).
+template <bool BWD>
+__global__ void __launch_bounds__(256)
+convex_up_kernel(const float* __restrict__ depth, const float* __restrict__ mask, float* __restrict__ out,
+                 const float* __restrict__ gout, float* __restrict__ gdepth, float* __restrict__ gmask, int B, int h,
+                 int w, int f) {
+    const int hw = h * w, ff = f * f;
+    const size_t total = static_cast<size_t>(B) * ff * hw;
+    const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (idx >= total) return;
+    const int p = static_cast<int>(idx % hw);
+    const int ij = static_cast<int>((idx / hw) % ff);
+    const int b = static_cast<int>(idx / (static_cast<size_t>(hw) * ff));
+    const int y = p / w, x = p - y * w;
+    const int i = ij / f, j = ij - i * f;
+    const float* mp = mask + (static_cast<size_t>(b) * 9 * ff + ij) * hw + p;
+    float mk[9], nb[9];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        mk[k] = __ldg(mp + static_cast<size_t>(k) * ff * hw);
+        mx = fmaxf(mx, mk[k]);
+        const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
+        nb[k] = (yy >= 0 && yy < h && xx >= 0 && xx < w) ? __ldg(depth + static_cast<size_t>(b) * hw + yy * w + xx) : 0.f;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        mk[k] = expf(mk[k] - mx);
+        s += mk[k];
+    }
+    const float inv = 1.f / s;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+        mk[k] *= inv;
+        acc = fmaf(mk[k], nb[k], acc);
+    }
+    const size_t oix = (static_cast<size_t>(b) * h * f + (y * f + i)) * (static_cast<size_t>(w) * f) + (x * f + j);
+    if (!BWD) {
+        out[oix] = acc;
+    } else {
+        const float go = __ldg(gout + oix);
+        float* gm = gmask + (static_cast<size_t>(b) * 9 * ff + ij) * hw + p;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+            gm[static_cast<size_t>(k) * ff * hw] = go * mk[k] * (nb[k] - acc);
+            const int yy = y + k / 3 - 1, xx = x + k % 3 - 1;
+            if (yy >= 0 && yy < h && xx >= 0 && xx < w)
+                atomicAdd(gdepth + static_cast<size_t>(b) * hw + yy * w + xx, go * mk[k]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ Adam
+// torch.optim.Adam (no amsgrad, no weight decay): p -= step_size * m / (sqrt(v)/bias2 + eps)
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            long long n4, long long n, float b1, float b2, float eps, float step_size, float bias2, float gscale) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
+        float4 pv = reinterpret_cast<float4*>(p)[i];
+        const float4 gv = reinterpret_cast<const float4*>(g)[i];
+        float4 mv = reinterpret_cast<float4*>(m)[i];
+        float4 vv = reinterpret_cast<float4*>(v)[i];
+        float* pa = reinterpret_cast<float*>(&pv);
+        const float* ga = reinterpret_cast<const float*>(&gv);
+        float* ma = reinterpret_cast<float*>(&mv);
+        float* va = reinterpret_cast<float*>(&vv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gg = ga[k] * gscale;
+            ma[k] = ma[k] + (gg - ma[k]) * (1.f - b1);          // lerp form used by torch
+            va[k] = va[k] * b2 + (1.f - b2) * gg * gg;
+            const float denom = sqrtf(va[k]) / bias2 + eps;
+            pa[k] = pa[k] - step_size * (ma[k] / denom);
+        }
+        reinterpret_cast<float4*>(p)[i] = pv;
+        reinterpret_cast<float4*>(m)[i] = mv;
+        reinterpret_cast<float4*>(v)[i] = vv;
+    }
+    // tail (n not a multiple of 4)
+    for (long long i = n4 * 4 + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+        const float gg = g[i] * gscale;
+        const float mm = m[i] + (gg - m[i]) * (1.f - b1);
+        const float vv = v[i] * b2 + (1.f - b2) * gg * gg;
+        m[i] = mm;
+        v[i] = vv;
+        p[i] = p[i] - step_size * (mm / (sqrtf(vv) / bias2 + eps));
+    }
+}
+
+}  // namespace mvd
+
+extern "C" {
+
+int mvd_regress_fwd(const float* logits, const float* inv_a, const float* inv_b, float* prob, float* entropy,
+                    float* depth, int* amax, int B, int D, int hw, int radius, void* stream) {
+    MVD_REQUIRE(logits && inv_a && inv_b && entropy && depth && amax, "null pointer argument");
+    MVD_REQUIRE(B > 0 && D > 1 && hw > 0 && radius >= 0, "bad shape B=%d D=%d hw=%d radius=%d", B, D, hw, radius);
+    const int n = B * hw;
+    mvd::regress_fwd_kernel<<<(n + 127) / 128, 128, 0, mvd::as_stream(stream)>>>(logits, inv_a, inv_b, prob, entropy,
+                                                                                  depth, amax, B, D, hw, radius);
+    return mvd::check_launch("regress_fwd");
+}
+
+int mvd_regress_bwd(const float* logits, const float* inv_a, const float* inv_b, const int* amax,
+                    const float* g_entropy, const float* g_depth, float* glogits, int B, int D, int hw, int radius,
+                    void* stream) {
+    MVD_REQUIRE(logits && inv_a && inv_b && amax && glogits, "null pointer argument");
+    MVD_REQUIRE(B > 0 && D > 1 && hw > 0 && radius >= 0, "bad shape B=%d D=%d hw=%d radius=%d", B, D, hw, radius);
+    const int n = B * hw;
+    mvd::regress_bwd_kernel<<<(n + 127) / 128, 128, 0, mvd::as_stream(stream)>>>(logits, inv_a, inv_b, amax, g_entropy,
+                                                                                  g_depth, glogits, B, D, hw, radius);
+    return mvd::check_launch("regress_bwd");
+}
+
+int mvd_convex_up_fwd(const float* depth, const float* mask, float* out, int B, int h, int w, int f, void* stream) {
+    MVD_REQUIRE(depth && mask && out, "null pointer argument");
+    MVD_REQUIRE(B > 0 && h > 0 && w > 0 && f > 0, "bad shape");
+    const size_t total = static_cast<size_t>(B) * f * f * h * w;
+    mvd::convex_up_kernel<false><<<static_cast<unsigned>((total + 255) / 256), 256, 0, mvd::as_stream(stream)>>>(
+        depth, mask, out, nullptr, nullptr, nullptr, B, h, w, f);
+    return mvd::check_launch("convex_up_fwd");
+}
+
+int mvd_convex_up_bwd(const float* depth, const float* mask, const float* gout, float* gdepth, float* gmask, int B,
+                      int h, int w, int f, void* stream) {
+    MVD_REQUIRE(depth && mask && gout && gdepth && gmask, "null pointer argument");
+    MVD_REQUIRE(B > 0 && h > 0 && w > 0 && f > 0, "bad shape");
+    cudaStream_t st = mvd::as_stream(stream);
+    cudaError_t e = cudaMemsetAsync(gdepth, 0, sizeof(float) * B * h * w, st);
+    if (e != cudaSuccess) return mvd::fail(static_cast<int>(e), "convex_up_bwd memset: %s", cudaGetErrorString(e));
+    const size_t total = static_cast<size_t>(B) * f * f * h * w;
+    mvd::convex_up_kernel<true><<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(depth, mask, nullptr, gout,
+                                                                                            gdepth, gmask, B, h, w, f);
+    return mvd::check_launch("convex_up_bwd");
+}
+
+int mvd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float beta1,
+                  float beta2, float eps, float step_size, float bias2, float grad_scale, void* stream) {
+    MVD_REQUIRE(param && grad && exp_avg && exp_avg_sq, "null pointer argument");
+    MVD_REQUIRE(n >= 0, "negative length");
+    MVD_REQUIRE(mvd::aligned16(param) && mvd::aligned16(grad) && mvd::aligned16(exp_avg) && mvd::aligned16(exp_avg_sq),
+                "Adam arenas must be 16-byte aligned");
+    if (n == 0) return 0;
+    const long long n4 = n / 4;
+    const int grid = static_cast<int>(min(static_cast<long long>(mvd::sm_count()) * 8, (n4 + 255) / 256 + 1));
+    mvd::adam_kernel<<<grid, 256, 0, mvd::as_stream(stream)>>>(param, grad, exp_avg, exp_avg_sq, n4, n, beta1, beta2, eps,
+                                                               step_size, bias2, grad_scale);
+    return mvd::check_launch("adam_step");
+}
+
+}

@@ -1,0 +1,69 @@
+"""Mono disparity decoder and the entropy -> trust-mono-mask head.
+
+State-dict keys follow the reference (`decoder.{0..13}.conv.conv.*` / `decoder.{10..13}.conv.*`;
+`conv{1,2}.{0,1}.*`, `head_convs.weight`), SURVEY.md section 4.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..layers import ConvBlock, Conv3x3, upsample
+
+
+class DepthDecoder(nn.Module):
+    """U-Net decoder over the 5 encoder maps -> sigmoid disparity at `scales`.
+    Reference: movedepth/networks/depth_decoder.py:10-101 in the configuration the trainer uses
+    (trainer.py:74-75: skips on, one output channel; the ddv / mono_conf / match_conv variants
+    are never enabled there and are not built)."""
+
+    def __init__(self, num_ch_enc, scales=range(4), num_output_channels=1, use_skips=True, **unused):
+        super().__init__()
+        self.num_output_channels, self.use_skips, self.scales = num_output_channels, use_skips, list(scales)
+        self.num_ch_enc = num_ch_enc
+        self.num_ch_dec = np.array([16, 32, 64, 128, 256])
+        enc = [int(c) for c in num_ch_enc]
+        dec = [int(c) for c in self.num_ch_dec]
+        blocks, self._slot = [], {}
+
+        def add(key, module):
+            self._slot[key] = len(blocks)
+            blocks.append(module)
+
+        for i in range(4, -1, -1):                       # same insertion order as the reference's OrderedDict
+            add(("upconv", i, 0), ConvBlock(enc[-1] if i == 4 else dec[i + 1], dec[i]))
+            add(("upconv", i, 1), ConvBlock(dec[i] + (enc[i - 1] if (use_skips and i > 0) else 0), dec[i]))
+        for s in self.scales:
+            add(("dispconv", s), Conv3x3(dec[s], num_output_channels))
+        self.decoder = nn.ModuleList(blocks)
+
+    def _m(self, *key):
+        return self.decoder[self._slot[key]]
+
+    def forward(self, input_features, **unused):
+        self.outputs = {}
+        x = input_features[-1]
+        for i in range(4, -1, -1):
+            x = upsample(self._m("upconv", i, 0)(x))
+            if self.use_skips and i > 0:
+                x = torch.cat([x, input_features[i - 1]], 1)
+            x = self._m("upconv", i, 1)(x)
+            if i in self.scales:
+                self.outputs[("disp", i)] = torch.sigmoid(self._m("dispconv", i)(x))
+        return self.outputs
+
+
+class UncertNet(nn.Module):
+    """Entropy map [B,1,h,w] -> trust-mono mask in (0,1).  Reference: depth_decoder.py:371-393.
+    The 1-channel input is added (broadcast) to the 8-channel feature before the head; written
+    out of place (the reference's in-place add breaks autograd on current torch)."""
+
+    def __init__(self):
+        super().__init__()
+        self.conv1 = nn.Sequential(nn.Conv2d(1, 8, 3, 1, 1, bias=False), nn.BatchNorm2d(8), nn.ReLU(inplace=True))
+        self.conv2 = nn.Sequential(nn.Conv2d(8, 8, 3, 1, 1, bias=False), nn.BatchNorm2d(8), nn.ReLU(inplace=True))
+        self.head_convs = nn.Conv2d(8, 1, 3, 1, 1, bias=False)
+
+    def forward(self, x):
+        y = self.conv2(self.conv1(x)) + x
+        return torch.sigmoid(self.head_convs(y))

@@ -1,0 +1,227 @@
+"""torch.autograd bindings of the hand-written sm_100a kernels (through the C ABI, via ctypes).
+
+PyTorch is used here for device memory, streams and the autograd tape only; all arithmetic of
+these ops happens in libmovedepth_b200.so.  CPU tensors are rejected: there is no fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+LAYOUT_BGDHW = 0
+LAYOUT_BDHWG = 1
+FLAG_NO_TMA = 1
+
+# counts kernel launches issued through the C ABI (bench.py reports it as `gpu_launches`)
+launch_counter = {"n": 0}
+# when set to a list, the cost-volume forward appends (start, end) CUDA events recorded on the
+# launching stream around its kernel (bench.py's live roofline measurement)
+costvol_events = None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    if t is None:
+        return ctypes.c_void_p(0)
+    if not t.is_cuda:
+        raise RuntimeError("movedepth_b200 ops need CUDA tensors (no CPU fallback)")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _f32(t):
+    return t if t.dtype == torch.float32 else t.float()
+
+
+def _mat(m, B):
+    m = _f32(m).reshape(-1, 4, 4)
+    if m.shape[0] == 1 and B > 1:
+        m = m.expand(B, 4, 4)
+    assert m.shape[0] == B, "expected %d 4x4 matrices, got %d" % (B, m.shape[0])
+    return m.contiguous()
+
+
+def _nhwc(t):
+    return _f32(t).contiguous(memory_format=torch.channels_last)
+
+
+# ------------------------------------------------------------------------------------- K1
+class _CostVolumeGrouped(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ref, src, prior, ratio, hyps, K, invK, T, groups, layout, flags):
+        B, C, h, w = ref.shape
+        ref_cl, src_cl = _nhwc(ref), _nhwc(src)
+        if hyps is not None:
+            hyps = _f32(hyps).contiguous()
+            D = hyps.shape[1]
+            prior_c = ratio_c = None
+        else:
+            prior_c = _f32(prior).reshape(B, h, w).contiguous()
+            ratio_c = _f32(ratio).contiguous()
+            D = ratio_c.shape[1]
+        K, invK, T = _mat(K, B), _mat(invK, B), _mat(T, B)
+        fmt = torch.contiguous_format if layout == LAYOUT_BGDHW else torch.channels_last_3d
+        out = torch.empty((B, groups, D, h, w), device=ref.device, dtype=torch.float32, memory_format=fmt)
+        ev = None
+        if costvol_events is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        rc = _lib.lib().mvd_costvol_grouped_fwd(_p(ref_cl), _p(src_cl), _p(prior_c), _p(ratio_c), _p(hyps), _p(K),
+                                                _p(invK), _p(T), _p(out), B, C, groups, h, w, D, layout, flags, _stream())
+        _lib.check(rc, "mvd_costvol_grouped_fwd")
+        if ev is not None:
+            ev[1].record()
+            costvol_events.append(ev)
+        launch_counter["n"] += 1
+        ctx.save_for_backward(ref_cl, src_cl, prior_c, ratio_c, hyps, K, invK, T)
+        ctx.meta = (B, C, groups, h, w, D, layout, flags, fmt)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        ref_cl, src_cl, prior_c, ratio_c, hyps, K, invK, T = ctx.saved_tensors
+        B, C, groups, h, w, D, layout, flags, fmt = ctx.meta
+        gout = _f32(gout).contiguous(memory_format=fmt)
+        gref = torch.empty_like(ref_cl)
+        gsrc = torch.empty_like(src_cl)
+        rc = _lib.lib().mvd_costvol_grouped_bwd(_p(gout), _p(ref_cl), _p(src_cl), _p(prior_c), _p(ratio_c), _p(hyps),
+                                                _p(K), _p(invK), _p(T), _p(gref), _p(gsrc), B, C, groups, h, w, D,
+                                                layout, flags, _stream())
+        _lib.check(rc, "mvd_costvol_grouped_bwd")
+        launch_counter["n"] += 3
+        return gref, gsrc, None, None, None, None, None, None, None, None, None
+
+
+def costvol_grouped(ref, src, K, invK, T, prior=None, ratio=None, hyps=None, groups=16, layout=LAYOUT_BGDHW, flags=0):
+    """Fused warp + gather + group correlation.  Returns the grouped volume as a logical
+    [B,G,D,h,w] tensor (physically [B,D,h,w,G] when layout == LAYOUT_BDHWG).
+    Reference: movedepth/layers.py:778-794 + movedepth/trainer.py:359."""
+    return _CostVolumeGrouped.apply(ref, src, prior, ratio, hyps, K, invK, T, groups, layout, flags)
+
+
+class _CostVolumeFull(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ref, src, hyps, K, invK, T):
+        B, C, h, w = ref.shape
+        ref, src, hyps = _f32(ref).contiguous(), _f32(src).contiguous(), _f32(hyps).contiguous()
+        D = hyps.shape[1]
+        K, invK, T = _mat(K, B), _mat(invK, B), _mat(T, B)
+        out = torch.empty((B, D, C, h, w), device=ref.device, dtype=torch.float32)
+        rc = _lib.lib().mvd_costvol_full_fwd(_p(ref), _p(src), _p(hyps), _p(K), _p(invK), _p(T), _p(out), B, C, h, w, D,
+                                             _stream())
+        _lib.check(rc, "mvd_costvol_full_fwd")
+        launch_counter["n"] += 1
+        ctx.save_for_backward(ref, src, hyps, K, invK, T)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        ref, src, hyps, K, invK, T = ctx.saved_tensors
+        B, C, h, w = ref.shape
+        D = hyps.shape[1]
+        gout = _f32(gout).contiguous()
+        gref, gsrc = torch.empty_like(ref), torch.empty_like(src)
+        rc = _lib.lib().mvd_costvol_full_bwd(_p(gout), _p(ref), _p(src), _p(hyps), _p(K), _p(invK), _p(T), _p(gref),
+                                             _p(gsrc), B, C, h, w, D, _stream())
+        _lib.check(rc, "mvd_costvol_full_bwd")
+        launch_counter["n"] += 3
+        return gref, gsrc, None, None, None, None
+
+
+def costvol_full(ref, src, hyps, K, invK, T):
+    """Reference-layout volume [B,D,C,h,w] (movedepth/layers.py:778-794)."""
+    return _CostVolumeFull.apply(ref, src, hyps, K, invK, T)
+
+
+# ------------------------------------------------------------------------------------- K3
+class _Regress(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, inv_a, inv_b, radius, want_prob):
+        B, D, h, w = logits.shape
+        logits = _f32(logits).contiguous()
+        inv_a = _f32(inv_a).reshape(B, h, w).contiguous()
+        inv_b = _f32(inv_b).reshape(B, h, w).contiguous()
+        prob = torch.empty_like(logits) if want_prob else None
+        ent = torch.empty((B, 1, h, w), device=logits.device, dtype=torch.float32)
+        depth = torch.empty((B, h, w), device=logits.device, dtype=torch.float32)
+        amax = torch.empty((B, h, w), device=logits.device, dtype=torch.int32)
+        rc = _lib.lib().mvd_regress_fwd(_p(logits), _p(inv_a), _p(inv_b), _p(prob), _p(ent), _p(depth), _p(amax), B, D,
+                                        h * w, radius, _stream())
+        _lib.check(rc, "mvd_regress_fwd")
+        launch_counter["n"] += 1
+        ctx.save_for_backward(logits, inv_a, inv_b, amax)
+        ctx.radius = radius
+        if prob is None:
+            prob = logits.new_empty(0)
+        ctx.mark_non_differentiable(prob)
+        return prob, ent, depth
+
+    @staticmethod
+    def backward(ctx, _gprob, gent, gdepth):
+        logits, inv_a, inv_b, amax = ctx.saved_tensors
+        B, D, h, w = logits.shape
+        gent = None if gent is None else _f32(gent).contiguous()
+        gdepth = None if gdepth is None else _f32(gdepth).contiguous()
+        gl = torch.empty_like(logits)
+        rc = _lib.lib().mvd_regress_bwd(_p(logits), _p(inv_a), _p(inv_b), _p(amax), _p(gent), _p(gdepth), _p(gl), B, D,
+                                        h * w, ctx.radius, _stream())
+        _lib.check(rc, "mvd_regress_bwd")
+        launch_counter["n"] += 1
+        return gl, None, None, None, None
+
+
+def regress_depth(logits, inv_a, inv_b, radius=1, want_prob=False):
+    """softmax over D + entropy + local-max regression in one kernel.
+    Returns (prob [B,D,h,w] or empty, entropy [B,1,h,w], depth [B,h,w]).  prob carries no gradient.
+    Reference: movedepth/trainer.py:367-371, layers.py:796-812, 862-863."""
+    return _Regress.apply(logits, inv_a, inv_b, radius, want_prob)
+
+
+# ------------------------------------------------------------------------------------- K4
+class _ConvexUp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, mask, f):
+        B, h, w = depth.shape
+        depth, mask = _f32(depth).contiguous(), _f32(mask).contiguous()
+        assert mask.shape == (B, 9 * f * f, h, w), mask.shape
+        out = torch.empty((B, f * h, f * w), device=depth.device, dtype=torch.float32)
+        rc = _lib.lib().mvd_convex_up_fwd(_p(depth), _p(mask), _p(out), B, h, w, f, _stream())
+        _lib.check(rc, "mvd_convex_up_fwd")
+        launch_counter["n"] += 1
+        ctx.save_for_backward(depth, mask)
+        ctx.f = f
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        depth, mask = ctx.saved_tensors
+        B, h, w = depth.shape
+        gout = _f32(gout).contiguous()
+        gdepth, gmask = torch.empty_like(depth), torch.empty_like(mask)
+        rc = _lib.lib().mvd_convex_up_bwd(_p(depth), _p(mask), _p(gout), _p(gdepth), _p(gmask), B, h, w, ctx.f, _stream())
+        _lib.check(rc, "mvd_convex_up_bwd")
+        launch_counter["n"] += 2
+        return gdepth, gmask, None
+
+
+def convex_upsample(depth, mask, scale=2):
+    """movedepth/layers.py:200-214.  depth [B,h,w] or [B,1,h,w]; mask [B,9*4**scale,h,w]."""
+    if depth.dim() == 4:
+        depth = depth[:, 0]
+    return _ConvexUp.apply(depth, mask, 2 ** scale)
+
+
+# ------------------------------------------------------------------------------------- Adam
+def adam_step(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
+    """One fused Adam update over flat fp32 arenas (torch.optim.Adam semantics)."""
+    n = param.numel()
+    assert grad.numel() == n and exp_avg.numel() == n and exp_avg_sq.numel() == n
+    step_size = lr / (1.0 - beta1 ** step)
+    bias2 = (1.0 - beta2 ** step) ** 0.5
+    rc = _lib.lib().mvd_adam_step(_p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), n, beta1, beta2, eps, step_size,
+                                  bias2, grad_scale, _stream())
+    _lib.check(rc, "mvd_adam_step")
+    launch_counter["n"] += 1

@@ -1,0 +1,554 @@
+"""Trainer with the reference's API surface (movedepth/trainer.py:33-911) on the B200-native hot path.
+
+Same constructor (`Trainer(options)`), same `models` dict keys, same method names
+(`train`, `run_epoch`, `process_batch`, `predict_poses`, `compute_losses`, `save_model`, ...), same
+item-dict schema for batches (movedepth/datasets/mono_dataset.py:134-154) and the same checkpoint
+files.  What differs is how a step executes:
+
+  * the cost volume is built by one fused kernel straight into the layout reg3d consumes
+    (no [B,D,C,h,w] tensor, no Python loop over the batch, no hypothesis tensor);
+  * softmax + entropy + local-max and the convex upsampling are single kernels;
+  * all parameters / gradients / Adam moments live in flat fp32 arenas: one fused Adam kernel per
+    parameter group, and data-parallel training all-reduces the gradient arena over NCCL in two
+    pieces (cost-volume branch first, overlapping the mono/pose backward) instead of eight DDP
+    reducers;
+  * the step is two autograd graphs joined only by detached tensors, so the
+    two backward passes run with different cuDNN precision policies.
+
+There is no CPU path: `--no_cuda` raises.
+"""
+import json
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import networks, ops
+from . import photometric as photo
+from .layers import (disp_to_depth, get_smooth_loss, transformation_from_parameters, hypothesis_ratios,
+                     fused_group_costvol, convex_upsample_layer, compute_depth_errors)
+
+GROUP0 = ("mono_encoder", "mono_depth", "pose_encoder", "pose", "up")   # lr            (trainer.py:62-141)
+GROUP1 = ("mask_cnn", "mvs_encoder", "reg3d")                           # lr * lr_fac
+
+
+def kitti_intrinsics(batch, height, width, device="cpu"):
+    """Normalised KITTI K (movedepth/datasets/kitti_dataset.py:26-29) scaled per
+    mono_dataset.py:209-218 -> (K, inv_K) [B,4,4]."""
+    K = torch.tensor([[0.58, 0, 0.5, 0], [0, 1.92, 0.5, 0], [0, 0, 1, 0], [0, 0, 0, 1]], dtype=torch.float64)
+    K[0] *= width
+    K[1] *= height
+    return (K.float().repeat(batch, 1, 1).to(device), torch.linalg.pinv(K).float().repeat(batch, 1, 1).to(device))
+
+
+class SyntheticKITTI:
+    """Iterable of synthetic KITTI-shape item dicts in pinned host memory (U[0,1) images, KITTI
+    intrinsics at 4 scales), schema of movedepth/datasets/mono_dataset.py:134-154."""
+
+    def __init__(self, opt, batch_size, steps, seed=1, pin=True):
+        self.opt, self.batch_size, self.steps, self.seed, self.pin = opt, batch_size, steps, seed, pin
+
+    def __len__(self):
+        return self.steps
+
+    def make(self, g):
+        o, B = self.opt, self.batch_size
+        item = {}
+        for f in o.frame_ids:
+            img = torch.rand(B, 3, o.height, o.width, generator=g)
+            for s in range(4):
+                im = img if s == 0 else F.interpolate(img, size=(o.height // 2 ** s, o.width // 2 ** s), mode="area")
+                item[("color", f, s)] = im
+                item[("color_aug", f, s)] = im.clone()
+        for s in range(4):
+            item[("K", s)], item[("inv_K", s)] = kitti_intrinsics(B, o.height // 2 ** s, o.width // 2 ** s)
+        if self.pin and torch.cuda.is_available():
+            item = {k: v.pin_memory() for k, v in item.items()}
+        return item
+
+    def __iter__(self):
+        g = torch.Generator().manual_seed(self.seed)
+        for _ in range(self.steps):
+            yield self.make(g)
+
+
+class FlatArena:
+    """All trainable parameters of a group re-homed into one flat fp32 buffer (+ gradient and Adam
+    moment buffers of the same shape), so the optimizer and the gradient all-reduce are single
+    calls.  Each tensor starts on a 16-byte boundary."""
+
+    def __init__(self, params, device):
+        self.params = list(params)
+        offs, n = [], 0
+        for p in self.params:
+            offs.append(n)
+            n += (p.numel() + 3) // 4 * 4
+        self.numel = n
+        self.data = torch.zeros(n, device=device)
+        self.grad = torch.zeros(n, device=device)
+        self.exp_avg = torch.zeros(n, device=device)
+        self.exp_avg_sq = torch.zeros(n, device=device)
+        for p, o in zip(self.params, offs):
+            view = self.data[o:o + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.grad[o:o + p.numel()].view_as(p)
+        self.offsets = offs
+
+    def rebind_grads(self):
+        for p, o in zip(self.params, self.offsets):
+            p.grad = self.grad[o:o + p.numel()].view_as(p)
+
+
+class Trainer:
+    def __init__(self, options, train_loader=None, val_loader=None):
+        self.opt = o = options
+        self.log_path = os.path.join(o.log_dir, o.model_name)
+        assert o.height % 32 == 0, "'height' must be a multiple of 32"
+        assert o.width % 32 == 0, "'width' must be a multiple of 32"
+        assert o.frame_ids[0] == 0, "frame_ids must start with 0"
+        assert len(o.frame_ids) > 1, "frame_ids must have more than 1 frame specified"
+        if o.no_cuda or not torch.cuda.is_available():
+            raise RuntimeError("movedepth_b200 has no CPU path: a CUDA device (B200, sm_100a) is required")
+        ops._lib.lib()                                    # fail loudly now if the extension is missing
+
+        self.local_rank = int(os.environ.get("LOCAL_RANK", o.local_rank))
+        torch.cuda.set_device(self.local_rank)
+        self.device = torch.device("cuda", self.local_rank)
+        self.world_size, self.rank = 1, 0
+        if o.ddp:
+            if not dist.is_initialized():
+                dist.init_process_group(backend="nccl")
+            self.world_size, self.rank = dist.get_world_size(), dist.get_rank()
+
+        self.num_scales = len(o.scales)
+        self.num_input_frames = len(o.frame_ids)
+        self.num_pose_frames = 2
+        self.matching_ids = o.matching_ids
+        self.precision = getattr(o, "b200_conv_precision", "mixed")
+        torch.backends.cudnn.benchmark = True
+
+        # ---- sub-models (trainer.py:65-131)
+        pretrained = o.weights_init == "pretrained"
+        m = {}
+        m["mono_encoder"] = networks.ResnetEncoder(o.res_arch, pretrained)
+        m["mono_depth"] = networks.DepthDecoder(m["mono_encoder"].num_ch_enc, o.scales)
+        m["pose_encoder"] = networks.ResnetEncoder(o.res_arch, pretrained, num_input_images=self.num_pose_frames)
+        m["pose"] = networks.PoseDecoder(m["pose_encoder"].num_ch_enc, num_input_features=1, num_frames_to_predict_for=2)
+        m["mask_cnn"] = networks.UncertNet()
+        m["mvs_encoder"] = networks.FPN4(base_channels=8, scale=o.prior_scale, dcn=o.dcn)
+        if o.num_depth_bins >= 8:
+            m["reg3d"] = networks.reg3d(o.reg3d_c, o.reg3d_c, 3)
+        else:
+            m["reg3d"] = networks.reg2d(o.reg3d_c, 8)
+        m["up"] = convex_upsample_layer(8 * 2 ** o.prior_scale, o.prior_scale)
+        for k in m:
+            if o.ddp and self.world_size > 1:
+                m[k] = nn.SyncBatchNorm.convert_sync_batchnorm(m[k])
+            m[k].to(self.device)
+        self.models = m
+        self.parameters_to_train = [p for k in GROUP0 for p in m[k].parameters()]
+        self.mvs_parameters_to_train = [p for k in GROUP1 for p in m[k].parameters()]
+
+        if o.load_weights_folder is not None:
+            self.load_model()
+        if o.mono_weights_folder is not None:
+            self.load_mono_model()
+        if o.ddp and self.world_size > 1:                 # what the DDP constructor's broadcast does
+            for k in m:
+                for t in list(m[k].parameters()) + list(m[k].buffers()):
+                    dist.broadcast(t.data, 0)
+
+        # ---- flat arenas + fused Adam (replaces optim.Adam + StepLR, trainer.py:137-141)
+        self.arenas = [FlatArena(self.parameters_to_train, self.device),
+                       FlatArena(self.mvs_parameters_to_train, self.device)]
+        self.base_lrs = [o.learning_rate, o.learning_rate * o.lr_fac]
+        self.opt_step = 0
+        self.epoch = 0
+        self.step = 0
+
+        # ---- data: any iterable of item dicts; synthetic KITTI-shape tensors by default
+        steps = 100
+        self.train_loader = train_loader if train_loader is not None else SyntheticKITTI(o, o.batch_size, steps, seed=1 + self.rank)
+        self.val_loader = val_loader if val_loader is not None else SyntheticKITTI(o, o.batch_size, 4, seed=10_000 + self.rank)
+        self.val_iter = iter(self.val_loader)
+        self.depth_metric_names = ["de/abs_rel", "de/sq_rel", "de/rms", "de/log_rms", "da/a1", "da/a2", "da/a3"]
+        if o.ddp:
+            o.log_frequency = max(1, o.log_frequency // self.world_size)
+        self._aug_box = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self.set_train()
+
+    # ------------------------------------------------------------------ mode switches
+    def set_train(self):
+        for mod in self.models.values():
+            mod.train()
+
+    def set_eval(self):
+        for mod in self.models.values():
+            mod.eval()
+
+    def current_lrs(self):
+        decay = 0.1 ** (self.epoch // self.opt.scheduler_step_size)
+        return [lr * decay for lr in self.base_lrs]
+
+    def _tf32(self, branch):
+        """cuDNN TF32 policy per branch: 'mono' (encoders/decoder/pose) or 'mvs' (FPN4/reg3d/heads)."""
+        on = self.precision == "tf32" or (self.precision == "mixed" and branch == "mono")
+        torch.backends.cudnn.allow_tf32 = on
+
+    # ------------------------------------------------------------------ training loop
+    def train(self):
+        """Run the entire training pipeline (movedepth/trainer.py:244-256)."""
+        self.epoch, self.step = 0, 0
+        self.start_time = time.time()
+        for self.epoch in range(self.opt.num_epochs):
+            self.run_epoch()
+            if (self.epoch + 1) % self.opt.save_frequency == 0 and self.epoch > 15:
+                self.save_model()
+
+    def run_epoch(self):
+        """One pass over the train loader (movedepth/trainer.py:258-295)."""
+        self.set_train()
+        for batch_idx, inputs in enumerate(self.train_loader):
+            t0 = time.time()
+            outputs, losses = self.train_step(inputs)
+            early = batch_idx % self.opt.log_frequency == 0 and self.step < 2000
+            late = self.step % 2000 == 0
+            if early or late:
+                if self.rank == 0:
+                    self.log_time(batch_idx, time.time() - t0, float(losses["loss"]))
+                    self.log("train", inputs, outputs, losses)
+            if self.opt.save_intermediate_models and late:
+                self.save_model(save_step=True)
+            self.step += 1
+
+    def train_step(self, inputs, noise=None, mask_xy=None):
+        """process_batch + zero_grad + backward + optimizer.step (movedepth/trainer.py:269-272)."""
+        for a in self.arenas:
+            a.grad.zero_()
+        outputs, losses = self.process_batch(inputs, is_train=True, noise=noise, mask_xy=mask_xy)
+        multi = self.opt.ddp and self.world_size > 1
+        # the two graphs share nothing but detached tensors: back-propagate them separately so the
+        # cost-volume branch keeps fp32 convolutions and its gradients can be reduced early
+        self._tf32("mvs")
+        losses["_mvs_total"].backward()
+        work = dist.all_reduce(self.arenas[1].grad, async_op=True) if multi else None
+        self._tf32("mono")
+        losses["_mono_total"].backward()
+        if multi:
+            dist.all_reduce(self.arenas[0].grad)
+            work.wait()
+        self.opt_step += 1
+        for a, lr in zip(self.arenas, self.current_lrs()):
+            ops.adam_step(a.data, a.grad, a.exp_avg, a.exp_avg_sq, self.opt_step, lr, grad_scale=1.0 / self.world_size)
+        return outputs, losses
+
+    # ------------------------------------------------------------------ forward + losses
+    def predict_poses(self, inputs):
+        """Pose net on (earlier, later) frame pairs (movedepth/trainer.py:445-468)."""
+        outputs = {}
+        for f in self.opt.frame_ids[1:]:
+            if f == "s":
+                continue
+            a, b = inputs[("color_aug", f, 0)], inputs[("color_aug", 0, 0)]
+            pair = [a, b] if f < 0 else [b, a]
+            feats = [self.models["pose_encoder"](torch.cat(pair, 1))]
+            axisangle, translation = self.models["pose"](feats)
+            outputs[("axisangle", 0, f)], outputs[("translation", 0, f)] = axisangle, translation
+            outputs[("cam_T_cam", 0, f)] = transformation_from_parameters(axisangle[:, 0], translation[:, 0], invert=(f < 0))
+        for f in self.matching_ids[1:]:
+            inputs[("relative_pose", f)] = outputs[("cam_T_cam", 0, f)].clone().detach()
+        return outputs
+
+    def _volume_logits(self, ref_feat, src_feats, inputs, prior, ratio, poses):
+        """cost volume over the matching frames -> reg3d logits (trainer.py:349-366)."""
+        K, invK = inputs[("K", 2)], inputs[("inv_K", 2)]       # scale index 2 is hard-coded in the reference
+        vols = [fused_group_costvol(ref_feat, src_feats[i], K, invK, poses[:, i], prior, ratio, self.opt.reg3d_c)
+                for i in range(len(src_feats))]
+        if len(vols) == 1:
+            vol = vols[0]        # single view: the view weight w/(1e-8+w) is 1 to within 2e-7
+        else:
+            wsum, acc = 1e-8, 0
+            for v in vols:       # [B,G,D,h,w]: mean over D, softmax over G, max (trainer.py:360)
+                wgt = torch.softmax(v.mean(2), dim=1).max(1)[0]
+                wsum = wsum + wgt
+                acc = acc + wgt[:, None, None] * v
+            vol = acc / wsum[:, None, None]
+        return self.models["reg3d"].forward_volume(vol), vol
+
+    def process_batch(self, inputs, is_train=False, noise=None, mask_xy=None):
+        """Forward pass and all losses for one minibatch (movedepth/trainer.py:297-442).
+        `noise` (list of [B,1,H,W] N(0,1) tensors) and `mask_xy` (box corner) override the random
+        draws so that parity tests can reproduce the reference bit for bit."""
+        o = self.opt
+        inputs = {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in inputs.items()}
+        B = inputs[("color_aug", 0, 0)].shape[0]
+        noise = list(noise) if noise is not None else None
+
+        # ---------------- mono / pose graph (TF32 allowed under the 'mixed' policy)
+        self._tf32("mono")
+        outputs = self.predict_poses(inputs)
+        poses = torch.stack([inputs[("relative_pose", f)] for f in self.matching_ids[1:]], 1)   # [B,M,4,4]
+        outputs.update(self.models["mono_depth"](self.models["mono_encoder"](inputs[("color_aug", 0, 0)])))
+        losses = self.compute_losses(inputs, outputs, is_mvs=False, noise=noise)
+
+        # ---------------- hypotheses around the mono prior (trainer.py:333-346), separable form
+        disp_prior = outputs[("disp", o.prior_scale)].detach()
+        prior = 1.0 / (1.0 / o.max_depth + disp_prior * (1.0 / o.min_depth - 1.0 / o.max_depth))
+        if self.epoch > o.ztrans_start_epc:
+            s = o.depth_bin_fac * o.z_scale * poses[:, 0, 2, 3]
+        else:
+            s = torch.full((B,), float(o.depth_bin_fac), device=self.device)
+        ratio = hypothesis_ratios(o.num_depth_bins, s, self.device, o.schedule_type)          # [B,D]
+        inv_a = 1.0 / (prior[:, 0] * ratio[:, -1].view(B, 1, 1))
+        inv_b = 1.0 / (prior[:, 0] * ratio[:, 0].view(B, 1, 1))
+        outputs["depth_prior"], outputs["hypothesis_ratio"] = prior, ratio
+
+        # ---------------- cost-volume graph (fp32 convolutions under 'mixed')
+        self._tf32("mvs")
+        enc = self.models["mvs_encoder"]
+        ref_feat, ref_ctx = enc(inputs[("color_aug", 0, 0)])
+        src_feats = [enc(inputs[("color_aug", f, 0)])[0] for f in self.matching_ids[1:]]
+        logits, vol = self._volume_logits(ref_feat, src_feats, inputs, prior, ratio, poses)
+        _, ent, depth_mvs = ops.regress_depth(logits, inv_a, inv_b, o.norm_radius)
+        trust = self.models["mask_cnn"](ent)
+        outputs["cost_volume"], outputs["cost_logits"], outputs["depth_mvs_lowres"] = vol, logits, depth_mvs
+
+        # masked-augmentation consistency (trainer.py:374-403): zero a random box of the reference image
+        fh, fw = o.height // 3, o.width // 3
+        if mask_xy is None:
+            mask_xy = (np.random.randint(0, o.width - fw), np.random.randint(0, o.height - fh))   # x first, as the reference
+        self._aug_box.copy_(torch.tensor(mask_xy, dtype=torch.int64), non_blocking=True)
+        ys = torch.arange(o.height, device=self.device).view(1, 1, -1, 1)
+        xs = torch.arange(o.width, device=self.device).view(1, 1, 1, -1)
+        inside = (xs >= self._aug_box[0]) & (xs < self._aug_box[0] + fw) & (ys >= self._aug_box[1]) & (ys < self._aug_box[1] + fh)
+        aug_mask = (~inside).float().expand(B, 3, o.height, o.width)
+        aug_feat, _ = enc(inputs[("color_aug", 0, 0)] * aug_mask)
+        logits_aug, _ = self._volume_logits(aug_feat, src_feats, inputs, prior, ratio, poses)
+        _, _, depth_aug = ops.regress_depth(logits_aug, inv_a, inv_b, o.norm_radius)
+        sel = (F.interpolate(aug_mask, list(depth_aug.shape[1:]), mode="bilinear", align_corners=True).sum(1) != 0).float()
+        masked = (F.smooth_l1_loss(depth_aug, depth_mvs, reduction="none") * sel).sum() / sel.sum()
+        masked = masked * o.mask_lw * o.mask_lw            # weight applied twice in the reference (trainer.py:399-400)
+        outputs["masked_depth"], outputs["masked_aug"] = depth_aug, aug_mask
+
+        # upsample + fuse (trainer.py:405-416)
+        if o.convex_up:
+            depth_up = self.models["up"](depth_mvs, ref_ctx)
+        else:
+            depth_up = F.interpolate(depth_mvs.unsqueeze(1), [o.height, o.width], mode="bilinear", align_corners=True)[:, 0]
+        outputs["depth_mvs"] = depth_up
+        _, mono_depth = disp_to_depth(outputs[("disp", 0)], o.min_depth, o.max_depth)
+        trust = F.interpolate(trust, [o.height, o.width], mode="bilinear", align_corners=True)
+        outputs["trust_mono_mask"] = trust
+        outputs["fused_depth"] = (1 - trust) * depth_up.unsqueeze(1).detach() + trust * mono_depth.detach()
+        fuse_loss = self.compute_fuse_losses(inputs, outputs, noise=noise)
+        mvs_losses = self.compute_losses(inputs, outputs, is_mvs=True, noise=noise)
+
+        # ---------------- totals (trainer.py:429-440): loss = mvs + (mono + masked) + fuse
+        losses["masked_loss"] = masked
+        losses["fuse_reproj_loss"] = fuse_loss
+        losses.update({k: v for k, v in mvs_losses.items() if k != "loss"})
+        losses["_mono_total"] = losses["loss"]
+        losses["_mvs_total"] = mvs_losses["loss"] + masked + fuse_loss
+        losses["loss"] = losses["_mono_total"] + losses["_mvs_total"]
+        return outputs, losses
+
+    def compute_reprojection_loss(self, pred, target, ssim_lw=None):
+        """movedepth/trainer.py:535-550."""
+        w = self.opt.ssim_lw if ssim_lw is None else ssim_lw
+        return photo.photo_error(pred, target, 0 if self.opt.no_ssim else w)
+
+    def _identity_min(self, inputs, ssim_w):
+        tgt = inputs[("color", 0, 0)]
+        ident = [photo.identity_loss(inputs[("color", f, 0)], tgt, ssim_w) for f in self.opt.frame_ids[1:]]
+        return torch.cat(ident, 1).min(1, keepdim=True)[0]
+
+    def compute_losses(self, inputs, outputs, is_mvs=False, noise=None):
+        """Photometric + smoothness losses (movedepth/trainer.py:491-532 warps, 614-724 losses)."""
+        o = self.opt
+        tgt = inputs[("color", 0, 0)]
+        K, invK = inputs[("K", 0)], inputs[("inv_K", 0)]
+        ssim_w = 0 if o.no_ssim else o.ssim_lw
+        losses = {}
+        if is_mvs:
+            depth = outputs["depth_mvs"]
+            per_src = []
+            for f in o.frame_ids[1:]:
+                T = outputs[("cam_T_cam", 0, f)].detach()
+                l, warped = photo.reprojection_loss(depth, inputs[("color", f, 0)], tgt, K, invK, T, ssim_w)
+                outputs[("mvs_color", f)] = warped
+                per_src.append(l)
+            reproj = torch.cat(per_src, 1).min(1, keepdim=True)[0]
+            if o.mask_mvs_auto and noise is not None and len(noise):
+                noise.pop(0)                         # drawn by the reference, the mask is then overwritten by ones
+            outputs["mvs_reprojection_loss"] = reproj
+            loss = reproj.sum() / (reproj.numel() + 1e-7)
+            if o.mvs_smooth_loss:
+                d = depth.unsqueeze(1)
+                sm = get_smooth_loss(d / (d.mean(2, True).mean(3, True) + 1e-7), tgt)
+                losses["mvs_smooth_loss/0"] = sm
+                loss = loss + o.disparity_smoothness * sm
+            losses["mvs_reproj_loss"] = loss
+            losses["loss"] = loss
+            return losses
+
+        ident = None if o.disable_automasking else self._identity_min(inputs, ssim_w)
+        total = 0
+        for s in o.scales:
+            disp = outputs[("disp", s)]
+            disp_full = F.interpolate(disp, [o.height, o.width], mode="bilinear", align_corners=False)
+            _, depth = disp_to_depth(disp_full, o.min_depth, o.max_depth)
+            outputs[("depth", 0, s)] = depth
+            per_src = []
+            for f in o.frame_ids[1:]:
+                l, warped = photo.reprojection_loss(depth, inputs[("color", f, 0)], tgt, K, invK,
+                                                    outputs[("cam_T_cam", 0, f)], ssim_w)
+                outputs[("color", f, s)] = warped
+                per_src.append(l)
+            reproj = torch.cat(per_src, 1).min(1, keepdim=True)[0]
+            if ident is not None:
+                nz = noise.pop(0).to(self.device) if noise is not None else torch.randn_like(ident)
+                mask = (reproj <= ident + nz * 1e-5).float()            # argmin over [reproj, identity] == 0
+            else:
+                mask = torch.ones_like(reproj)
+            if s == 0:
+                outputs["mono_reproj_loss"] = reproj
+            loss = (reproj * mask).sum() / (mask.sum() + 1e-7)
+            norm_disp = disp / (disp.mean(2, True).mean(3, True) + 1e-7)
+            sm = get_smooth_loss(norm_disp, inputs[("color", 0, s)])
+            losses["mono_smooth_loss/{}".format(s)] = sm
+            loss = loss + o.disparity_smoothness * sm / (2 ** s)
+            total = total + loss
+            losses["loss/{}".format(s)] = loss
+        losses["loss"] = total / self.num_scales
+        return losses
+
+    def compute_fuse_losses(self, inputs, outputs, noise=None):
+        """L1-only reprojection of the fused depth; trains the trust mask (trainer.py:569-612)."""
+        o = self.opt
+        tgt = inputs[("color", 0, 0)]
+        K, invK = inputs[("K", 0)], inputs[("inv_K", 0)]
+        per_src = []
+        for f in o.frame_ids[1:]:
+            l, warped = photo.reprojection_loss(outputs["fused_depth"], inputs[("color", f, 0)], tgt, K, invK,
+                                                outputs[("cam_T_cam", 0, f)].detach(), 0)
+            outputs[("mvs_color_fuse", f)] = warped
+            per_src.append(l)
+        reproj = torch.cat(per_src, 1).min(1, keepdim=True)[0]
+        if o.mask_mvs_auto:
+            ident = self._identity_min(inputs, 0)
+            nz = noise.pop(0).to(self.device) if noise is not None else torch.randn_like(ident)
+            mask = (reproj <= ident + nz * 1e-5).float()
+        else:
+            mask = torch.ones_like(reproj)
+        return (reproj * mask).sum() / (mask.sum() + 1e-7)
+
+    # ------------------------------------------------------------------ validation / logging / checkpoints
+    def val(self):
+        """One validation minibatch (movedepth/trainer.py:470-489)."""
+        self.set_eval()
+        try:
+            inputs = next(self.val_iter)
+        except StopIteration:
+            self.val_iter = iter(self.val_loader)
+            inputs = next(self.val_iter)
+        with torch.no_grad():
+            outputs, losses = self.process_batch(inputs)
+            if "depth_gt" in inputs:
+                self.compute_depth_losses(inputs, outputs, losses)
+            if self.rank == 0:
+                self.log("val", inputs, outputs, losses)
+        self.set_train()
+        return losses
+
+    def compute_depth_losses(self, inputs, outputs, losses):
+        """KITTI depth metrics on a minibatch, for monitoring (movedepth/trainer.py:726-757)."""
+        pred = torch.clamp(F.interpolate(outputs[("depth", 0, 0)], [375, 1242], mode="bilinear", align_corners=False),
+                           1e-3, 80).detach()
+        gt = inputs["depth_gt"].to(self.device)
+        mask = gt > 0
+        crop = torch.zeros_like(mask)
+        crop[:, :, 153:371, 44:1197] = 1
+        mask = mask * crop
+        gt, pred = gt[mask], pred[mask]
+        pred = torch.clamp(pred * torch.median(gt) / torch.median(pred), min=1e-3, max=80)
+        for name, v in zip(self.depth_metric_names, compute_depth_errors(gt, pred)):
+            losses[name] = np.array(v.cpu())
+
+    def log_time(self, batch_idx, duration, loss):
+        """movedepth/trainer.py:759-770."""
+        rate = self.opt.batch_size / max(duration, 1e-9)
+        spent = time.time() - getattr(self, "start_time", time.time())
+        print("epoch {:>3} | batch {:>6} | examples/s: {:5.1f} | loss: {:.5f} | time elapsed: {:.0f}s".format(
+            self.epoch, batch_idx, rate, loss, spent))
+
+    def log(self, mode, inputs, outputs, losses):
+        """Scalars go to <log_path>/<mode>/scalars.jsonl (tensorboardX is not a dependency here;
+        movedepth/trainer.py:772-793 writes the same scalars to tensorboard)."""
+        d = os.path.join(self.log_path, mode)
+        os.makedirs(d, exist_ok=True)
+        row = {"step": self.step}
+        for k, v in losses.items():
+            if not k.startswith("_"):
+                row[k] = float(v)
+        with open(os.path.join(d, "scalars.jsonl"), "a") as f:
+            f.write(json.dumps(row) + "\n")
+
+    def save_opts(self):
+        """movedepth/trainer.py:796-805."""
+        d = os.path.join(self.log_path, "models")
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "opt.json"), "w") as f:
+            json.dump(dict(self.opt.__dict__), f, indent=2)
+
+    def save_model(self, save_step=False):
+        """One <name>.pth state_dict per sub-model + adam.pth (movedepth/trainer.py:807-831); rank 0 only."""
+        if self.rank != 0:
+            return
+        tag = "weights_{}".format(self.epoch) if not save_step else "weights_{}_{}".format(self.epoch, self.step)
+        if self.epoch == self.opt.num_epochs - 1 and not save_step:
+            tag = "last"
+        folder = os.path.join(self.log_path, "models", tag)
+        os.makedirs(folder, exist_ok=True)
+        for name, model in self.models.items():
+            sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+            if name == "mono_encoder":
+                sd["height"], sd["width"] = self.opt.height, self.opt.width
+            torch.save(sd, os.path.join(folder, "{}.pth".format(name)))
+        torch.save({"step": self.opt_step, "epoch": self.epoch,
+                    "exp_avg": [a.exp_avg.clone() for a in self.arenas],
+                    "exp_avg_sq": [a.exp_avg_sq.clone() for a in self.arenas]}, os.path.join(folder, "adam.pth"))
+
+    def _load_into(self, name, path):
+        model = self.models[name]
+        have = model.state_dict()
+        sd = torch.load(path, map_location="cpu")
+        have.update({k: v for k, v in sd.items() if k in have})
+        model.load_state_dict(have)
+
+    def load_mono_model(self):
+        """movedepth/trainer.py:833-844."""
+        folder = os.path.expanduser(self.opt.mono_weights_folder)
+        for name in ("pose_encoder", "pose", "mono_encoder", "mono_depth"):
+            self._load_into(name, os.path.join(folder, "{}.pth".format(name)))
+
+    def load_model(self):
+        """movedepth/trainer.py:846-880 (names not in `models`, e.g. the stale defaults, are skipped)."""
+        folder = os.path.expanduser(self.opt.load_weights_folder)
+        assert os.path.isdir(folder), "Cannot find folder {}".format(folder)
+        for name in self.opt.models_to_load:
+            path = os.path.join(folder, "{}.pth".format(name))
+            if name in self.models and os.path.isfile(path):
+                self._load_into(name, path)
+        adam = os.path.join(folder, "adam.pth")
+        if hasattr(self, "arenas") and os.path.isfile(adam):
+            st = torch.load(adam, map_location=self.device)
+            if "exp_avg" in st:
+                for a, m1, m2 in zip(self.arenas, st["exp_avg"], st["exp_avg_sq"]):
+                    a.exp_avg.copy_(m1)
+                    a.exp_avg_sq.copy_(m2)
+                self.opt_step = int(st.get("step", 0))

@@ -1,0 +1,275 @@
+"""GPU parity: every hand-written kernel, called through the C ABI (ctypes), against the CPU oracle
+on the same seeded inputs and against the reference-generated golden vectors.  Tolerances are
+stated per test; the end-to-end bar is 1e-3 relative on fp32 depth (BASELINE.json north_star)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import _cases as C
+from _weights import fill_deterministic
+from oracle import layers as OL
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from movedepth_b200 import ops as _ops
+    _ops._lib.lib()
+    return _ops
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return dict(np.load(os.path.join(GOLD, "ops.npz")))
+
+
+def g(t):
+    return t.to(DEV)
+
+
+def grouped_oracle(c, G=16):
+    ref, src = c["ref"].clone().requires_grad_(True), c["src"].clone().requires_grad_(True)
+    vol = OL.group_correlation(OL.cost_volume(ref, src, c["K"], c["invK"], c["hyps"], c["pose"]), G)   # [B,D,G,h,w]
+    return ref, src, vol
+
+
+# ---------------------------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("name", C.COSTVOL_CASES)
+@pytest.mark.parametrize("flags", [0, 1], ids=["tma", "gather"])
+@pytest.mark.parametrize("layout", [0, 1], ids=["bgdhw", "bdhwg"])
+def test_costvol_grouped_forward_backward(ops, name, flags, layout):
+    """fused warp+gather+group-correlation vs oracle generate_costvol + group mean.
+    atol 2e-4: sampling coordinates differ by <=6e-5 px from the reference's normalise/unnormalise
+    round trip on smooth N(0,1) features."""
+    c = C.case_costvol(name)
+    ref_o, src_o, want = grouped_oracle(c)
+    gv = torch.randn(want.shape, generator=torch.Generator().manual_seed(5))
+    (want * gv).sum().backward()
+    ref, src = g(c["ref"]).requires_grad_(True), g(c["src"]).requires_grad_(True)
+    got = ops.costvol_grouped(ref, src, g(c["K"]), g(c["invK"]), g(c["pose"][:, 0]), prior=g(c["prior"]),
+                              ratio=g(c["ratio"]), layout=layout, flags=flags)
+    assert got.shape == (c["B"], 16, c["D"], c["h"], c["w"])
+    torch.testing.assert_close(got.permute(0, 2, 1, 3, 4).cpu(), want.detach(), atol=2e-4, rtol=1e-4)
+    (got * g(gv).permute(0, 2, 1, 3, 4)).sum().backward()
+    scale = float(ref_o.grad.abs().max())
+    torch.testing.assert_close(ref.grad.cpu(), ref_o.grad, atol=2e-4 * scale, rtol=1e-3)
+    torch.testing.assert_close(src.grad.cpu(), src_o.grad, atol=2e-4 * float(src_o.grad.abs().max()), rtol=1e-3)
+
+
+def test_costvol_grouped_explicit_hypotheses_equal_ratio_form(ops):
+    c = C.case_costvol("forward")
+    args = (g(c["ref"]), g(c["src"]), g(c["K"]), g(c["invK"]), g(c["pose"][:, 0]))
+    a = ops.costvol_grouped(*args, prior=g(c["prior"]), ratio=g(c["ratio"]))
+    b = ops.costvol_grouped(*args, hyps=g(c["hyps"]))
+    torch.testing.assert_close(a, b, atol=1e-6, rtol=1e-6)
+
+
+def test_costvol_grouped_tma_and_gather_routes_agree_bitwise(ops):
+    c = C.case_costvol("sideways", B=3, h=24, w=96, D=24)
+    args = (g(c["ref"]), g(c["src"]), g(c["K"]), g(c["invK"]), g(c["pose"][:, 0]))
+    a = ops.costvol_grouped(*args, prior=g(c["prior"]), ratio=g(c["ratio"]), flags=0)
+    b = ops.costvol_grouped(*args, prior=g(c["prior"]), ratio=g(c["ratio"]), flags=1)
+    assert torch.equal(a, b)
+
+
+def test_costvol_grouped_identity_pose_is_plain_correlation(ops):
+    """SURVEY section 4 known answer: identity pose -> ref*src broadcast over D."""
+    c = C.case_costvol("identity", B=1, h=16, w=64, D=8)
+    got = ops.costvol_grouped(g(c["ref"]), g(c["src"]), g(c["K"]), g(c["invK"]), g(c["pose"][:, 0]),
+                              prior=g(c["prior"]), ratio=g(c["ratio"]))
+    prod = (c["ref"] * c["src"]).view(1, 2, 16, 16, 64).mean(1)                      # group g = {g, g+16}
+    torch.testing.assert_close(got.cpu(), prod[:, :, None].expand(-1, -1, 8, -1, -1), atol=1e-3, rtol=0)
+
+
+def test_costvol_grouped_ragged_shapes(ops):
+    """width not a multiple of the 32-pixel tile, odd height, D not a multiple of the chunk count."""
+    c = C.case_costvol("forward", B=1, h=7, w=45, D=5)
+    _, _, want = grouped_oracle(c)
+    for flags in (0, 1):
+        got = ops.costvol_grouped(g(c["ref"]), g(c["src"]), g(c["K"]), g(c["invK"]), g(c["pose"][:, 0]),
+                                  prior=g(c["prior"]), ratio=g(c["ratio"]), flags=flags)
+        torch.testing.assert_close(got.permute(0, 2, 1, 3, 4).cpu(), want.detach(), atol=2e-4, rtol=1e-4)
+
+
+def test_costvol_grouped_linearity_at_full_size(ops):
+    """Size-independent property at BASELINE config 2 (B=6, 48x160, D=96): the volume is bilinear in
+    (ref, src): V(a*ref, src1+src2) == a*(V(ref,src1) + V(ref,src2))."""
+    c = C.case_costvol("forward", B=6, h=48, w=160, D=96)
+    geo = (g(c["K"]), g(c["invK"]), g(c["pose"][:, 0]))
+    kw = dict(prior=g(c["prior"]), ratio=g(c["ratio"]))
+    ref, s1 = g(c["ref"]), g(c["src"])
+    s2 = g(C.smooth_noise((6, 32, 48, 160), 99))
+    lhs = ops.costvol_grouped(2.0 * ref, s1 + s2, *geo, **kw)
+    rhs = 2.0 * (ops.costvol_grouped(ref, s1, *geo, **kw) + ops.costvol_grouped(ref, s2, *geo, **kw))
+    torch.testing.assert_close(lhs, rhs, atol=1e-4, rtol=1e-4)
+    assert lhs.shape == (6, 16, 96, 48, 160)
+
+
+@pytest.mark.parametrize("name", C.COSTVOL_CASES)
+def test_costvol_full_matches_reference_golden(ops, gold, name):
+    """public generate_costvol layout [B,D,C,h,w] against the reference's own output."""
+    from movedepth_b200 import layers as PL
+    c = C.case_costvol(name)
+    ref, src = g(c["ref"]).requires_grad_(True), g(c["src"]).requires_grad_(True)
+    vol = PL.generate_costvol(ref, src, g(c["K"]), g(c["invK"]), g(c["hyps"]), g(c["pose"]), c["D"], None, None)
+    np.testing.assert_allclose(vol.detach().cpu().numpy(), gold["costvol_%s" % name], atol=2e-4, rtol=1e-4)
+    (vol * g(c["gvol"])).sum().backward()
+    for got, key in ((ref.grad, "gref"), (src.grad, "gsrc")):
+        want = gold["costvol_%s_%s" % (name, key)]
+        np.testing.assert_allclose(got.cpu().numpy(), want, atol=3e-4 * np.abs(want).max(), rtol=1e-3)
+
+
+# ---------------------------------------------------------------------------------------------- K3
+@pytest.mark.parametrize("radius", [1, 2])
+def test_regress_matches_oracle_and_golden(ops, gold, radius):
+    c = C.case_localmax()
+    logits = torch.log(c["prob"])
+    lg = g(logits).requires_grad_(True)
+    prob, ent, depth = ops.regress_depth(lg, g(c["inv_a"]), g(c["inv_b"]), radius, want_prob=True)
+    np.testing.assert_allclose(prob.cpu().numpy(), c["prob"].numpy(), atol=1e-6, rtol=1e-5)
+    np.testing.assert_allclose(ent.detach().cpu().numpy(), gold["entropy"], atol=1e-5, rtol=1e-5)
+    np.testing.assert_allclose(depth.detach().cpu().numpy(), gold["localmax_r%d" % radius], atol=0, rtol=1e-5)
+    # backward vs autograd through the oracle
+    lo = logits.clone().requires_grad_(True)
+    p = torch.softmax(lo, 1)
+    gen = torch.Generator().manual_seed(3)
+    ge, gd = torch.randn(ent.shape, generator=gen), torch.randn(depth.shape, generator=gen)
+    ((OL.entropy(p, 1, True) * ge).sum() + (OL.localmax(p, radius, c["D"], c["inv_a"], c["inv_b"]) * gd).sum()).backward()
+    ((ent * g(ge)).sum() + (depth * g(gd)).sum()).backward()
+    torch.testing.assert_close(lg.grad.cpu(), lo.grad, atol=1e-5 * float(lo.grad.abs().max()), rtol=1e-3)
+
+
+def test_localmax_public_signature_and_known_answer(ops, gold):
+    from movedepth_b200 import layers as PL
+    c = C.case_localmax()
+    got = PL.localmax(g(c["onehot"]), 1, c["D"], g(c["inv_a"]), g(c["inv_b"]))
+    np.testing.assert_allclose(got.cpu().numpy(), gold["localmax_onehot"], atol=0, rtol=1e-5)
+    # one-hot at i picks hypothesis D-1-i
+    D = 16
+    hyp = OL.depth_hypotheses(torch.full((1, 1, 1, 1), 10.0), D, 0.3)
+    for i, want in ((0, 10 / 1.3), (5, 8.9041), (15, 13.0)):
+        p = torch.zeros(1, D, 1, 1)
+        p[0, i] = 1
+        d = PL.localmax(g(p), 1, D, g(1 / hyp[:, -1]), g(1 / hyp[:, 0]))
+        assert abs(float(d) - want) < 1e-3
+
+
+def test_regress_window_clamps_at_both_ends(ops):
+    """argmax at index 0 / D-1: clamped duplicates are counted twice (reference behaviour)."""
+    D = 6
+    for top in (0, D - 1):
+        logits = torch.randn(1, D, 2, 3, generator=torch.Generator().manual_seed(top))
+        logits[:, top] += 6.0
+        inv_a, inv_b = torch.full((1, 2, 3), 0.1), torch.full((1, 2, 3), 0.4)
+        lg = g(logits).requires_grad_(True)
+        _, _, depth = ops.regress_depth(lg, g(inv_a), g(inv_b), 2)
+        lo = logits.clone().requires_grad_(True)
+        want = OL.localmax(torch.softmax(lo, 1), 2, D, inv_a, inv_b)
+        torch.testing.assert_close(depth.cpu(), want.detach(), atol=0, rtol=1e-5)
+        want.sum().backward()
+        depth.sum().backward()
+        torch.testing.assert_close(lg.grad.cpu(), lo.grad, atol=1e-6, rtol=1e-3)
+
+
+# ---------------------------------------------------------------------------------------------- K4
+def test_convex_upsample_matches_golden_and_autograd(ops, gold):
+    c = C.case_convex()
+    d, m = g(c["depth"]).requires_grad_(True), g(c["mask"]).requires_grad_(True)
+    up = ops.convex_upsample(d, m, 2)
+    np.testing.assert_allclose(up.detach().cpu().numpy(), gold["convex_up"], atol=1e-5, rtol=1e-5)
+    do, mo = c["depth"].clone().requires_grad_(True), c["mask"].clone().requires_grad_(True)
+    gu = torch.randn(up.shape, generator=torch.Generator().manual_seed(2))
+    (OL.convex_upsample(do, mo, 2) * gu).sum().backward()
+    (up * g(gu)).sum().backward()
+    torch.testing.assert_close(d.grad.cpu(), do.grad, atol=1e-5, rtol=1e-4)
+    torch.testing.assert_close(m.grad.cpu(), mo.grad, atol=1e-5, rtol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------- Adam
+def test_fused_adam_matches_torch_adam(ops):
+    gen = torch.Generator().manual_seed(7)
+    n = 10007                                           # not a multiple of 4: exercises the tail
+    p0 = torch.randn(n, generator=gen)
+    want = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([want], lr=2e-4)
+    p, m, v = g(p0.clone()), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    for step in range(1, 4):
+        grad = torch.randn(n, generator=gen)
+        want.grad = grad.clone()
+        opt.step()
+        ops.adam_step(p, g(grad * 2), m, v, step, 2e-4, grad_scale=0.5)
+        torch.testing.assert_close(p.cpu(), want.detach(), atol=1e-7, rtol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------- whole step
+def _trainer(cfg, precision="fp32"):
+    from movedepth_b200.options import MonodepthOptions
+    from movedepth_b200.trainer import Trainer
+    argv = ["--height", str(cfg["H"]), "--width", str(cfg["W"]), "--num_depth_bins", str(cfg["D"]), "--batch_size",
+            str(cfg["B"]), "--res_arch", str(cfg.get("arch", 18)), "--weights_init", "scratch", "--convex_up",
+            "--learning_rate", "2e-4", "--b200_conv_precision", precision, "--log_dir", "/tmp/mvd_test",
+            "--frame_ids"] + [str(f) for f in cfg["frame_ids"]]
+    tr = Trainer(MonodepthOptions().parse(argv))
+    for k, m in tr.models.items():
+        fill_deterministic(m, salt=k + "/")
+    tr.epoch = cfg["epoch"]
+    return tr
+
+
+@pytest.mark.parametrize("name", list(C.STEP_CASES))
+def test_whole_step_matches_reference_golden(name):
+    """Trainer.process_batch + backward + fused Adam on the GPU vs the REFERENCE's outputs for the same
+    weights and inputs (tests/golden/step_*.npz).  fp32 convolutions.  Depth maps: fraction of pixels
+    within 1e-3 relative (argmax ties flip under 1-ulp noise)."""
+    cfg = C.STEP_CASES[name]
+    gold = dict(np.load(os.path.join(GOLD, "step_%s.npz" % name)))
+    tr = _trainer(cfg)
+    inputs, noise, xy = C.step_inputs(cfg)
+    out, losses = tr.train_step(dict(inputs), noise=noise, mask_xy=xy)
+    torch.cuda.synchronize()
+
+    def close(a, b, atol, rtol):
+        np.testing.assert_allclose(a.detach().float().cpu().numpy().reshape(b.shape), b, atol=atol, rtol=rtol)
+
+    for s in range(4):
+        close(out[("disp", s)], gold["disp%d" % s], 1e-5, 1e-4)
+    for f in cfg["frame_ids"][1:]:
+        close(out[("cam_T_cam", 0, f)], gold["cam_T_cam_%d" % f], 1e-6, 1e-4)
+        close(out[("color", f, 0)], gold["warped_%d_s0" % f], 1e-4, 1e-4)
+    close(out["cost_volume"].permute(0, 2, 1, 3, 4), gold["cost_volume"], 2e-4, 1e-3)
+    for key in ("depth_mvs", "masked_depth", "fused_depth"):
+        got = out[key].detach().cpu().numpy().reshape(gold[key].shape)
+        rel = np.abs(got - gold[key]) / np.abs(gold[key])
+        assert (rel < 1e-3).mean() > 0.99, (key, float((rel < 1e-3).mean()))
+    close(out["trust_mono_mask"], gold["trust_mono_mask"], 1e-4, 1e-3)
+    for key in gold:
+        if key.startswith("loss/"):
+            k = key[5:]
+            # the masked-consistency term (and hence the total) sums |depth_aug - depth_mvs| over pixels whose
+            # argmax can flip under 1-ulp conv noise: looser bound there
+            loose = k in ("masked_loss", "loss")
+            close(losses[k], gold[key], 1e-4, 5e-2 if loose else 2e-3)
+    named = {k: dict(m.named_parameters()) for k, m in tr.models.items()}
+    for k in tr.models:
+        sq = sum(float((p.grad.double() ** 2).sum()) for p in tr.models[k].parameters())
+        tol = 1e-2 if k in ("mono_encoder", "mono_depth", "pose_encoder", "pose") else 0.15
+        assert abs(sq ** 0.5 - gold["gradnorm/" + k]) <= tol * gold["gradnorm/" + k] + 1e-9, (k, sq ** 0.5, gold["gradnorm/" + k])
+    for mk, pk in C.GRAD_PROBES:
+        if mk in ("pose", "mono_depth"):
+            gr = gold["grad/%s/%s" % (mk, pk)]
+            close(named[mk][pk].grad, gr, 1e-2 * np.abs(gr).max() + 1e-9, 1e-2)
+            close(named[mk][pk], gold["adam/%s/%s" % (mk, pk)], 1e-5, 1e-4)
+
+
+def test_step_runs_under_mixed_precision_and_loss_is_close():
+    cfg = C.STEP_CASES["r18_2f"]
+    gold = dict(np.load(os.path.join(GOLD, "step_r18_2f.npz")))
+    tr = _trainer(cfg, "mixed")
+    inputs, noise, xy = C.step_inputs(cfg)
+    _, losses = tr.train_step(dict(inputs), noise=noise, mask_xy=xy)
+    assert abs(float(losses["loss/0"]) - float(gold["loss/loss/0"])) < 5e-3 * abs(float(gold["loss/loss/0"]))

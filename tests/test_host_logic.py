@@ -1,0 +1,184 @@
+"""Host-side logic of the product package, on CPU: checkpoint key layout, parameter counts, the
+plain-tensor glue in layers.py against the oracle, option parsing, flat arenas, and the
+world_size-2 gradient exchange (gloo)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import _cases as C
+from oracle import layers as OL
+from oracle import networks as ON
+from movedepth_b200 import layers as PL
+from movedepth_b200 import networks as PN
+from movedepth_b200.options import MonodepthOptions
+from movedepth_b200.trainer import FlatArena, SyntheticKITTI, kitti_intrinsics
+
+
+def _pairs():
+    enc_o, enc_p = ON.ResnetEncoder(18, False), PN.ResnetEncoder(18, False)
+    yield "mono_encoder", enc_o, enc_p, 11176512
+    yield "mono_depth", ON.DepthDecoder(enc_o.num_ch_enc, range(4)), PN.DepthDecoder(enc_p.num_ch_enc, range(4)), 3152724
+    yield "pose_encoder", ON.ResnetEncoder(18, False, 2), PN.ResnetEncoder(18, False, num_input_images=2), 11185920
+    yield "pose", ON.PoseDecoder(enc_o.num_ch_enc, 1, 2), PN.PoseDecoder(enc_p.num_ch_enc, 1, 2), 1314572
+    yield "mvs_encoder", ON.FPN4(8, 2), PN.FPN4(base_channels=8, scale=2), 186008
+    yield "reg3d", ON.Reg3d(16, 16, 3), PN.reg3d(16, 16, 3), 1169712
+    yield "mask_cnn", ON.UncertNet(), PN.UncertNet(), 752
+    yield "up", ON.ConvexUpsampleLayer(32, 2), PL.convex_upsample_layer(32, 2), 27648
+
+
+def test_state_dict_keys_and_param_counts_match_reference_layout():
+    for name, o, p, count in _pairs():
+        so, sp = o.state_dict(), p.state_dict()
+        assert list(so.keys()) == list(sp.keys()), name
+        assert all(so[k].shape == sp[k].shape for k in so), name
+        assert sum(t.numel() for t in p.parameters()) == count, name
+
+
+def test_r50_encoder_channels():
+    e = PN.ResnetEncoder(50, False)
+    assert list(e.num_ch_enc) == [64, 256, 512, 1024, 2048]
+    assert sum(t.numel() for t in e.parameters()) == 23508032
+
+
+def test_networks_forward_equal_oracle_on_cpu():
+    torch.manual_seed(0)
+    x = torch.rand(1, 3, 64, 96)
+    for name, o, p, _ in _pairs():
+        p.load_state_dict(o.state_dict())
+        o.eval(), p.eval()
+    pairs = {n: (o, p) for n, o, p, _ in _pairs()}
+    o, p = ON.FPN4(8, 2).eval(), PN.FPN4(8, 2).eval()
+    p.load_state_dict(o.state_dict())
+    for a, b in zip(o(x), p(x)):
+        assert torch.equal(a, b)
+    o, p = ON.Reg3d(16, 16, 3).eval(), PN.reg3d(16, 16, 3).eval()
+    p.load_state_dict(o.state_dict())
+    v = torch.rand(1, 8, 16, 16, 24)
+    assert torch.equal(o(v), p(v))
+    assert torch.equal(o(v), p.forward_volume(v.permute(0, 2, 1, 3, 4)))
+    o, p = ON.UncertNet().eval(), PN.UncertNet().eval()
+    p.load_state_dict(o.state_dict())
+    e = torch.rand(1, 1, 16, 24)
+    assert torch.equal(o(e), p(e))
+    eo, ep = ON.ResnetEncoder(18, False).eval(), PN.ResnetEncoder(18, False).eval()
+    ep.load_state_dict(eo.state_dict())
+    do, dp = ON.DepthDecoder(eo.num_ch_enc).eval(), PN.DepthDecoder(ep.num_ch_enc).eval()
+    dp.load_state_dict(do.state_dict())
+    a, b = do(eo(x)), dp(ep(x))
+    for s in range(4):
+        assert torch.equal(a[("disp", s)], b[("disp", s)])
+    po, pp = ON.PoseDecoder(eo.num_ch_enc, 1, 2).eval(), PN.PoseDecoder(ep.num_ch_enc, 1, 2).eval()
+    pp.load_state_dict(po.state_dict())
+    for u, v in zip(po([eo(x)]), pp([ep(x)])):
+        assert torch.equal(u, v)
+
+
+def test_pose_and_disparity_glue_match_oracle():
+    c = C.case_pose()
+    for inv in (False, True):
+        a = OL.transformation_from_parameters(c["aa"], c["tr"], inv)
+        b = PL.transformation_from_parameters(c["aa"], c["tr"], inv)
+        torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-7)
+    d = torch.rand(2, 1, 4, 4)
+    for a, b in zip(OL.disp_to_depth(d, 0.1, 100.0), PL.disp_to_depth(d, 0.1, 100.0)):
+        assert torch.equal(a, b)
+
+
+def test_hypothesis_schedules_and_separable_ratios():
+    c = C.case_hypotheses()
+    for kind in ("inverse", "linear"):
+        assert torch.equal(OL.depth_hypotheses(c["prior"], c["D"], c["fac"], kind=kind),
+                           PL.schedule_depth_rangev2(c["prior"], c["D"], c["fac"], kind))
+    want = OL.depth_hypotheses(c["prior"], c["D"], c["fac"], z_trans=c["z_trans"])
+    assert torch.equal(want, PL.schedule_depth_range_zv2(c["prior"], c["D"], c["fac"], c["z_trans"]))
+    s = (c["fac"] * c["z_trans"]).reshape(-1)
+    sep = c["prior"] * PL.hypothesis_ratios(c["D"], s, "cpu").view(2, c["D"], 1, 1)
+    torch.testing.assert_close(sep, want, rtol=2e-6, atol=0)
+
+
+def test_ssim_smoothness_projection_modules_match_oracle():
+    c = C.case_images()
+    torch.testing.assert_close(PL.SSIM()(c["x"], c["y"]), OL.ssim(c["x"], c["y"]), rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(PL.get_smooth_loss(c["disp"], c["x"]), OL.smooth_loss(c["disp"], c["x"]), rtol=1e-6, atol=0)
+    w = C.case_warp()
+    pts = PL.BackprojectDepth(w["B"], w["H"], w["W"])(w["depth"], w["invK"])
+    torch.testing.assert_close(pts, OL.backproject(w["depth"], w["invK"], w["H"], w["W"]), rtol=1e-6, atol=1e-6)
+    grid = PL.Project3D(w["B"], w["H"], w["W"])(pts, w["K"], w["T"])
+    torch.testing.assert_close(grid, OL.project(pts, w["K"], w["T"], w["H"], w["W"]), rtol=1e-5, atol=1e-6)
+
+
+def test_options_keep_reference_flags_and_defaults():
+    o = MonodepthOptions().parse([])
+    assert (o.height, o.width, o.num_depth_bins, o.reg3d_c, o.prior_scale, o.norm_radius) == (192, 640, 16, 16, 2, 1)
+    assert o.frame_ids == [0, -1, 1] and o.matching_ids == [0, -1] and o.scales == [0, 1, 2, 3]
+    assert (o.depth_bin_fac, o.z_scale, o.ztrans_start_epc, o.ssim_lw, o.mask_lw) == (0.3, 30, 8, 0.85, 10)
+    assert o.learning_rate == 1e-4 and o.scheduler_step_size == 15 and o.batch_size == 12
+    o = MonodepthOptions().parse("--frame_ids 0 -1 --convex_up --ddp --local_rank 3 --learning_rate 2e-4".split())
+    assert o.frame_ids == [0, -1] and o.convex_up and o.ddp and o.local_rank == 3 and o.learning_rate == 2e-4
+
+
+def test_product_refuses_to_run_without_cuda():
+    from movedepth_b200.trainer import Trainer
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    o = MonodepthOptions().parse(["--frame_ids", "0", "-1", "--weights_init", "scratch", "--no_cuda"])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        Trainer(o)
+    from movedepth_b200 import ops
+    c = C.case_convex()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ops.convex_upsample(c["depth"], c["mask"], 2)
+
+
+def test_flat_arena_rehomes_parameters_and_grads():
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 3), torch.nn.Linear(3, 2))
+    before = [p.detach().clone() for p in net.parameters()]
+    arena = FlatArena(net.parameters(), "cpu")
+    assert arena.numel % 4 == 0 and all(o % 4 == 0 for o in arena.offsets)
+    for p, b in zip(net.parameters(), before):
+        assert torch.equal(p, b) and p.data_ptr() >= arena.data.data_ptr()
+    net(torch.rand(4, 5)).sum().backward()
+    g = torch.cat([p.grad.reshape(-1) for p in net.parameters()])
+    assert float(arena.grad.abs().sum()) == pytest.approx(float(g.abs().sum()), rel=1e-6)
+    arena.data.mul_(0)
+    assert all(float(p.abs().sum()) == 0 for p in net.parameters())
+
+
+def test_synthetic_batches_follow_the_item_schema():
+    o = MonodepthOptions().parse(["--frame_ids", "0", "-1", "--height", "64", "--width", "96"])
+    item = next(iter(SyntheticKITTI(o, 2, 1, pin=False)))
+    for f in (0, -1):
+        for s in range(4):
+            assert item[("color", f, s)].shape == (2, 3, 64 >> s, 96 >> s)
+            assert item[("color_aug", f, s)].shape == (2, 3, 64 >> s, 96 >> s)
+    K, iK = kitti_intrinsics(2, 16, 24)
+    torch.testing.assert_close(item[("K", 2)], K)
+    torch.testing.assert_close(torch.matmul(K, iK), torch.eye(4).repeat(2, 1, 1), atol=1e-5, rtol=0)
+
+
+def _exchange_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Linear(6, 4)
+    arena = FlatArena(net.parameters(), "cpu")
+    x = torch.full((3, 6), float(rank + 1))
+    net(x).sum().backward()
+    work = dist.all_reduce(arena.grad, async_op=True)     # the trainer's exchange: SUM, scaled in the Adam kernel
+    work.wait()
+    torch.save(arena.grad / world, os.path.join(out, "g%d.pt" % rank))
+    dist.destroy_process_group()
+
+
+def test_gradient_exchange_world_size_2_gloo(tmp_path):
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_exchange_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    g0, g1 = torch.load(tmp_path / "g0.pt"), torch.load(tmp_path / "g1.pt")
+    assert torch.equal(g0, g1)
+    # mean over ranks of d/dW sum(Wx+b): x summed over the 3 rows -> 3*(1+2)/2 = 4.5 per weight, 3 per bias
+    assert torch.allclose(g0[:24], torch.full((24,), 4.5)) and torch.allclose(g0[24:28], torch.full((4,), 3.0))
