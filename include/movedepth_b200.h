@@ -107,6 +107,25 @@ int mvd_convex_up_bwd(const float* depth, const float* mask, const float* gout, 
                       float* gmask, int B, int h, int w, int f, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * K5+K6  photometric reprojection loss of ONE source frame.
+ * Replaces: BackprojectDepth/Project3D + F.grid_sample(border) movedepth/trainer.py:501-507,
+ * 519-529, 575-580; SSIM layers.py:646-677; compute_reprojection_loss trainer.py:535-550.
+ *   depth : [B,H,W];  src, tgt : [B,3,H,W];  K, invK, T : [B,4,4]
+ *   warped (nullable) : [B,3,H,W] the border-padded bilinear warp of src
+ *   loss : [B,H,W] = ssim_w * mean_c SSIM(warped,tgt) + (1-ssim_w) * mean_c |tgt-warped|
+ *   (ssim_w == 0 -> L1 only).  identity != 0: skip the warp, compare src with tgt directly.
+ * ------------------------------------------------------------------------------------- */
+int mvd_photometric_fwd(const float* depth, const float* src, const float* tgt, const float* K,
+                        const float* invK, const float* T, float* warped, float* loss, int B, int H,
+                        int W, float ssim_w, int identity, void* stream);
+/* Backward: gloss [B,H,W] -> gdepth [B,H,W] (OVERWRITTEN) and, when gP != NULL, gP [B,3,4]
+ * (OVERWRITTEN) = d loss / d (K @ T)[:3,:], from which d loss / d T = K[:3,:]^T @ gP.
+ * Needs the forward's `warped`. */
+int mvd_photometric_bwd(const float* gloss, const float* depth, const float* src, const float* tgt,
+                        const float* warped, const float* K, const float* invK, const float* T,
+                        float* gdepth, float* gP, int B, int H, int W, float ssim_w, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Fused multi-tensor Adam on a flat fp32 arena (torch.optim.Adam semantics, no amsgrad, no
  * weight decay; replaces optimizer.step() movedepth/trainer.py:137-141, 272).
  *   step_size = lr / (1 - beta1^t);  bias2 = sqrt(1 - beta2^t)

@@ -225,3 +225,63 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999
                                   bias2, grad_scale, _stream())
     _lib.check(rc, "mvd_adam_step")
     launch_counter["n"] += 1
+
+
+# ------------------------------------------------------------------------------------- K5 + K6
+class _Photometric(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, src, tgt, K, invK, T, ssim_w):
+        B, _, H, W = src.shape
+        depth = _f32(depth).reshape(B, H, W).contiguous()
+        src, tgt = _f32(src).contiguous(), _f32(tgt).contiguous()
+        K, invK, Tm = _mat(K, B), _mat(invK, B), _mat(T, B)
+        warped = torch.empty_like(src)
+        loss = torch.empty((B, 1, H, W), device=src.device, dtype=torch.float32)
+        rc = _lib.lib().mvd_photometric_fwd(_p(depth), _p(src), _p(tgt), _p(K), _p(invK), _p(Tm), _p(warped), _p(loss), B, H,
+                                            W, float(ssim_w), 0, _stream())
+        _lib.check(rc, "mvd_photometric_fwd")
+        launch_counter["n"] += 1
+        ctx.save_for_backward(depth, src, tgt, warped, K, invK, Tm)
+        ctx.ssim_w = float(ssim_w)
+        ctx.depth_shape = None
+        ctx.mark_non_differentiable(warped)
+        return loss, warped
+
+    @staticmethod
+    def backward(ctx, gloss, _gwarped):
+        depth, src, tgt, warped, K, invK, Tm = ctx.saved_tensors
+        B, _, H, W = src.shape
+        gloss = _f32(gloss).contiguous()
+        need_T = ctx.needs_input_grad[5]
+        gdepth = torch.empty_like(depth)
+        gP = torch.empty((B, 3, 4), device=src.device, dtype=torch.float32) if need_T else None
+        rc = _lib.lib().mvd_photometric_bwd(_p(gloss), _p(depth), _p(src), _p(tgt), _p(warped), _p(K), _p(invK), _p(Tm),
+                                            _p(gdepth), _p(gP), B, H, W, ctx.ssim_w, _stream())
+        _lib.check(rc, "mvd_photometric_bwd")
+        launch_counter["n"] += 2 if need_T else 1
+        gT = None
+        if need_T:                                   # P = K @ T  ->  dL/dT = K^T[:, :3] @ dL/dP  (4x3 @ 3x4, glue)
+            gT = torch.matmul(K[:, :3, :].transpose(1, 2), gP)
+        return gdepth, None, None, None, None, gT, None
+
+
+def photometric_loss(depth, src, tgt, K, invK, T, ssim_w=0.85):
+    """Warp `src` into the target view with per-pixel `depth` and compare with `tgt`.
+    Returns (loss [B,1,H,W], warped [B,3,H,W]); gradients flow to depth (same shape as given) and T.
+    Reference: movedepth/trainer.py:519-529 + 535-550, layers.py:646-677."""
+    shape = depth.shape
+    loss, warped = _Photometric.apply(depth.reshape(shape[0], *shape[-2:]), src, tgt, K, invK, T, ssim_w)
+    return loss, warped
+
+
+def photometric_identity(src, tgt, ssim_w=0.85):
+    """SSIM/L1 error between two images without any warp (the auto-masking identity term,
+    movedepth/trainer.py:689-693).  No gradient (both inputs are images)."""
+    B, _, H, W = src.shape
+    src, tgt = _f32(src.detach()).contiguous(), _f32(tgt.detach()).contiguous()
+    loss = torch.empty((B, 1, H, W), device=src.device, dtype=torch.float32)
+    rc = _lib.lib().mvd_photometric_fwd(_p(None), _p(src), _p(tgt), _p(None), _p(None), _p(None), _p(None), _p(loss), B, H, W,
+                                        float(ssim_w), 1, _stream())
+    _lib.check(rc, "mvd_photometric_fwd(identity)")
+    launch_counter["n"] += 1
+    return loss
