@@ -47,6 +47,27 @@ __device__ __forceinline__ void load_geo(PhGeo* geo, const float* K, const float
     }
 }
 
+
+// Window statistics -> SSIM numerator / denominator factors.  Products are rounded explicitly (no FMA
+// contraction asymmetry) so that x == y gives n == d bit for bit, like the reference's pooled form.
+struct SsimTerms {
+    float mx, my, A1, A2, B1, B2;
+};
+__device__ __forceinline__ SsimTerms ssim_terms(float sx, float sy, float sxx, float syy, float sxy) {
+    const float k9 = 1.f / 9.f;
+    SsimTerms t;
+    t.mx = __fmul_rn(sx, k9);
+    t.my = __fmul_rn(sy, k9);
+    const float mxx = __fmul_rn(t.mx, t.mx), myy = __fmul_rn(t.my, t.my), mxy = __fmul_rn(t.mx, t.my);
+    const float vx = __fsub_rn(__fmul_rn(sxx, k9), mxx), vy = __fsub_rn(__fmul_rn(syy, k9), myy);
+    const float cxy = __fsub_rn(__fmul_rn(sxy, k9), mxy);
+    t.A1 = __fadd_rn(__fmul_rn(2.f, mxy), SSIM_C1);
+    t.A2 = __fadd_rn(__fmul_rn(2.f, cxy), SSIM_C2);
+    t.B1 = __fadd_rn(__fadd_rn(mxx, myy), SSIM_C1);
+    t.B2 = __fadd_rn(__fadd_rn(vx, vy), SSIM_C2);
+    return t;
+}
+
 struct WarpPt {
     float u, v;            // clamped source coordinates
     float X[3];            // camera point depth * ray
@@ -192,11 +213,8 @@ photometric_fwd_kernel(const float* __restrict__ depth, const float* __restrict_
                     syy = fmaf(bb, bb, syy);
                     sxy = fmaf(a, bb, sxy);
                 }
-            const float k9 = 1.f / 9.f;
-            const float mx = sx_ * k9, my = sy_ * k9;
-            const float vx = sxx * k9 - mx * mx, vy = syy * k9 - my * my, cxy = sxy * k9 - mx * my;
-            const float n = (2.f * mx * my + SSIM_C1) * (2.f * cxy + SSIM_C2);
-            const float d = (mx * mx + my * my + SSIM_C1) * (vx + vy + SSIM_C2);
+            const SsimTerms st = ssim_terms(sx_, sy_, sxx, syy, sxy);
+            const float n = __fmul_rn(st.A1, st.A2), d = __fmul_rn(st.B1, st.B2);
             ss += fminf(fmaxf((1.f - n / d) * 0.5f, 0.f), 1.f);
         }
     }
@@ -274,11 +292,9 @@ photometric_bwd_kernel(const float* __restrict__ gloss, const float* __restrict_
                             sxy = fmaf(a, bb, sxy);
                         }
                     const float k9 = 1.f / 9.f;
-                    const float mx = sx_ * k9, my = sy_ * k9;
-                    const float vx = sxx * k9 - mx * mx, vy = syy * k9 - my * my, cxy = sxy * k9 - mx * my;
-                    const float A1 = 2.f * mx * my + SSIM_C1, A2 = 2.f * cxy + SSIM_C2;
-                    const float B1 = mx * mx + my * my + SSIM_C1, B2 = vx + vy + SSIM_C2;
-                    const float n = A1 * A2, d = B1 * B2;
+                    const SsimTerms st = ssim_terms(sx_, sy_, sxx, syy, sxy);
+                    const float mx = st.mx, my = st.my, A1 = st.A1, A2 = st.A2, B1 = st.B1, B2 = st.B2;
+                    const float n = __fmul_rn(A1, A2), d = __fmul_rn(B1, B2);
                     const float val = (1.f - n / d) * 0.5f;
                     if (val >= 0.f && val <= 1.f) {          // clamp passes gradient on the closed interval
                         const float inv_d = 1.f / d, k = gl * k9 * inv_d;

