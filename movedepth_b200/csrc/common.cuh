@@ -95,5 +95,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 // box = {32 channels, box_w, box_h, 1}; out-of-bounds elements are zero-filled, which is the
 // `padding_mode='zeros'` of the reference's grid_sample.
 int make_nhwc32_tensor_map(CUtensorMap* map, const float* base, int B, int h, int w, int box_w, int box_h);
+// generic fp32 tiled descriptor, no swizzle; dims/box innermost first, strides (bytes) for dims 1..rank-1
+int make_f32_tensor_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                        const uint32_t* box);
 
 }  // namespace mvd

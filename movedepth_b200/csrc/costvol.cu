@@ -55,6 +55,7 @@ struct CvArgs {
     int B, h, w, D;
     int layout;
     int use_tma;
+    int tma_store;
     int tiles_x, tiles_y, num_tiles;
     int DC;              // hypotheses per chunk
 };
@@ -69,7 +70,9 @@ struct CvSmem {
     static constexpr int OFF_GEO = OFF_RATIO + CV_MAXD * 4;
     static constexpr int OFF_RED = OFF_GEO + 32 * 4;
     static constexpr int OFF_BAR = OFF_RED + 2 * CV_WARPS * 4 * 4;
-    static constexpr int TOTAL = OFF_BAR + 16;
+    static constexpr int OFF_STAGE = (OFF_BAR + 16 + 127) / 128 * 128;      // per-warp double-buffered output rows
+    static constexpr int STAGE_BYTES = CV_WARPS * 2 * CV_G * CV_TW * 4;
+    static constexpr int TOTAL = OFF_STAGE + STAGE_BYTES;
     static constexpr int ALLOC = TOTAL + 1024;   // slack for manual 1024 B alignment
 };
 
@@ -286,83 +289,185 @@ __device__ __forceinline__ bool cell_in_box(const PixelCtx& c, int ix, int iy, i
 }
 
 // ------------------------------------------------------------------------------------------ forward
+// Packed fp32 math (Blackwell FFMA2: two fp32 FMAs per instruction on a 64-bit register pair).
+__device__ __forceinline__ uint64_t pk2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpk2(uint64_t v, float& a, float& b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ ulonglong2 lds128p(const unsigned char* base, int pix, int j) {
+    return *reinterpret_cast<const ulonglong2*>(base + pix * 128 + ((j ^ (pix & 7)) << 4));
+}
+
+// 5-D TMA tiled store shared::cta -> global (SASS: UTMASTG), bulk-group completion.
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3,
+                                             int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Per-tap group correlations of one bilinear cell, packed: P2[t][k] = (P_t[2k], P_t[2k+1]),
+// P_t[g] = 1/2 (ref[g] src_t[g] + ref[g+16] src_t[g+16]).
+__device__ __forceinline__ void load_cell(const CvArgs& a, const PixelCtx& c, const unsigned char* smem, int ref_pix,
+                                          int cx, int cy, uint64_t (&P2)[4][8]) {
+    const unsigned char* sbox = smem + CvSmem::OFF_SRC;
+    const unsigned char* rbox = smem + CvSmem::OFF_REF;
+    int rel;
+    const bool in_box = cell_in_box(c, cx, cy, rel);
+    const uint64_t half2 = pk2(0.5f, 0.5f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        ulonglong2 rl = lds128p(rbox, ref_pix, j), rh = lds128p(rbox, ref_pix, j + 4);
+        rl.x = mul2(rl.x, half2);
+        rl.y = mul2(rl.y, half2);
+        rh.x = mul2(rh.x, half2);
+        rh.y = mul2(rh.y, half2);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int px = cx + (t & 1), py = cy + (t >> 1);
+            ulonglong2 lo, hi;
+            if (in_box) {
+                const int rp = rel + (t & 1) + (t >> 1) * CV_BOX_W;
+                lo = lds128p(sbox, rp, j);
+                hi = lds128p(sbox, rp, j + 4);
+            } else if (px >= 0 && px < a.w && py >= 0 && py < a.h) {
+                const ulonglong2* g =
+                    reinterpret_cast<const ulonglong2*>(a.src + (static_cast<size_t>(c.b * a.h + py) * a.w + px) * CV_C);
+                lo = __ldg(g + j);
+                hi = __ldg(g + j + 4);
+            } else {
+                lo = make_ulonglong2(0ull, 0ull);
+                hi = lo;
+            }
+            P2[t][2 * j] = fma2(rl.x, lo.x, mul2(rh.x, hi.x));
+            P2[t][2 * j + 1] = fma2(rl.y, lo.y, mul2(rh.y, hi.y));
+        }
+    }
+}
+
+constexpr int CV_STAGE_BYTES = CV_G * CV_TW * 4;   // one hypothesis of one tile row: 16 groups x 32 pixels
+
 __global__ void __launch_bounds__(CV_THREADS, 2)
 costvol_grouped_fwd_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_ref,
-                           const CvArgs a) {
+                           const __grid_constant__ CUtensorMap map_out, const CvArgs a) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + CvSmem::OFF_BAR);
     const float* ratio_s = reinterpret_cast<const float*>(smem + CvSmem::OFF_RATIO);
-    const unsigned char* sbox = smem + CvSmem::OFF_SRC;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* stage = reinterpret_cast<float*>(smem + CvSmem::OFF_STAGE + warp * 2 * CV_STAGE_BYTES);
     if (tid == 0) {
         tma_prefetch_desc(&map_src);
         tma_prefetch_desc(&map_ref);
+        tma_prefetch_desc(&map_out);
         mbar_init(bar, 1);
         mbar_fence_init();
     }
     uint32_t phase = 0;
-    const size_t hw = static_cast<size_t>(a.h) * a.w;
+    const int hw = a.h * a.w;
     int iter = 0;
+    uint32_t sbuf = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++iter) {
         PixelCtx c;
         tile_prologue(a, &map_src, &map_ref, smem, tile, iter, phase, c);
-        if (!c.active) continue;
+        if (c.y >= a.h || c.d0 >= c.d1) continue;            // warp-uniform
+        const bool lane_ok = c.x < a.w;
+        const int ref_pix = (warp % CV_R) * CV_TW + lane;
+        const int tx0 = c.x - lane;
 
-        float rh[CV_C];
-        load_half_ref(smem, warp, lane, rh);
-        float P[4][CV_G];
+        uint64_t P2[4][8];
 #pragma unroll
         for (int t = 0; t < 4; ++t)
 #pragma unroll
-            for (int g = 0; g < CV_G; ++g) P[t][g] = 0.f;
+            for (int k = 0; k < 8; ++k) P2[t][k] = 0ull;
         int cx = INT_MIN, cy = INT_MIN;
 
-        const size_t pix = static_cast<size_t>(c.y) * a.w + c.x;
-        const float prior_v = (a.hyps == nullptr) ? __ldg(a.prior + c.b * hw + pix) : 0.f;
+        const int pix = c.y * a.w + (lane_ok ? c.x : a.w - 1);
+        const float prior_v = (a.hyps == nullptr) ? __ldg(a.prior + static_cast<size_t>(c.b) * hw + pix) : 0.f;
         const float* hp = (a.hyps != nullptr) ? a.hyps + static_cast<size_t>(c.b) * a.D * hw + pix : nullptr;
+        float* obase = a.out + static_cast<size_t>(c.b) * CV_G * a.D * hw;
 
         for (int d = c.d0; d < c.d1; ++d) {
-            const float depth = hp ? __ldg(hp + d * hw) : prior_v * ratio_s[d];
+            const float depth = hp ? __ldg(hp + static_cast<size_t>(d) * hw) : prior_v * ratio_s[d];
             float u, v, pz;
             project_uv(c, depth, u, v, pz);
             const Bilinear s = bilinear_at(a, u, v);
             if (s.ok && (s.ix != cx || s.iy != cy)) {
                 cx = s.ix;
                 cy = s.iy;
-                int rel;
-                const bool in_box = cell_in_box(c, cx, cy, rel);
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    const int px = cx + (t & 1), py = cy + (t >> 1);
-                    const int rp = rel + (t & 1) + (t >> 1) * CV_BOX_W;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float4 lo, hi;
-                        fetch_tap(a, c, sbox, in_box, rp, px, py, j, lo, hi);
-                        P[t][4 * j + 0] = fmaf(rh[4 * j + 0], lo.x, rh[16 + 4 * j + 0] * hi.x);
-                        P[t][4 * j + 1] = fmaf(rh[4 * j + 1], lo.y, rh[16 + 4 * j + 1] * hi.y);
-                        P[t][4 * j + 2] = fmaf(rh[4 * j + 2], lo.z, rh[16 + 4 * j + 2] * hi.z);
-                        P[t][4 * j + 3] = fmaf(rh[4 * j + 3], lo.w, rh[16 + 4 * j + 3] * hi.w);
-                    }
-                }
+                load_cell(a, c, smem, ref_pix, cx, cy, P2);
             }
-            float o[CV_G];
+            const uint64_t w00 = pk2(s.w00, s.w00), w01 = pk2(s.w01, s.w01), w10 = pk2(s.w10, s.w10),
+                           w11 = pk2(s.w11, s.w11);
+            uint64_t o2[8];
 #pragma unroll
-            for (int g = 0; g < CV_G; ++g)
-                o[g] = fmaf(s.w11, P[3][g], fmaf(s.w10, P[2][g], fmaf(s.w01, P[1][g], s.w00 * P[0][g])));
-            if (a.layout == MVD_LAYOUT_BGDHW) {
-                float* op = a.out + (static_cast<size_t>(c.b) * CV_G * a.D + d) * hw + pix;
-                const size_t gs = static_cast<size_t>(a.D) * hw;
+            for (int k = 0; k < 8; ++k) o2[k] = fma2(w11, P2[3][k], fma2(w10, P2[2][k], fma2(w01, P2[1][k], mul2(w00, P2[0][k]))));
+
+            if (a.tma_store) {
+                float* buf = stage + sbuf * (CV_STAGE_BYTES / 4);
+                if (lane == 0) bulk_wait_read<1>();          // the store issued two hypotheses ago has drained this buffer
+                __syncwarp();
+                if (a.layout == MVD_LAYOUT_BGDHW) {           // buf[g][lane]
 #pragma unroll
-                for (int g = 0; g < CV_G; ++g) op[g * gs] = o[g];
-            } else {
-                float4* op = reinterpret_cast<float4*>(a.out + ((static_cast<size_t>(c.b) * a.D + d) * hw + pix) * CV_G);
+                    for (int k = 0; k < 8; ++k) {
+                        float e, f;
+                        unpk2(o2[k], e, f);
+                        buf[(2 * k) * CV_TW + lane] = e;
+                        buf[(2 * k + 1) * CV_TW + lane] = f;
+                    }
+                } else {                                      // buf[lane][g]
+                    ulonglong2* bp = reinterpret_cast<ulonglong2*>(buf + lane * CV_G);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) op[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                    for (int q = 0; q < 4; ++q) bp[q] = make_ulonglong2(o2[2 * q], o2[2 * q + 1]);
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if (a.layout == MVD_LAYOUT_BGDHW) tma_store_5d(&map_out, buf, tx0, c.y, d, 0, c.b);
+                    else tma_store_5d(&map_out, buf, 0, tx0, c.y, d, c.b);
+                    bulk_commit();
+                }
+                sbuf ^= 1u;
+            } else if (lane_ok) {
+                if (a.layout == MVD_LAYOUT_BGDHW) {
+                    const int off = d * hw + pix, gs = a.D * hw;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        float e, f;
+                        unpk2(o2[k], e, f);
+                        obase[off + (2 * k) * gs] = e;
+                        obase[off + (2 * k + 1) * gs] = f;
+                    }
+                } else {
+                    ulonglong2* op = reinterpret_cast<ulonglong2*>(obase + (static_cast<size_t>(d) * hw + pix) * CV_G);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) op[q] = make_ulonglong2(o2[2 * q], o2[2 * q + 1]);
+                }
             }
         }
     }
+    if (lane == 0) bulk_wait_read<0>();                       // shared memory must outlive the in-flight stores
 }
 
 // ------------------------------------------------------------------------------------------ backward
@@ -520,12 +625,30 @@ static int costvol_grouped_launch(bool bwd, CvArgs a, int C, int G, int flags, c
         costvol_grouped_bwd_kernel<<<grid, CV_THREADS, smem, st>>>(map_src, map_ref, a);
         return check_launch("costvol_grouped_bwd");
     }
+    // output descriptor for the per-warp TMA stores (one hypothesis x one tile row x 16 groups per store)
+    CUtensorMap map_out;
+    const uint64_t W = a.w, H = a.h, Dd = a.D;
+    a.tma_store = a.use_tma;
+    if (a.layout == MVD_LAYOUT_BGDHW) {
+        if (a.w % 4 != 0) a.tma_store = 0;      // TMA needs 16-byte global strides; ragged widths use plain stores
+        const uint64_t dims[5] = {W, H, Dd, CV_G, static_cast<uint64_t>(a.B)};
+        const uint64_t str[4] = {W * 4, W * H * 4, W * H * Dd * 4, W * H * Dd * CV_G * 4};
+        const uint32_t box[5] = {CV_TW, 1, 1, CV_G, 1};
+        if (a.tma_store) rc = make_f32_tensor_map(&map_out, a.out, 5, dims, str, box);
+    } else {
+        const uint64_t dims[5] = {CV_G, W, H, Dd, static_cast<uint64_t>(a.B)};
+        const uint64_t str[4] = {CV_G * 4, W * CV_G * 4, W * H * CV_G * 4, W * H * Dd * CV_G * 4};
+        const uint32_t box[5] = {CV_G, CV_TW, 1, 1, 1};
+        rc = make_f32_tensor_map(&map_out, a.out, 5, dims, str, box);
+    }
+    if (rc) return rc;
+    if (!a.tma_store) map_out = map_ref;        // unused by the kernel, but must be a valid descriptor
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(costvol_grouped_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_done = true;
     }
-    costvol_grouped_fwd_kernel<<<grid, CV_THREADS, smem, st>>>(map_src, map_ref, a);
+    costvol_grouped_fwd_kernel<<<grid, CV_THREADS, smem, st>>>(map_src, map_ref, map_out, a);
     return check_launch("costvol_grouped_fwd");
 }
 

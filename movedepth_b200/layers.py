@@ -12,6 +12,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
+from . import precision as PR
 
 
 # ------------------------------------------------------------------ disparity / pose algebra
@@ -192,9 +193,9 @@ class convex_upsample_layer(nn.Module):
         super().__init__()
         self.scale = scale
         self.upsample_mask = nn.Sequential(
-            nn.Conv2d(feature_dim, 64, 3, stride=1, padding=1, bias=False),
+            PR.Conv2d(feature_dim, 64, 3, stride=1, padding=1, bias=False),
             nn.ReLU(inplace=True),
-            nn.Conv2d(64, (2 ** scale) ** 2 * 9, 1, stride=1, padding=0, bias=False))
+            PR.Conv2d(64, (2 ** scale) ** 2 * 9, 1, stride=1, padding=0, bias=False))
 
     def forward(self, depth, feat):
         return convex_upsample(depth, self.upsample_mask(feat), self.scale)

@@ -8,6 +8,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import precision as PR
 from ..layers import ConvBlock, Conv3x3, upsample
 
 
@@ -60,9 +61,9 @@ class UncertNet(nn.Module):
 
     def __init__(self):
         super().__init__()
-        self.conv1 = nn.Sequential(nn.Conv2d(1, 8, 3, 1, 1, bias=False), nn.BatchNorm2d(8), nn.ReLU(inplace=True))
-        self.conv2 = nn.Sequential(nn.Conv2d(8, 8, 3, 1, 1, bias=False), nn.BatchNorm2d(8), nn.ReLU(inplace=True))
-        self.head_convs = nn.Conv2d(8, 1, 3, 1, 1, bias=False)
+        self.conv1 = nn.Sequential(PR.Conv2d(1, 8, 3, 1, 1, bias=False), nn.BatchNorm2d(8), nn.ReLU(inplace=True))
+        self.conv2 = nn.Sequential(PR.Conv2d(8, 8, 3, 1, 1, bias=False), nn.BatchNorm2d(8), nn.ReLU(inplace=True))
+        self.head_convs = PR.Conv2d(8, 1, 3, 1, 1, bias=False)
 
     def forward(self, x):
         y = self.conv2(self.conv1(x)) + x

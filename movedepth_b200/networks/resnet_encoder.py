@@ -16,6 +16,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 import torchvision.models as tvm
 
+from .. import precision as PR
+
 
 def _resnet(num_layers, num_input_images):
     ctor = {18: tvm.resnet18, 34: tvm.resnet34, 50: tvm.resnet50, 101: tvm.resnet101, 152: tvm.resnet152}
@@ -82,7 +84,7 @@ class Conv2d(nn.Module):
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, relu=True, bn=True, bn_momentum=0.1, **kw):
         super().__init__()
-        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride=stride, bias=(not bn), **kw)
+        self.conv = PR.Conv2d(in_channels, out_channels, kernel_size, stride=stride, bias=(not bn), **kw)
         self.bn = nn.BatchNorm2d(out_channels, momentum=bn_momentum) if bn else None
         self.relu = relu
 
@@ -113,15 +115,15 @@ class FPN4(nn.Module):
         self.conv1, self.conv2, self.conv3 = stages
         top = 8 * b
         if scale < 3:
-            self.inner1 = nn.Conv2d(4 * b, top, 1, bias=True)
+            self.inner1 = PR.Conv2d(4 * b, top, 1, bias=True)
         if scale < 2:
-            self.inner2 = nn.Conv2d(2 * b, top, 1, bias=True)
+            self.inner2 = PR.Conv2d(2 * b, top, 1, bias=True)
         if scale < 1:
-            self.inner3 = nn.Conv2d(b, top, 1, bias=True)
+            self.inner3 = PR.Conv2d(b, top, 1, bias=True)
         if scale == 3:
-            self.out = nn.Conv2d(top, 8 * b, 1, bias=False)
+            self.out = PR.Conv2d(top, 8 * b, 1, bias=False)
         else:
-            self.out = nn.Conv2d(top, b * 2 ** scale, 3, padding=1, bias=False)
+            self.out = PR.Conv2d(top, b * 2 ** scale, 3, padding=1, bias=False)
 
     def forward(self, x):
         feats = [self.conv0(x)]
@@ -139,7 +141,7 @@ class ConvBnReLU3D(nn.Module):
 
     def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, pad=1):
         super().__init__()
-        self.conv = nn.Conv3d(in_channels, out_channels, kernel_size, stride=stride, padding=pad, bias=False)
+        self.conv = PR.Conv3d(in_channels, out_channels, kernel_size, stride=stride, padding=pad, bias=False)
         self.bn = nn.BatchNorm3d(out_channels)
 
     def forward(self, x):
@@ -147,7 +149,7 @@ class ConvBnReLU3D(nn.Module):
 
 
 def _up3d(cin, cout, k=3, p=1, op=1, s=2):
-    return nn.Sequential(nn.ConvTranspose3d(cin, cout, kernel_size=k, padding=p, output_padding=op, stride=s, bias=False),
+    return nn.Sequential(PR.ConvTranspose3d(cin, cout, kernel_size=k, padding=p, output_padding=op, stride=s, bias=False),
                          nn.BatchNorm3d(cout), nn.ReLU(inplace=True))
 
 
@@ -190,7 +192,7 @@ class reg3d(_UNet3D):
         self.conv7 = _up3d(8 * b, 4 * b)
         self.conv9 = _up3d(4 * b, 2 * b)
         self.conv11 = _up3d(2 * b, b)
-        self.prob = nn.Conv3d(b, 1, 3, stride=1, padding=1, bias=False)
+        self.prob = PR.Conv3d(b, 1, 3, stride=1, padding=1, bias=False)
 
 
 class reg2d(_UNet3D):
@@ -210,4 +212,4 @@ class reg2d(_UNet3D):
         self.conv7 = _up3d(8 * b, 4 * b, k, p, p, s)
         self.conv9 = _up3d(4 * b, 2 * b, k, p, p, s)
         self.conv11 = _up3d(2 * b, b, k, p, p, s)
-        self.prob = nn.Conv3d(8, 1, 1, stride=1, padding=0)
+        self.prob = PR.Conv3d(8, 1, 1, stride=1, padding=0)

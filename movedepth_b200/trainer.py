@@ -28,6 +28,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import networks, ops
+from . import precision as PR
 from . import photometric as photo
 from .layers import (disp_to_depth, get_smooth_loss, transformation_from_parameters, hypothesis_ratios,
                      fused_group_costvol, convex_upsample_layer, compute_depth_errors)
@@ -196,9 +197,12 @@ class Trainer:
         return [lr * decay for lr in self.base_lrs]
 
     def _tf32(self, branch):
-        """cuDNN TF32 policy per branch: 'mono' (encoders/decoder/pose) or 'mvs' (FPN4/reg3d/heads)."""
-        on = self.precision == "tf32" or (self.precision == "mixed" and branch == "mono")
-        torch.backends.cudnn.allow_tf32 = on
+        """Conv arithmetic policy per branch: 'mono' (encoders/decoder/pose) or 'mvs' (FPN4/reg3d/heads).
+        mixed = TF32 (PyTorch's default conv policy) on mono, 3xTF32 split on mvs (movedepth_b200/precision.py)."""
+        if branch == "mono":
+            PR.set_policy("tf32" if self.precision in ("tf32", "mixed", "mixed_fp32") else "fp32")
+        else:
+            PR.set_policy({"tf32": "tf32", "mixed": "3xtf32", "mixed_fp32": "fp32", "fp32": "fp32"}[self.precision])
 
     # ------------------------------------------------------------------ training loop
     def train(self):
@@ -267,8 +271,9 @@ class Trainer:
     def _volume_logits(self, ref_feat, src_feats, inputs, prior, ratio, poses):
         """cost volume over the matching frames -> reg3d logits (trainer.py:349-366)."""
         K, invK = inputs[("K", 2)], inputs[("inv_K", 2)]       # scale index 2 is hard-coded in the reference
-        vols = [fused_group_costvol(ref_feat, src_feats[i], K, invK, poses[:, i], prior, ratio, self.opt.reg3d_c)
-                for i in range(len(src_feats))]
+        # channels-last-3d volume ([B,D,h,w,G] in memory): what cuDNN's tensor-core NDHWC kernels consume
+        vols = [fused_group_costvol(ref_feat, src_feats[i], K, invK, poses[:, i], prior, ratio, self.opt.reg3d_c,
+                                    layout=ops.LAYOUT_BDHWG) for i in range(len(src_feats))]
         if len(vols) == 1:
             vol = vols[0]        # single view: the view weight w/(1e-8+w) is 1 to within 2e-7 (SURVEY A5)
         else:
@@ -311,8 +316,10 @@ class Trainer:
         # ---------------- cost-volume graph (fp32 convolutions under 'mixed')
         self._tf32("mvs")
         enc = self.models["mvs_encoder"]
-        ref_feat, ref_ctx = enc(inputs[("color_aug", 0, 0)])
-        src_feats = [enc(inputs[("color_aug", f, 0)])[0] for f in self.matching_ids[1:]]
+        cl = torch.channels_last       # NHWC through FPN4: its output is then already the layout K1's TMA boxes read
+        ref_img = inputs[("color_aug", 0, 0)].contiguous(memory_format=cl)
+        ref_feat, ref_ctx = enc(ref_img)
+        src_feats = [enc(inputs[("color_aug", f, 0)].contiguous(memory_format=cl))[0] for f in self.matching_ids[1:]]
         logits, vol = self._volume_logits(ref_feat, src_feats, inputs, prior, ratio, poses)
         _, ent, depth_mvs = ops.regress_depth(logits, inv_a, inv_b, o.norm_radius)
         trust = self.models["mask_cnn"](ent)
@@ -327,7 +334,7 @@ class Trainer:
         xs = torch.arange(o.width, device=self.device).view(1, 1, 1, -1)
         inside = (xs >= self._aug_box[0]) & (xs < self._aug_box[0] + fw) & (ys >= self._aug_box[1]) & (ys < self._aug_box[1] + fh)
         aug_mask = (~inside).float().expand(B, 3, o.height, o.width)
-        aug_feat, _ = enc(inputs[("color_aug", 0, 0)] * aug_mask)
+        aug_feat, _ = enc((ref_img * aug_mask).contiguous(memory_format=cl))
         logits_aug, _ = self._volume_logits(aug_feat, src_feats, inputs, prior, ratio, poses)
         _, _, depth_aug = ops.regress_depth(logits_aug, inv_a, inv_b, o.norm_radius)
         sel = (F.interpolate(aug_mask, list(depth_aug.shape[1:]), mode="bilinear", align_corners=True).sum(1) != 0).float()

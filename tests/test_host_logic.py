@@ -182,3 +182,33 @@ def test_gradient_exchange_world_size_2_gloo(tmp_path):
     assert torch.equal(g0, g1)
     # mean over ranks of d/dW sum(Wx+b): x summed over the 3 rows -> 3*(1+2)/2 = 4.5 per weight, 3 per bias
     assert torch.allclose(g0[:24], torch.full((24,), 4.5)) and torch.allclose(g0[24:28], torch.full((4,), 3.0))
+
+
+def test_3xtf32_split_conv_matches_plain_conv_and_its_gradients():
+    """movedepth_b200/precision.py: the split evaluates x_hi*w_hi + x_lo*w_hi + x_hi*w_lo; on CPU (exact fp32
+    products) that differs from conv(x, w) only by the dropped x_lo*w_lo term (~2^-22 relative)."""
+    from movedepth_b200 import precision as PR
+    g = torch.Generator().manual_seed(0)
+    cases = [
+        (PR.Conv3d(4, 6, 3, stride=2, padding=1, bias=False), torch.nn.Conv3d(4, 6, 3, stride=2, padding=1, bias=False), (2, 4, 8, 8, 10)),
+        (PR.ConvTranspose3d(6, 4, 3, stride=2, padding=1, output_padding=1, bias=False),
+         torch.nn.ConvTranspose3d(6, 4, 3, stride=2, padding=1, output_padding=1, bias=False), (2, 6, 4, 4, 5)),
+        (PR.Conv2d(3, 5, 5, stride=2, padding=2, bias=True), torch.nn.Conv2d(3, 5, 5, stride=2, padding=2, bias=True), (2, 3, 12, 14)),
+    ]
+    for mine, plain, shape in cases:
+        plain.load_state_dict(mine.state_dict())
+        x1 = torch.randn(shape, generator=g).requires_grad_(True)
+        x2 = x1.detach().clone().requires_grad_(True)
+        PR.set_policy("3xtf32")
+        y1 = mine(x1)
+        PR.set_policy("fp32")
+        y2 = plain(x2)
+        assert list(mine.state_dict()) == list(plain.state_dict())
+        torch.testing.assert_close(y1, y2, rtol=1e-5, atol=2e-6)
+        gy = torch.randn(y2.shape, generator=g)
+        y1.backward(gy)
+        y2.backward(gy)
+        torch.testing.assert_close(x1.grad, x2.grad, rtol=1e-5, atol=5e-6)
+        torch.testing.assert_close(mine.weight.grad, plain.weight.grad, rtol=1e-5, atol=2e-5)
+    hi = PR.tf32_round(torch.tensor([1.0 + 2 ** -11, 3.14159274]))
+    assert (hi.view(torch.int32) & 0x1FFF).abs().sum() == 0

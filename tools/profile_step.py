@@ -1,0 +1,53 @@
+"""Kernel-time breakdown of one steady-state training step (torch.profiler / CUPTI; no replay).
+   python tools/profile_step.py [--precision mixed] [--top 40]"""
+import argparse
+import collections
+import os
+import re
+import sys
+
+import torch
+from torch.profiler import profile, ProfilerActivity
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from movedepth_b200.options import MonodepthOptions  # noqa: E402
+from movedepth_b200.trainer import Trainer, SyntheticKITTI  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--precision", default="mixed")
+    ap.add_argument("--top", type=int, default=45)
+    ap.add_argument("--D", type=int, default=96)
+    ap.add_argument("--B", type=int, default=6)
+    a = ap.parse_args()
+    argv = ["--height", "192", "--width", "640", "--num_depth_bins", str(a.D), "--batch_size", str(a.B), "--frame_ids", "0", "-1",
+            "--weights_init", "scratch", "--convex_up", "--learning_rate", "2e-4", "--b200_conv_precision", a.precision,
+            "--log_dir", "/tmp/mvd_prof"]
+    opt = MonodepthOptions().parse(argv)
+    torch.manual_seed(0)
+    tr = Trainer(opt)
+    batch = {k: v.cuda() for k, v in next(iter(SyntheticKITTI(opt, a.B, 1))).items()}
+    for _ in range(4):
+        tr.train_step(batch)
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+        tr.train_step(batch)
+        torch.cuda.synchronize()
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    total = 0.0
+    for e in prof.events():
+        if e.device_type == torch.autograd.DeviceType.CUDA:
+            name = re.sub(r"<.*", "", e.name)[:100]
+            agg[name][0] += 1
+            agg[name][1] += e.device_time if hasattr(e, "device_time") else e.cuda_time
+            total += e.device_time if hasattr(e, "device_time") else e.cuda_time
+    n = sum(c for c, _ in agg.values())
+    print("GPU busy %.2f ms over %d kernels/copies in one step (precision=%s)" % (total / 1e3, n, a.precision))
+    for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:a.top]:
+        print("%9.1f us %5d %5.1f%%  %s" % (t, c, 100 * t / total, k))
+
+
+if __name__ == "__main__":
+    main()
