@@ -183,10 +183,9 @@ def run_own(args):
         "metric": METRIC, "value": frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "precision": {"mixed": "3xTF32-split tensor-core convs (near-fp32, movedepth_b200/precision.py) on the cost-volume "
-                   "branch; cuDNN TF32 (PyTorch's default conv policy) on the mono/pose branch",
-                   "mixed_fp32": "cuDNN fp32 SIMT convs on the cost-volume branch; TF32 on the mono/pose branch",
-                   "fp32": "fp32 everywhere", "tf32": "cuDNN TF32 everywhere"}[args.precision],
+        "config": {"workload": WORKLOAD, "precision": {"3xtf32": "convs on tensor cores with a 3-way TF32 operand split in the forward (near-fp32 outputs, "
+                   "movedepth_b200/precision.py); gradients single-pass TF32 (PyTorch's default conv policy)",
+                   "fp32": "fp32 everywhere (cuDNN SIMT convs)", "tf32": "cuDNN TF32 everywhere"}[args.precision],
                    "schedule": "velocity-guided (epoch 9)" if args.velocity else "fixed range (epoch 0)",
                    "l2": "256 MiB buffer written between timed steps (L2 flush); per-step activations also exceed L2",
                    "parallelism": "dp%d, flat-arena gradient all-reduce over NCCL" % world},
@@ -213,7 +212,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
-    ap.add_argument("--precision", default="mixed", choices=["mixed", "mixed_fp32", "fp32", "tf32"])
+    ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "fp32", "tf32"])
     ap.add_argument("--velocity", action="store_true", help="use the velocity-guided hypothesis range (epoch > 8)")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from the committed ncu capture")

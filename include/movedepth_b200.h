@@ -134,6 +134,13 @@ int mvd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   float beta1, float beta2, float eps, float step_size, float bias2,
                   float grad_scale, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * 3xTF32 operand split for the tensor-core convolutions of movedepth_b200/precision.py:
+ * x = hi + lo (hi = x rounded to TF32).  x: [rows, C] (channels-last), out: [rows, 3C] =
+ * [hi, lo, hi] (pattern 0, activations) or [hi, hi, lo] (pattern 1, weights).  n = rows * C.
+ * ------------------------------------------------------------------------------------- */
+int mvd_split_tf32(const float* x, float* out, long long n, int C, int pattern, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,7 @@ SIGNATURES = {
     "mvd_convex_up_bwd": ([_P] * 5 + [_I] * 4 + [_P], _I),
     "mvd_photometric_fwd": ([_P] * 8 + [_I] * 3 + [_F, _I, _P], _I),
     "mvd_photometric_bwd": ([_P] * 10 + [_I] * 3 + [_F, _P], _I),
+    "mvd_split_tf32": ([_P, _P, _LL, _I, _I, _P], _I),
     "mvd_adam_step": ([_P] * 4 + [_LL] + [_F] * 6 + [_P], _I),
 }
 

@@ -258,3 +258,34 @@ int mvd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
 }
 
 }
+
+// ------------------------------------------------------------------------------------------ 3xTF32 operand split
+// out[r, 0:C | C:2C | 2C:3C] = pieces of x[r, 0:C] split as x = hi + lo with hi = x rounded to TF32's
+// 10-bit mantissa.  pattern 0: [hi, lo, hi] (activations / gradients), pattern 1: [hi, hi, lo] (weights).
+// One pass instead of round/sub/cat; rows are channels-last pixels (C innermost).
+namespace mvd {
+__global__ void __launch_bounds__(256)
+split_tf32_kernel(const float* __restrict__ x, float* __restrict__ out, long long n, int C, int pattern) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+        const float v = __ldg(x + i);
+        const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+        const float lo = v - hi;
+        const long long r = i / C;
+        const int c = static_cast<int>(i - r * C);
+        float* o = out + r * (3LL * C) + c;
+        o[0] = hi;
+        o[C] = pattern == 0 ? lo : hi;
+        o[2 * C] = pattern == 0 ? hi : lo;
+    }
+}
+}  // namespace mvd
+
+extern "C" int mvd_split_tf32(const float* x, float* out, long long n, int C, int pattern, void* stream) {
+    MVD_REQUIRE(x && out, "null pointer argument");
+    MVD_REQUIRE(n >= 0 && C > 0 && n % C == 0 && (pattern == 0 || pattern == 1), "bad split arguments n=%lld C=%d", n, C);
+    if (n == 0) return 0;
+    const int grid = static_cast<int>(min(static_cast<long long>(mvd::sm_count()) * 16, (n + 255) / 256));
+    mvd::split_tf32_kernel<<<grid, 256, 0, mvd::as_stream(stream)>>>(x, out, n, C, pattern);
+    return mvd::check_launch("split_tf32");
+}

@@ -58,10 +58,11 @@ class MonodepthOptions:
         # torch >= 2 launchers pass --local-rank; accept both spellings
         p.add_argument("--local-rank", dest="local_rank", type=int, default=0)
         # ---- this build only
-        p.add_argument("--b200_conv_precision", choices=["fp32", "tf32", "mixed", "mixed_fp32"], default="mixed",
-                       help="conv arithmetic: fp32 everywhere; TF32 everywhere; mixed = TF32 on the mono/pose branch + "
-                            "3xTF32 split (near-fp32) on the cost-volume branch, whose argmax is precision-sensitive "
-                            "(SURVEY Appendix C5); mixed_fp32 = TF32 mono + cuDNN fp32 SIMT cost-volume branch")
+        p.add_argument("--b200_conv_precision", choices=["fp32", "3xtf32", "tf32"], default="3xtf32",
+                       help="conv arithmetic (movedepth_b200/precision.py): fp32 = cuDNN SIMT kernels; 3xtf32 = tensor-core "
+                            "convs with a 3-way TF32 operand split in the forward (near-fp32 outputs), TF32 gradients; "
+                            "tf32 = PyTorch's default conv policy")
+        p.add_argument("--b200_split_backward", action="store_true", help="3xtf32: split dgrad/wgrad as well")
         p.add_argument("--b200_cuda_graph", action="store_true", help="capture the training step in a CUDA graph")
         p.add_argument("--b200_synthetic", action="store_true", help="train on synthetic KITTI-shape tensors")
         self.parser = p

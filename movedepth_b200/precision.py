@@ -1,30 +1,36 @@
-"""Arithmetic policy of the convolution GEMMs (cuDNN library calls) on the cost-volume branch.
+"""Arithmetic policy of the convolution GEMMs (cuDNN library calls).
 
-The depth regression ends in an argmax (localmax, movedepth/layers.py:796-812), so `depth_mvs`
-flips at individual pixels when the conv outputs move by more than a few ulp (SURVEY Appendix C5:
-TF32 operands move 25 % of the pixels by >1e-3).  cuDNN's fp32 SIMT convolutions are exact enough
-but 5-20x slower than its tensor-core kernels on B200, so the default policy is a **3xTF32 split**:
+The reference is fp32.  Two of its outputs are precision-sensitive: the mono disparity feeds the
+hypothesis range, and the depth regression ends in an argmax (localmax, movedepth/layers.py:796-812),
+so `depth_mvs` flips at individual pixels when conv outputs move by more than a few ulp (SURVEY
+Appendix C5; measured here in tools/parity_report.py: plain TF32 leaves only ~62 % of the pixels
+within 1e-3 of the reference).  cuDNN's fp32 SIMT convolutions are exact enough but 5-20x slower
+than its tensor-core kernels on B200, so the default policy is a **3xTF32 split** of the forward:
 
     x = x_hi + x_lo,  w = w_hi + w_lo     (x_hi = x rounded to TF32's 10-bit mantissa)
     conv(x, w) ~= conv(x_hi, w_hi) + conv(x_lo, w_hi) + conv(x_hi, w_lo)
 
-evaluated as ONE tensor-core convolution over a 3x wider reduction dimension (channels for the
-forward and the data gradient, batch for the weight gradient).  Every operand product is exact in
-TF32; what remains is the tensor core's fp32 accumulation (~4e-6 relative, measured in
-tools/bench_convs.py) instead of TF32's ~3e-4.
+evaluated as ONE tensor-core convolution over a 3x wider channel dimension.  Every operand product
+is exact in TF32; what remains is the tensor core's fp32 accumulation (~4e-6 relative, measured in
+tools/bench_convs.py) instead of TF32's ~3e-4.  The operand split is one hand-written kernel
+(`mvd_split_tf32`).  Gradients (dgrad / wgrad) use single-pass TF32 -- PyTorch's default conv
+policy on this hardware -- unless `split_backward` is set.
 
-Policies: "fp32" (cuDNN SIMT kernels), "3xtf32" (above), "tf32" (PyTorch's default conv policy).
+Policies: "fp32" (cuDNN SIMT kernels, bit-level parity runs), "3xtf32" (default), "tf32".
 """
+import ctypes
+
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
-_policy = {"mode": "fp32"}
+_policy = {"mode": "fp32", "split_backward": False}
 
 
-def set_policy(mode):
+def set_policy(mode, split_backward=None):
     assert mode in ("fp32", "3xtf32", "tf32"), mode
     _policy["mode"] = mode
+    if split_backward is not None:
+        _policy["split_backward"] = bool(split_backward)
     torch.backends.cudnn.allow_tf32 = mode != "fp32"
 
 
@@ -41,23 +47,41 @@ def _fmt(t):
     return torch.channels_last_3d if t.dim() == 5 else torch.channels_last
 
 
-def _split(t, dim, pattern):
-    """cat of (hi | lo) pieces of t along `dim`, e.g. pattern 'hlh' -> [hi, lo, hi]."""
+def _split_dim1(t, weight):
+    """[N, C, ...] channels-last -> [N, 3C, ...] channels-last holding [hi, lo, hi] (activations) or
+    [hi, hi, lo] (weights) along the channel dimension."""
+    t = t.contiguous(memory_format=_fmt(t))
+    C = t.shape[1]
+    if t.is_cuda:
+        from . import _lib, ops
+        out = torch.empty((t.shape[0], 3 * C) + tuple(t.shape[2:]), device=t.device, dtype=torch.float32,
+                          memory_format=_fmt(t))
+        rc = _lib.lib().mvd_split_tf32(ctypes.c_void_p(t.data_ptr()), ctypes.c_void_p(out.data_ptr()), t.numel(), C,
+                                       1 if weight else 0, ops._stream())
+        _lib.check(rc, "mvd_split_tf32")
+        ops.launch_counter["n"] += 1
+        return out
     hi = tf32_round(t)
     lo = t - hi
-    return torch.cat([hi if p == "h" else lo for p in pattern], dim)
+    return torch.cat([hi, hi, lo] if weight else [hi, lo, hi], 1)
+
+
+def _split_dim0(t, weight):
+    hi = tf32_round(t)
+    lo = t - hi
+    return torch.cat([hi, hi, lo] if weight else [hi, lo, hi], 0).contiguous(memory_format=_fmt(t))
 
 
 class _SplitConv(torch.autograd.Function):
-    """y = conv(x, w) (+ transposed variant) with the 3xTF32 split in forward, dgrad and wgrad."""
+    """y = conv(x, w) (or its transposed variant) with the 3xTF32 operand split."""
 
     @staticmethod
     def forward(ctx, x, w, stride, padding, output_padding, transposed):
         x = x.contiguous(memory_format=_fmt(x))
         ctx.save_for_backward(x, w)
         ctx.cfg = (stride, padding, output_padding, transposed)
-        x3 = _split(x, 1, "hlh")
-        w3 = _split(w, 0 if transposed else 1, "hhl").contiguous(memory_format=_fmt(w))
+        x3 = _split_dim1(x, False)
+        w3 = _split_dim0(w, True) if transposed else _split_dim1(w, True)
         prev = torch.backends.cudnn.allow_tf32
         torch.backends.cudnn.allow_tf32 = True
         try:
@@ -77,18 +101,22 @@ class _SplitConv(torch.autograd.Function):
         torch.backends.cudnn.allow_tf32 = True
         gx = gw = None
         try:
-            if ctx.needs_input_grad[0]:
-                # reduction over output channels -> split along them
-                gy3 = _split(gy, 1, "hlh")
-                w3 = _split(w, 1 if transposed else 0, "hhl").contiguous(memory_format=_fmt(w))
-                gx = torch.ops.aten.convolution_backward(gy3, x, w3, None, stride, padding, (1,) * nd, transposed,
-                                                         output_padding, 1, [True, False, False])[0]
-            if ctx.needs_input_grad[1]:
-                # reduction over batch and positions -> split along the batch
-                xb = _split(x, 0, "hlh")
-                gb = _split(gy, 0, "hhl")
-                gw = torch.ops.aten.convolution_backward(gb, xb, w, None, stride, padding, (1,) * nd, transposed,
-                                                         output_padding, 1, [False, True, False])[1]
+            need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+            if not _policy["split_backward"]:
+                gx, gw, _ = torch.ops.aten.convolution_backward(gy, x, w.contiguous(memory_format=_fmt(w)), None, stride,
+                                                                padding, (1,) * nd, transposed, output_padding, 1,
+                                                                [need_x, need_w, False])
+            else:
+                if need_x:       # reduction over output channels -> split along them
+                    gy3 = _split_dim1(gy, False)
+                    w3 = _split_dim1(w, True) if transposed else _split_dim0(w, True)
+                    gx = torch.ops.aten.convolution_backward(gy3, x, w3, None, stride, padding, (1,) * nd, transposed,
+                                                             output_padding, 1, [True, False, False])[0]
+                if need_w:       # reduction over batch and positions -> split along the batch
+                    xb = _split_dim0(x, False)
+                    gb = _split_dim0(gy, True)
+                    gw = torch.ops.aten.convolution_backward(gb, xb, w, None, stride, padding, (1,) * nd, transposed,
+                                                             output_padding, 1, [False, True, False])[1]
         finally:
             torch.backends.cudnn.allow_tf32 = prev
         return gx, gw, None, None, None, None
@@ -102,8 +130,8 @@ class _PolicyMixin:
     _transposed = False
 
     def forward(self, x):
-        mode = _policy["mode"]
-        if mode != "3xtf32":
+        if _policy["mode"] != "3xtf32" or getattr(self, "padding_mode", "zeros") != "zeros" or self.groups != 1 \
+                or any(d != 1 for d in _tup(self.dilation, x.dim() - 2)):
             return super().forward(x)
         nd = x.dim() - 2
         y = _SplitConv.apply(x, self.weight, _tup(self.stride, nd), _tup(self.padding, nd),
@@ -114,13 +142,26 @@ class _PolicyMixin:
 
 
 class Conv2d(_PolicyMixin, nn.Conv2d):
-    """nn.Conv2d (same parameters / state-dict keys) that honours the branch precision policy."""
+    """nn.Conv2d (same parameters / state-dict keys) that honours the precision policy."""
 
 
 class Conv3d(_PolicyMixin, nn.Conv3d):
-    """nn.Conv3d that honours the branch precision policy."""
+    """nn.Conv3d that honours the precision policy."""
 
 
 class ConvTranspose3d(_PolicyMixin, nn.ConvTranspose3d):
-    """nn.ConvTranspose3d that honours the branch precision policy."""
+    """nn.ConvTranspose3d that honours the precision policy."""
     _transposed = True
+
+
+_SWAP = {nn.Conv2d: Conv2d, nn.Conv3d: Conv3d, nn.ConvTranspose3d: ConvTranspose3d}
+
+
+def adopt(module):
+    """Make every plain conv inside `module` (e.g. a torchvision ResNet) policy-aware, in place.
+    Parameters, buffers and state-dict keys are untouched (only the class of the conv modules changes)."""
+    for m in module.modules():
+        cls = _SWAP.get(type(m))
+        if cls is not None:
+            m.__class__ = cls
+    return module

@@ -12,8 +12,10 @@ files.  What differs is how a step executes:
     parameter group, and data-parallel training all-reduces the gradient arena over NCCL in two
     pieces (cost-volume branch first, overlapping the mono/pose backward) instead of eight DDP
     reducers;
-  * the step is two autograd graphs joined only by detached tensors, so the
-    two backward passes run with different cuDNN precision policies.
+  * the step is two autograd graphs joined only by detached tensors: they are
+    back-propagated separately so the first gradient arena can be reduced while the second runs;
+  * convolutions run channels-last on cuDNN's tensor-core kernels under the 3xTF32 split policy
+    of movedepth_b200/precision.py (fp32 available for bit-level parity runs).
 
 There is no CPU path: `--no_cuda` raises.
 """
@@ -130,7 +132,8 @@ class Trainer:
         self.num_input_frames = len(o.frame_ids)
         self.num_pose_frames = 2
         self.matching_ids = o.matching_ids
-        self.precision = getattr(o, "b200_conv_precision", "mixed")
+        self.precision = getattr(o, "b200_conv_precision", "3xtf32")
+        PR.set_policy(self.precision, split_backward=getattr(o, "b200_split_backward", False))
         torch.backends.cudnn.benchmark = True
 
         # ---- sub-models (trainer.py:65-131)
@@ -150,6 +153,7 @@ class Trainer:
         for k in m:
             if o.ddp and self.world_size > 1:
                 m[k] = nn.SyncBatchNorm.convert_sync_batchnorm(m[k])
+            PR.adopt(m[k])                                # torchvision convs follow the precision policy too
             m[k].to(self.device)
         self.models = m
         self.parameters_to_train = [p for k in GROUP0 for p in m[k].parameters()]
@@ -196,13 +200,9 @@ class Trainer:
         decay = 0.1 ** (self.epoch // self.opt.scheduler_step_size)
         return [lr * decay for lr in self.base_lrs]
 
-    def _tf32(self, branch):
-        """Conv arithmetic policy per branch: 'mono' (encoders/decoder/pose) or 'mvs' (FPN4/reg3d/heads).
-        mixed = TF32 (PyTorch's default conv policy) on mono, 3xTF32 split on mvs (movedepth_b200/precision.py)."""
-        if branch == "mono":
-            PR.set_policy("tf32" if self.precision in ("tf32", "mixed", "mixed_fp32") else "fp32")
-        else:
-            PR.set_policy({"tf32": "tf32", "mixed": "3xtf32", "mixed_fp32": "fp32", "fp32": "fp32"}[self.precision])
+    def _tf32(self, branch=None):
+        """Apply the conv arithmetic policy (movedepth_b200/precision.py): fp32 | 3xtf32 | tf32."""
+        PR.set_policy(self.precision)
 
     # ------------------------------------------------------------------ training loop
     def train(self):
@@ -260,7 +260,7 @@ class Trainer:
                 continue
             a, b = inputs[("color_aug", f, 0)], inputs[("color_aug", 0, 0)]
             pair = [a, b] if f < 0 else [b, a]
-            feats = [self.models["pose_encoder"](torch.cat(pair, 1))]
+            feats = [self.models["pose_encoder"](torch.cat(pair, 1).contiguous(memory_format=torch.channels_last))]
             axisangle, translation = self.models["pose"](feats)
             outputs[("axisangle", 0, f)], outputs[("translation", 0, f)] = axisangle, translation
             outputs[("cam_T_cam", 0, f)] = transformation_from_parameters(axisangle[:, 0], translation[:, 0], invert=(f < 0))
@@ -294,11 +294,12 @@ class Trainer:
         B = inputs[("color_aug", 0, 0)].shape[0]
         noise = list(noise) if noise is not None else None
 
-        # ---------------- mono / pose graph (TF32 allowed under the 'mixed' policy)
+        # ---------------- mono / pose graph
         self._tf32("mono")
         outputs = self.predict_poses(inputs)
         poses = torch.stack([inputs[("relative_pose", f)] for f in self.matching_ids[1:]], 1)   # [B,M,4,4]
-        outputs.update(self.models["mono_depth"](self.models["mono_encoder"](inputs[("color_aug", 0, 0)])))
+        ref_cl = inputs[("color_aug", 0, 0)].contiguous(memory_format=torch.channels_last)    # NHWC for cuDNN's tensor-core kernels
+        outputs.update(self.models["mono_depth"](self.models["mono_encoder"](ref_cl)))
         losses = self.compute_losses(inputs, outputs, is_mvs=False, noise=noise)
 
         # ---------------- hypotheses around the mono prior (trainer.py:333-346), separable form
@@ -313,7 +314,7 @@ class Trainer:
         inv_b = 1.0 / (prior[:, 0] * ratio[:, 0].view(B, 1, 1))
         outputs["depth_prior"], outputs["hypothesis_ratio"] = prior, ratio
 
-        # ---------------- cost-volume graph (fp32 convolutions under 'mixed')
+        # ---------------- cost-volume graph
         self._tf32("mvs")
         enc = self.models["mvs_encoder"]
         cl = torch.channels_last       # NHWC through FPN4: its output is then already the layout K1's TMA boxes read

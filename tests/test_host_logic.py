@@ -195,19 +195,23 @@ def test_3xtf32_split_conv_matches_plain_conv_and_its_gradients():
          torch.nn.ConvTranspose3d(6, 4, 3, stride=2, padding=1, output_padding=1, bias=False), (2, 6, 4, 4, 5)),
         (PR.Conv2d(3, 5, 5, stride=2, padding=2, bias=True), torch.nn.Conv2d(3, 5, 5, stride=2, padding=2, bias=True), (2, 3, 12, 14)),
     ]
-    for mine, plain, shape in cases:
+    for mine, plain, shape in cases * 2:
+        split_bwd = mine.weight.grad is not None         # second visit of each case: split the backward too
+        mine.weight.grad = plain.weight.grad = None
         plain.load_state_dict(mine.state_dict())
         x1 = torch.randn(shape, generator=g).requires_grad_(True)
         x2 = x1.detach().clone().requires_grad_(True)
-        PR.set_policy("3xtf32")
+        PR.set_policy("3xtf32", split_backward=split_bwd)
         y1 = mine(x1)
         PR.set_policy("fp32")
         y2 = plain(x2)
         assert list(mine.state_dict()) == list(plain.state_dict())
         torch.testing.assert_close(y1, y2, rtol=1e-5, atol=2e-6)
         gy = torch.randn(y2.shape, generator=g)
+        PR.set_policy("3xtf32")
         y1.backward(gy)
         y2.backward(gy)
+        PR.set_policy("fp32", split_backward=False)
         torch.testing.assert_close(x1.grad, x2.grad, rtol=1e-5, atol=5e-6)
         torch.testing.assert_close(mine.weight.grad, plain.weight.grad, rtol=1e-5, atol=2e-5)
     hi = PR.tf32_round(torch.tensor([1.0 + 2 ** -11, 3.14159274]))

@@ -21,7 +21,7 @@ def main():
     print("%-10s %-11s %9s %9s %9s %11s %11s" % ("case", "policy", "depth_mvs", "masked", "fused", "disp0 maxrel", "loss rel"))
     for name, cfg in C.STEP_CASES.items():
         gold = dict(np.load(os.path.join(gold_dir, "step_%s.npz" % name)))
-        for pol in ("fp32", "mixed_fp32", "mixed", "tf32"):
+        for pol in ("fp32", "3xtf32", "tf32"):
             argv = ["--height", str(cfg["H"]), "--width", str(cfg["W"]), "--num_depth_bins", str(cfg["D"]), "--batch_size",
                     str(cfg["B"]), "--res_arch", str(cfg.get("arch", 18)), "--weights_init", "scratch", "--convex_up",
                     "--b200_conv_precision", pol, "--log_dir", "/tmp/mvd_parity", "--frame_ids"] + [str(f) for f in cfg["frame_ids"]]

@@ -1,5 +1,5 @@
 """Kernel-time breakdown of one steady-state training step (torch.profiler / CUPTI; no replay).
-   python tools/profile_step.py [--precision mixed] [--top 40]"""
+   python tools/profile_step.py [--precision 3xtf32] [--top 40]"""
 import argparse
 import collections
 import os
@@ -17,7 +17,7 @@ from movedepth_b200.trainer import Trainer, SyntheticKITTI  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--precision", default="mixed")
+    ap.add_argument("--precision", default="3xtf32")
     ap.add_argument("--top", type=int, default=45)
     ap.add_argument("--D", type=int, default=96)
     ap.add_argument("--B", type=int, default=6)
