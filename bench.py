@@ -165,7 +165,11 @@ def run_own(args):
     sampler.start()
     ops.costvol_events = []
     n0 = ops.launch_counter["n"]
+    if args.ncu_range:                       # `ncu --profile-from-start off`: capture exactly the timed steps
+        torch.cuda.profiler.start()
     ms = timed(dev_batches, args.steps, read_loss=False)
+    if args.ncu_range:
+        torch.cuda.profiler.stop()
     launches = ops.launch_counter["n"] - n0
     cv = [a.elapsed_time(b) for a, b in ops.costvol_events]
     ops.costvol_events = None
@@ -215,6 +219,7 @@ def main():
     ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "fp32", "tf32"])
     ap.add_argument("--velocity", action="store_true", help="use the velocity-guided hypothesis range (epoch > 8)")
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--ncu_range", action="store_true", help="cudaProfilerStart/Stop around the device-timed steps")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from the committed ncu capture")
     args = ap.parse_args()
     if args.impl == "reference":

