@@ -31,7 +31,8 @@ extern "C" {
 #define MVD_LAYOUT_BDHWG 1 /* [B,D,h,w,G] : channels-last-3d view of the same logical tensor */
 
 /* flags */
-#define MVD_FLAG_NO_TMA 1 /* force the global-gather route (debug / parity isolation) */
+#define MVD_FLAG_NO_TMA 1   /* no TMA staging: taps are gathered from global memory (debug / parity isolation) */
+#define MVD_FLAG_NO_TABLE 2 /* forward: no per-pixel tap-correlation table, recompute each bilinear cell directly */
 
 int mvd_version(void);
 const char* mvd_last_error_string(void);

@@ -71,7 +71,7 @@ int make_nhwc32_tensor_map(CUtensorMap* map, const float* base, int B, int h, in
 
 // Generic fp32 tiled descriptor (no swizzle): dims/box innermost first, strides in bytes for dims 1..rank-1.
 int make_f32_tensor_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                        const uint32_t* box) {
+                        const uint32_t* box, int swizzle_bytes) {
     auto fn = encode_fn();
     if (!fn) return fail(-2, "cuTensorMapEncodeTiled entry point unavailable");
     cuuint64_t gdim[5], gstr[4];
@@ -82,8 +82,11 @@ int make_f32_tensor_map(CUtensorMap* map, const float* base, int rank, const uin
         estr[i] = 1u;
         if (i > 0) gstr[i - 1] = strides[i - 1];
     }
+    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<float*>(base), gdim, gstr, bx, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(-3, "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
     return 0;

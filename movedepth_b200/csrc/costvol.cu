@@ -55,6 +55,7 @@ struct CvArgs {
     int B, h, w, D;
     int layout;
     int use_tma;
+    int use_table;
     int tma_store;
     int tiles_x, tiles_y, num_tiles;
     int DC;              // hypotheses per chunk
@@ -327,14 +328,49 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// Per-tap group correlations of one bilinear cell, packed: P2[t][k] = (P_t[2k], P_t[2k+1]),
-// P_t[g] = 1/2 (ref[g] src_t[g] + ref[g+16] src_t[g+16]).
-__device__ __forceinline__ void load_cell(const CvArgs& a, const PixelCtx& c, const unsigned char* smem, int ref_pix,
-                                          int cx, int cy, uint64_t (&P2)[4][8]) {
-    const unsigned char* sbox = smem + CvSmem::OFF_SRC;
-    const unsigned char* rbox = smem + CvSmem::OFF_REF;
-    int rel;
-    const bool in_box = cell_in_box(c, cx, cy, rel);
+// ---- forward, v3 ---------------------------------------------------------------------------------
+// Tile = one row of 32 reference pixels x all D; warp = chunk of D/8 hypotheses, lane = pixel.
+// Over the whole hypothesis range a pixel's epipolar segment is only a few source pixels long, so
+// the per-tap group correlations  P_tap[g] = 1/2 * sum_{c in {g,g+16}} ref[c] * src_tap[c]  of
+// every tap the pixel can touch are computed ONCE per tile (8 warps share the taps of a pixel) into
+// a shared-memory table; the hypothesis loop refills its register-resident bilinear cell from
+// that table with 16 LDS.128 instead of recomputing 128 products whenever one lane of the warp
+// crosses a cell boundary.  Pixels whose footprint does not fit the table (degenerate poses)
+// fall back to the direct computation from the staged source box / global memory.
+namespace f3 {
+constexpr int TW = 32;
+constexpr int NCH = 8;                      // hypothesis chunks = warps per CTA
+constexpr int WARPS = NCH;
+constexpr int THREADS = 32 * WARPS;
+constexpr int BOX_W = 48;                   // staged source box (pixels)
+constexpr int BOX_H = 6;
+constexpr int NT = 16;                      // table capacity: taps per pixel
+constexpr int PT_STRIDE = NT * 64 + 16;     // bytes per pixel; the 16 B pad makes 8 consecutive lanes hit 8 bank groups
+constexpr int STAGE_ROW = CV_G * TW * 4;    // one hypothesis of the tile row: 16 groups x 32 pixels
+
+struct Smem {
+    static constexpr int SRC_BYTES = BOX_W * BOX_H * 128;
+    static constexpr int REF_BYTES = TW * 128;
+    static constexpr int OFF_SRC = 0;                                   // 1024 B aligned (128B swizzle)
+    static constexpr int OFF_REF = OFF_SRC + SRC_BYTES;
+    static constexpr int OFF_PTAB = OFF_REF + REF_BYTES;
+    static constexpr int OFF_STAGE = OFF_PTAB + TW * PT_STRIDE;         // per-warp double-buffered output rows
+    static constexpr int OFF_FOOT = OFF_STAGE + WARPS * 2 * STAGE_ROW;  // [2][WARPS][32] short4 cell ranges
+    static constexpr int OFF_GEO = OFF_FOOT + 2 * WARPS * 32 * 8;       // [2][32] floats
+    static constexpr int OFF_RED = OFF_GEO + 2 * 32 * 4;                // [2][WARPS][4] ints
+    static constexpr int OFF_BAR = OFF_RED + 2 * WARPS * 4 * 4;
+    static constexpr int TOTAL = OFF_BAR + 16;
+    static constexpr int ALLOC = TOTAL + 1024;                          // slack for manual 1024 B alignment
+};
+static_assert(Smem::OFF_REF % 1024 == 0 && Smem::OFF_STAGE % 512 == 0, "TMA alignment");
+
+// Direct computation of the four per-tap group correlations of cell (cx,cy) (no table).
+__device__ __forceinline__ void load_cell_direct(const CvArgs& a, int b, const unsigned char* sbox,
+                                                 const unsigned char* rbox, int ref_pix, bool boxed, int ox, int oy,
+                                                 int cx, int cy, uint64_t (&P2)[4][8]) {
+    const int rx = cx - ox, ry = cy - oy;
+    const bool in_box = boxed && rx >= 0 && rx <= BOX_W - 2 && ry >= 0 && ry <= BOX_H - 2;
+    const int rel = ry * BOX_W + rx;
     const uint64_t half2 = pk2(0.5f, 0.5f);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -348,12 +384,12 @@ __device__ __forceinline__ void load_cell(const CvArgs& a, const PixelCtx& c, co
             const int px = cx + (t & 1), py = cy + (t >> 1);
             ulonglong2 lo, hi;
             if (in_box) {
-                const int rp = rel + (t & 1) + (t >> 1) * CV_BOX_W;
+                const int rp = rel + (t & 1) + (t >> 1) * BOX_W;
                 lo = lds128p(sbox, rp, j);
                 hi = lds128p(sbox, rp, j + 4);
             } else if (px >= 0 && px < a.w && py >= 0 && py < a.h) {
                 const ulonglong2* g =
-                    reinterpret_cast<const ulonglong2*>(a.src + (static_cast<size_t>(c.b * a.h + py) * a.w + px) * CV_C);
+                    reinterpret_cast<const ulonglong2*>(a.src + (static_cast<size_t>(b * a.h + py) * a.w + px) * CV_C);
                 lo = __ldg(g + j);
                 hi = __ldg(g + j + 4);
             } else {
@@ -366,17 +402,33 @@ __device__ __forceinline__ void load_cell(const CvArgs& a, const PixelCtx& c, co
     }
 }
 
-constexpr int CV_STAGE_BYTES = CV_G * CV_TW * 4;   // one hypothesis of one tile row: 16 groups x 32 pixels
+// Refill the register cell from the pixel's table row: taps t00, t00+1, t00+nxp, t00+nxp+1.
+__device__ __forceinline__ void load_cell_table(const unsigned char* ptab_pix, int t00, int nxp, uint64_t (&P2)[4][8]) {
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const ulonglong2* p = reinterpret_cast<const ulonglong2*>(ptab_pix + (t00 + (t & 1) + (t >> 1) * nxp) * 64);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const ulonglong2 v = p[q];
+            P2[t][2 * q] = v.x;
+            P2[t][2 * q + 1] = v.y;
+        }
+    }
+}
+}  // namespace f3
 
-__global__ void __launch_bounds__(CV_THREADS, 2)
+__global__ void __launch_bounds__(f3::THREADS, 2)
 costvol_grouped_fwd_kernel(const __grid_constant__ CUtensorMap map_src, const __grid_constant__ CUtensorMap map_ref,
                            const __grid_constant__ CUtensorMap map_out, const CvArgs a) {
+    using namespace f3;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + CvSmem::OFF_BAR);
-    const float* ratio_s = reinterpret_cast<const float*>(smem + CvSmem::OFF_RATIO);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Smem::OFF_BAR);
+    const unsigned char* sbox = smem + Smem::OFF_SRC;
+    const unsigned char* rbox = smem + Smem::OFF_REF;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float* stage = reinterpret_cast<float*>(smem + CvSmem::OFF_STAGE + warp * 2 * CV_STAGE_BYTES);
+    unsigned char* ptab_pix = smem + Smem::OFF_PTAB + lane * PT_STRIDE;
+    float* stage = reinterpret_cast<float*>(smem + Smem::OFF_STAGE + warp * 2 * STAGE_ROW);
     if (tid == 0) {
         tma_prefetch_desc(&map_src);
         tma_prefetch_desc(&map_ref);
@@ -384,17 +436,183 @@ costvol_grouped_fwd_kernel(const __grid_constant__ CUtensorMap map_src, const __
         mbar_init(bar, 1);
         mbar_fence_init();
     }
-    uint32_t phase = 0;
+    __syncthreads();
+    uint32_t phase = 0, sbuf = 0;
     const int hw = a.h * a.w;
+    const int per_b = a.tiles_x * a.h;
     int iter = 0;
-    uint32_t sbuf = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++iter) {
+        const int b = tile / per_b;
+        const int trem = tile - b * per_b;
+        const int y = trem / a.tiles_x, txi = trem - y * a.tiles_x;
+        const int tx0 = txi * TW, x = tx0 + lane;
+        const bool lane_ok = x < a.w;
+        const int d0 = warp * a.DC, d1 = min(a.D, d0 + a.DC);
+        const int par = iter & 1;            // geo / foot / red are double buffered: no barrier against the previous tile
+        float* geo = reinterpret_cast<float*>(smem + Smem::OFF_GEO) + par * 32;
+        short4* foot = reinterpret_cast<short4*>(smem + Smem::OFF_FOOT) + par * WARPS * 32;
+        int* red = reinterpret_cast<int*>(smem + Smem::OFF_RED) + par * WARPS * 4;
+
+        if (tid < 12) {                      // P = (K @ T)[:3, :]   (movedepth/layers.py:609)
+            const int i = tid >> 2, j = tid & 3;
+            const float* Kb = a.K + b * 16;
+            const float* Tb = a.T + b * 16;
+            float s = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s = fmaf(Kb[i * 4 + k], Tb[k * 4 + j], s);
+            geo[tid] = s;
+        } else if (tid < 21) {               // inv_K[:3,:3]   (movedepth/layers.py:582)
+            const int q = tid - 12;
+            geo[12 + q] = a.invK[b * 16 + (q / 3) * 4 + (q % 3)];
+        }
+        __syncthreads();
+
         PixelCtx c;
-        tile_prologue(a, &map_src, &map_ref, smem, tile, iter, phase, c);
-        if (c.y >= a.h || c.d0 >= c.d1) continue;            // warp-uniform
-        const bool lane_ok = c.x < a.w;
-        const int ref_pix = (warp % CV_R) * CV_TW + lane;
-        const int tx0 = c.x - lane;
+        c.b = b;
+        c.x = x;
+        c.y = y;
+        c.d0 = d0;
+        c.d1 = d1;
+        {
+            const float xf = static_cast<float>(x), yf = static_cast<float>(y);
+            const float rx = fmaf(geo[12], xf, fmaf(geo[13], yf, geo[14]));
+            const float ry = fmaf(geo[15], xf, fmaf(geo[16], yf, geo[17]));
+            const float rz = fmaf(geo[18], xf, fmaf(geo[19], yf, geo[20]));
+            c.mrx = fmaf(geo[0], rx, fmaf(geo[1], ry, geo[2] * rz));
+            c.mry = fmaf(geo[4], rx, fmaf(geo[5], ry, geo[6] * rz));
+            c.mrz = fmaf(geo[8], rx, fmaf(geo[9], ry, geo[10] * rz));
+            c.tx = geo[3];
+            c.ty = geo[7];
+            c.tz = geo[11];
+        }
+        const int pix = y * a.w + (lane_ok ? x : a.w - 1);
+        const float prior_v = (a.hyps == nullptr) ? __ldg(a.prior + static_cast<size_t>(b) * hw + pix) : 0.f;
+        const float* hp = (a.hyps != nullptr) ? a.hyps + static_cast<size_t>(b) * a.D * hw + pix : nullptr;
+        const float* rp = (a.hyps == nullptr) ? a.ratio + static_cast<size_t>(b) * a.D : nullptr;
+
+        // ---- cells this (pixel, chunk) can touch: the projection of a depth interval is the segment
+        // between the projections of its end points as long as z stays positive.
+        short4 ft = make_short4(32767, -32768, 32767, -32768);     // empty
+        int bad = 0;
+        if (lane_ok && d0 < d1) {
+            float dmin, dmax;
+            if (hp != nullptr) {
+                dmin = 3.0e38f;
+                dmax = -3.0e38f;
+                for (int d = d0; d < d1; ++d) {
+                    const float dv = __ldg(hp + static_cast<size_t>(d) * hw);
+                    dmin = fminf(dmin, dv);
+                    dmax = fmaxf(dmax, dv);
+                }
+            } else {
+                const float d_a = prior_v * __ldg(rp + d0), d_b = prior_v * __ldg(rp + d1 - 1);
+                dmin = fminf(d_a, d_b);
+                dmax = fmaxf(d_a, d_b);
+            }
+            float u0, v0, z0, u1, v1, z1;
+            project_uv(c, dmin, u0, v0, z0);
+            project_uv(c, dmax, u1, v1, z1);
+            if (!(z0 > 1e-6f) || !(z1 > 1e-6f) || !(fabsf(u0) < 1e8f) || !(fabsf(u1) < 1e8f) || !(fabsf(v0) < 1e8f) ||
+                !(fabsf(v1) < 1e8f)) {
+                bad = 1;
+            } else {
+                const float wf = static_cast<float>(a.w), hf = static_cast<float>(a.h);
+                const float mnu = fminf(u0, u1), mxu = fmaxf(u0, u1), mnv = fminf(v0, v1), mxv = fmaxf(v0, v1);
+                if (mxu > -1.f && mnu < wf && mxv > -1.f && mnv < hf) {   // segment touches the image
+                    ft.x = static_cast<short>(floorf(fmaxf(mnu, -1.f)));
+                    ft.y = static_cast<short>(min(static_cast<int>(floorf(mxu)), a.w - 1));
+                    ft.z = static_cast<short>(floorf(fmaxf(mnv, -1.f)));
+                    ft.w = static_cast<short>(min(static_cast<int>(floorf(mxv)), a.h - 1));
+                }
+            }
+        }
+        foot[warp * 32 + lane] = ft;
+        {
+            const int lo_x = __reduce_min_sync(0xffffffffu, static_cast<int>(ft.x));
+            const int hi_x = __reduce_max_sync(0xffffffffu, static_cast<int>(ft.y));
+            const int lo_y = __reduce_min_sync(0xffffffffu, static_cast<int>(ft.z));
+            const int hi_y = __reduce_max_sync(0xffffffffu, static_cast<int>(ft.w));
+            if (lane == 0) {
+                red[warp * 4 + 0] = lo_x;
+                red[warp * 4 + 1] = hi_x;
+                red[warp * 4 + 2] = lo_y;
+                red[warp * 4 + 3] = hi_y;
+            }
+        }
+        const int any_bad = __syncthreads_or(bad);
+
+        // ---- tile box (TMA) and this pixel's table footprint (union over the 8 chunks)
+        int bx0 = 32767, bx1 = -32768, by0 = 32767, by1 = -32768;
+        int fx0 = 32767, fx1 = -32768, fy0 = 32767, fy1 = -32768;
+#pragma unroll
+        for (int wi = 0; wi < WARPS; ++wi) {
+            bx0 = min(bx0, red[wi * 4 + 0]);
+            bx1 = max(bx1, red[wi * 4 + 1]);
+            by0 = min(by0, red[wi * 4 + 2]);
+            by1 = max(by1, red[wi * 4 + 3]);
+            const short4 f = foot[wi * 32 + lane];
+            fx0 = min(fx0, static_cast<int>(f.x));
+            fx1 = max(fx1, static_cast<int>(f.y));
+            fy0 = min(fy0, static_cast<int>(f.z));
+            fy1 = max(fy1, static_cast<int>(f.w));
+        }
+        const bool box_empty = bx1 < bx0;
+        const bool boxed = a.use_tma && !any_bad && !box_empty && (bx1 - bx0 + 2 <= BOX_W) && (by1 - by0 + 2 <= BOX_H);
+        const int ox = bx0, oy = by0;
+        const int nxp = fx1 - fx0 + 2, nyp = fy1 - fy0 + 2;
+        const bool foot_empty = fx1 < fx0;
+        const bool tab_ok = a.use_table && !any_bad && (foot_empty || nxp * nyp <= NT);
+        const int ntaps = (tab_ok && !foot_empty && lane_ok) ? nxp * nyp : 0;
+
+        if (tid == 0) {
+            mbar_expect_tx(bar, Smem::REF_BYTES + (boxed ? Smem::SRC_BYTES : 0));
+            tma_load_4d(smem + Smem::OFF_REF, &map_ref, bar, 0, tx0, y, b);
+            if (boxed) tma_load_4d(smem + Smem::OFF_SRC, &map_src, bar, 0, ox, oy, b);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+
+        // ---- build the table: warp w computes taps w, w+8 of every pixel
+        if (__any_sync(0xffffffffu, warp < ntaps)) {
+            ulonglong2 rl[4], rh[4];
+            const uint64_t half2 = pk2(0.5f, 0.5f);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                rl[j] = lds128p(rbox, lane, j);
+                rh[j] = lds128p(rbox, lane, j + 4);
+                rl[j].x = mul2(rl[j].x, half2);
+                rl[j].y = mul2(rl[j].y, half2);
+                rh[j].x = mul2(rh[j].x, half2);
+                rh[j].y = mul2(rh[j].y, half2);
+            }
+            for (int t = warp; t < ntaps; t += WARPS) {
+                const int ty = t / nxp, tx = t - ty * nxp;
+                const int sx = fx0 + tx, sy = fy0 + ty;
+                const int rx = sx - ox, ry = sy - oy;
+                const bool in_box = boxed && rx >= 0 && rx < BOX_W && ry >= 0 && ry < BOX_H;
+                const bool in_img = sx >= 0 && sx < a.w && sy >= 0 && sy < a.h;
+                const ulonglong2* g = reinterpret_cast<const ulonglong2*>(
+                    a.src + (static_cast<size_t>(b * a.h + (in_img ? sy : 0)) * a.w + (in_img ? sx : 0)) * CV_C);
+                ulonglong2* dst = reinterpret_cast<ulonglong2*>(ptab_pix + t * 64);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    ulonglong2 lo, hi;
+                    if (in_box) {
+                        lo = lds128p(sbox, ry * BOX_W + rx, j);
+                        hi = lds128p(sbox, ry * BOX_W + rx, j + 4);
+                    } else if (in_img) {
+                        lo = __ldg(g + j);
+                        hi = __ldg(g + j + 4);
+                    } else {
+                        lo = make_ulonglong2(0ull, 0ull);
+                        hi = lo;
+                    }
+                    dst[j] = make_ulonglong2(fma2(rl[j].x, lo.x, mul2(rh[j].x, hi.x)), fma2(rl[j].y, lo.y, mul2(rh[j].y, hi.y)));
+                }
+            }
+        }
+        __syncthreads();
+        if (d0 >= d1) continue;                                   // warp-uniform (idle chunk: D < 8 * DC)
 
         uint64_t P2[4][8];
 #pragma unroll
@@ -402,21 +620,20 @@ costvol_grouped_fwd_kernel(const __grid_constant__ CUtensorMap map_src, const __
 #pragma unroll
             for (int k = 0; k < 8; ++k) P2[t][k] = 0ull;
         int cx = INT_MIN, cy = INT_MIN;
+        float* obase = a.out + static_cast<size_t>(b) * CV_G * a.D * hw;
 
-        const int pix = c.y * a.w + (lane_ok ? c.x : a.w - 1);
-        const float prior_v = (a.hyps == nullptr) ? __ldg(a.prior + static_cast<size_t>(c.b) * hw + pix) : 0.f;
-        const float* hp = (a.hyps != nullptr) ? a.hyps + static_cast<size_t>(c.b) * a.D * hw + pix : nullptr;
-        float* obase = a.out + static_cast<size_t>(c.b) * CV_G * a.D * hw;
-
-        for (int d = c.d0; d < c.d1; ++d) {
-            const float depth = hp ? __ldg(hp + static_cast<size_t>(d) * hw) : prior_v * ratio_s[d];
+        for (int d = d0; d < d1; ++d) {
+            const float depth = hp ? __ldg(hp + static_cast<size_t>(d) * hw) : prior_v * __ldg(rp + d);
             float u, v, pz;
             project_uv(c, depth, u, v, pz);
             const Bilinear s = bilinear_at(a, u, v);
             if (s.ok && (s.ix != cx || s.iy != cy)) {
                 cx = s.ix;
                 cy = s.iy;
-                load_cell(a, c, smem, ref_pix, cx, cy, P2);
+                if (tab_ok && cx >= fx0 && cx <= fx1 && cy >= fy0 && cy <= fy1)
+                    load_cell_table(ptab_pix, (cy - fy0) * nxp + (cx - fx0), nxp, P2);
+                else
+                    load_cell_direct(a, b, sbox, rbox, lane, boxed, ox, oy, cx, cy, P2);
             }
             const uint64_t w00 = pk2(s.w00, s.w00), w01 = pk2(s.w01, s.w01), w10 = pk2(s.w10, s.w10),
                            w11 = pk2(s.w11, s.w11);
@@ -425,7 +642,7 @@ costvol_grouped_fwd_kernel(const __grid_constant__ CUtensorMap map_src, const __
             for (int k = 0; k < 8; ++k) o2[k] = fma2(w11, P2[3][k], fma2(w10, P2[2][k], fma2(w01, P2[1][k], mul2(w00, P2[0][k]))));
 
             if (a.tma_store) {
-                float* buf = stage + sbuf * (CV_STAGE_BYTES / 4);
+                float* buf = stage + sbuf * (STAGE_ROW / 4);
                 if (lane == 0) bulk_wait_read<1>();          // the store issued two hypotheses ago has drained this buffer
                 __syncwarp();
                 if (a.layout == MVD_LAYOUT_BGDHW) {           // buf[g][lane]
@@ -433,19 +650,20 @@ costvol_grouped_fwd_kernel(const __grid_constant__ CUtensorMap map_src, const __
                     for (int k = 0; k < 8; ++k) {
                         float e, f;
                         unpk2(o2[k], e, f);
-                        buf[(2 * k) * CV_TW + lane] = e;
-                        buf[(2 * k + 1) * CV_TW + lane] = f;
+                        buf[(2 * k) * TW + lane] = e;
+                        buf[(2 * k + 1) * TW + lane] = f;
                     }
-                } else {                                      // buf[lane][g]
+                } else {                                      // buf[lane][g], 64B-swizzled like the output descriptor
                     ulonglong2* bp = reinterpret_cast<ulonglong2*>(buf + lane * CV_G);
+                    const int sw = (lane >> 1) & 3;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) bp[q] = make_ulonglong2(o2[2 * q], o2[2 * q + 1]);
+                    for (int q = 0; q < 4; ++q) bp[q ^ sw] = make_ulonglong2(o2[2 * q], o2[2 * q + 1]);
                 }
                 fence_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-                    if (a.layout == MVD_LAYOUT_BGDHW) tma_store_5d(&map_out, buf, tx0, c.y, d, 0, c.b);
-                    else tma_store_5d(&map_out, buf, 0, tx0, c.y, d, c.b);
+                    if (a.layout == MVD_LAYOUT_BGDHW) tma_store_5d(&map_out, buf, tx0, y, d, 0, b);
+                    else tma_store_5d(&map_out, buf, 0, tx0, y, d, b);
                     bulk_commit();
                 }
                 sbuf ^= 1u;
@@ -593,27 +811,28 @@ static int costvol_grouped_launch(bool bwd, CvArgs a, int C, int G, int flags, c
     MVD_REQUIRE(C == CV_C && G == CV_G, "grouped cost volume is built for C=32, G=16 (got C=%d, G=%d)", C, G);
     MVD_REQUIRE(a.B > 0 && a.h > 0 && a.w > 0 && a.D > 0, "empty shape B=%d h=%d w=%d D=%d", a.B, a.h, a.w, a.D);
     MVD_REQUIRE(a.D <= CV_MAXD, "D=%d exceeds the supported maximum %d", a.D, CV_MAXD);
+    MVD_REQUIRE(a.h < 32000 && a.w < 32000, "feature map %dx%d too large", a.h, a.w);
     MVD_REQUIRE(a.layout == MVD_LAYOUT_BGDHW || a.layout == MVD_LAYOUT_BDHWG, "unknown out_layout %d", a.layout);
     MVD_REQUIRE(a.hyps != nullptr || (a.prior != nullptr && a.ratio != nullptr), "need hyps or (prior, ratio)");
     MVD_REQUIRE(aligned16(a.ref) && aligned16(a.src) && aligned16(a.out) && aligned16(a.gout) && aligned16(a.gref) &&
                     aligned16(a.gsrc),
                 "feature / volume pointers must be 16-byte aligned");
     a.use_tma = (flags & MVD_FLAG_NO_TMA) ? 0 : 1;
+    a.use_table = (flags & MVD_FLAG_NO_TABLE) ? 0 : 1;
     a.tiles_x = (a.w + CV_TW - 1) / CV_TW;
-    a.tiles_y = (a.h + CV_R - 1) / CV_R;
-    a.num_tiles = a.tiles_x * a.tiles_y * a.B;
-    a.DC = (a.D + CV_NCH - 1) / CV_NCH;
 
     CUtensorMap map_src, map_ref;
-    int rc = make_nhwc32_tensor_map(&map_src, a.src, a.B, a.h, a.w, CV_BOX_W, CV_BOX_H);
-    if (rc) return rc;
-    rc = make_nhwc32_tensor_map(&map_ref, a.ref, a.B, a.h, a.w, CV_TW, CV_R);
-    if (rc) return rc;
-
-    const int smem = CvSmem::ALLOC;
-    const int per_sm = bwd ? 1 : 2;
-    const int grid = min(a.num_tiles, sm_count() * per_sm);
+    int rc;
     if (bwd) {
+        a.tiles_y = (a.h + CV_R - 1) / CV_R;
+        a.num_tiles = a.tiles_x * a.tiles_y * a.B;
+        a.DC = (a.D + CV_NCH - 1) / CV_NCH;
+        rc = make_nhwc32_tensor_map(&map_src, a.src, a.B, a.h, a.w, CV_BOX_W, CV_BOX_H);
+        if (rc) return rc;
+        rc = make_nhwc32_tensor_map(&map_ref, a.ref, a.B, a.h, a.w, CV_TW, CV_R);
+        if (rc) return rc;
+        const int smem = CvSmem::ALLOC;
+        const int grid = min(a.num_tiles, sm_count());
         cudaError_t e = cudaMemsetAsync(a.gref, 0, sizeof(float) * a.B * a.h * a.w * CV_C, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(a.gsrc, 0, sizeof(float) * a.B * a.h * a.w * CV_C, st);
         if (e != cudaSuccess) return fail(static_cast<int>(e), "costvol bwd memset: %s", cudaGetErrorString(e));
@@ -625,6 +844,15 @@ static int costvol_grouped_launch(bool bwd, CvArgs a, int C, int G, int flags, c
         costvol_grouped_bwd_kernel<<<grid, CV_THREADS, smem, st>>>(map_src, map_ref, a);
         return check_launch("costvol_grouped_bwd");
     }
+
+    // forward: one tile = one row of 32 pixels, 8 hypothesis chunks
+    a.tiles_y = a.h;
+    a.num_tiles = a.tiles_x * a.h * a.B;
+    a.DC = (a.D + f3::NCH - 1) / f3::NCH;
+    rc = make_nhwc32_tensor_map(&map_src, a.src, a.B, a.h, a.w, f3::BOX_W, f3::BOX_H);
+    if (rc) return rc;
+    rc = make_nhwc32_tensor_map(&map_ref, a.ref, a.B, a.h, a.w, f3::TW, 1);
+    if (rc) return rc;
     // output descriptor for the per-warp TMA stores (one hypothesis x one tile row x 16 groups per store)
     CUtensorMap map_out;
     const uint64_t W = a.w, H = a.h, Dd = a.D;
@@ -633,22 +861,24 @@ static int costvol_grouped_launch(bool bwd, CvArgs a, int C, int G, int flags, c
         if (a.w % 4 != 0) a.tma_store = 0;      // TMA needs 16-byte global strides; ragged widths use plain stores
         const uint64_t dims[5] = {W, H, Dd, CV_G, static_cast<uint64_t>(a.B)};
         const uint64_t str[4] = {W * 4, W * H * 4, W * H * Dd * 4, W * H * Dd * CV_G * 4};
-        const uint32_t box[5] = {CV_TW, 1, 1, CV_G, 1};
-        if (a.tma_store) rc = make_f32_tensor_map(&map_out, a.out, 5, dims, str, box);
+        const uint32_t box[5] = {f3::TW, 1, 1, CV_G, 1};
+        if (a.tma_store) rc = make_f32_tensor_map(&map_out, a.out, 5, dims, str, box, 0);
     } else {
         const uint64_t dims[5] = {CV_G, W, H, Dd, static_cast<uint64_t>(a.B)};
         const uint64_t str[4] = {CV_G * 4, W * CV_G * 4, W * H * CV_G * 4, W * H * Dd * CV_G * 4};
-        const uint32_t box[5] = {CV_G, CV_TW, 1, 1, 1};
-        rc = make_f32_tensor_map(&map_out, a.out, 5, dims, str, box);
+        const uint32_t box[5] = {CV_G, f3::TW, 1, 1, 1};
+        rc = make_f32_tensor_map(&map_out, a.out, 5, dims, str, box, 64);   // 64B swizzle: conflict-free staging writes
     }
     if (rc) return rc;
     if (!a.tma_store) map_out = map_ref;        // unused by the kernel, but must be a valid descriptor
+    const int smem = f3::Smem::ALLOC;
+    const int grid = min(a.num_tiles, sm_count() * 2);
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(costvol_grouped_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_done = true;
     }
-    costvol_grouped_fwd_kernel<<<grid, CV_THREADS, smem, st>>>(map_src, map_ref, map_out, a);
+    costvol_grouped_fwd_kernel<<<grid, f3::THREADS, smem, st>>>(map_src, map_ref, map_out, a);
     return check_launch("costvol_grouped_fwd");
 }
 

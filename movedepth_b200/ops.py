@@ -12,6 +12,7 @@ from . import _lib
 LAYOUT_BGDHW = 0
 LAYOUT_BDHWG = 1
 FLAG_NO_TMA = 1
+FLAG_NO_TABLE = 2
 
 # counts kernel launches issued through the C ABI (bench.py reports it as `gpu_launches`)
 launch_counter = {"n": 0}

@@ -40,7 +40,7 @@ def grouped_oracle(c, G=16):
 
 # ---------------------------------------------------------------------------------------------- K1
 @pytest.mark.parametrize("name", C.COSTVOL_CASES)
-@pytest.mark.parametrize("flags", [0, 1], ids=["tma", "gather"])
+@pytest.mark.parametrize("flags", [0, 1, 2, 3], ids=["tma", "gather", "tma-notable", "gather-notable"])
 @pytest.mark.parametrize("layout", [0, 1], ids=["bgdhw", "bdhwg"])
 def test_costvol_grouped_forward_backward(ops, name, flags, layout):
     """fused warp+gather+group-correlation vs oracle generate_costvol + group mean.
@@ -72,9 +72,10 @@ def test_costvol_grouped_explicit_hypotheses_equal_ratio_form(ops):
 def test_costvol_grouped_tma_and_gather_routes_agree_bitwise(ops):
     c = C.case_costvol("sideways", B=3, h=24, w=96, D=24)
     args = (g(c["ref"]), g(c["src"]), g(c["K"]), g(c["invK"]), g(c["pose"][:, 0]))
-    a = ops.costvol_grouped(*args, prior=g(c["prior"]), ratio=g(c["ratio"]), flags=0)
-    b = ops.costvol_grouped(*args, prior=g(c["prior"]), ratio=g(c["ratio"]), flags=1)
-    assert torch.equal(a, b)
+    outs = [ops.costvol_grouped(*args, prior=g(c["prior"]), ratio=g(c["ratio"]), flags=f, layout=l)
+            for f in (0, 1, 2, 3) for l in (0, 1)]          # TMA / gather x table / direct x both layouts
+    for o in outs[1:]:
+        assert torch.equal(outs[0], o)
 
 
 def test_costvol_grouped_identity_pose_is_plain_correlation(ops):
@@ -90,10 +91,25 @@ def test_costvol_grouped_ragged_shapes(ops):
     """width not a multiple of the 32-pixel tile, odd height, D not a multiple of the chunk count."""
     c = C.case_costvol("forward", B=1, h=7, w=45, D=5)
     _, _, want = grouped_oracle(c)
-    for flags in (0, 1):
+    for flags in (0, 1, 2):
+        for layout in (0, 1):
+            got = ops.costvol_grouped(g(c["ref"]), g(c["src"]), g(c["K"]), g(c["invK"]), g(c["pose"][:, 0]),
+                                      prior=g(c["prior"]), ratio=g(c["ratio"]), flags=flags, layout=layout)
+            torch.testing.assert_close(got.permute(0, 2, 1, 3, 4).cpu(), want.detach(), atol=2e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("name,hw,D", [("forward", (48, 160), 96), ("stress", (48, 160), 96), ("sideways", (80, 256), 128)])
+def test_costvol_grouped_matches_oracle_at_benchmark_shapes(ops, name, hw, D):
+    """One frame at the BASELINE config-2 / config-5 feature shapes (48x160 D=96, 80x256 D=128) against the oracle,
+    both layouts; `stress` is the degenerate pose whose footprints overflow the table and the TMA box."""
+    c = C.case_costvol(name, B=1, h=hw[0], w=hw[1], D=D)
+    with torch.no_grad():
+        want = OL.group_correlation(OL.cost_volume(c["ref"], c["src"], c["K"], c["invK"], c["hyps"], c["pose"]), 16)
+    scale = float(want.abs().max())
+    for layout in (0, 1):
         got = ops.costvol_grouped(g(c["ref"]), g(c["src"]), g(c["K"]), g(c["invK"]), g(c["pose"][:, 0]),
-                                  prior=g(c["prior"]), ratio=g(c["ratio"]), flags=flags)
-        torch.testing.assert_close(got.permute(0, 2, 1, 3, 4).cpu(), want.detach(), atol=2e-4, rtol=1e-4)
+                                  prior=g(c["prior"]), ratio=g(c["ratio"]), layout=layout)
+        torch.testing.assert_close(got.permute(0, 2, 1, 3, 4).cpu(), want, atol=2e-4 * max(1.0, scale), rtol=1e-4)
 
 
 def test_costvol_grouped_linearity_at_full_size(ops):
