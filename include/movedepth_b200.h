@@ -142,6 +142,17 @@ int mvd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
  * ------------------------------------------------------------------------------------- */
 int mvd_split_tf32(const float* x, float* out, long long n, int C, int pattern, void* stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Measurement helpers (bench.py's live cost-volume roofline): CUDA timing events that also
+ * work INSIDE a captured CUDA graph.  mvd_event_record with external != 0 uses
+ * cudaEventRecordExternal, i.e. the record becomes an event-record NODE when the stream is
+ * being captured and fires at every replay; mvd_event_elapsed_ms is cudaEventElapsedTime.
+ * ------------------------------------------------------------------------------------- */
+void* mvd_event_create(void);
+int mvd_event_record(void* event, void* stream, int external);
+int mvd_event_elapsed_ms(void* start, void* stop, float* ms);
+int mvd_event_destroy(void* event);
+
 #ifdef __cplusplus
 }
 #endif

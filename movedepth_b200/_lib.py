@@ -33,6 +33,10 @@ SIGNATURES = {
     "mvd_photometric_fwd": ([_P] * 8 + [_I] * 3 + [_F, _I, _P], _I),
     "mvd_photometric_bwd": ([_P] * 10 + [_I] * 3 + [_F, _P], _I),
     "mvd_split_tf32": ([_P, _P, _LL, _I, _I, _P], _I),
+    "mvd_event_create": ([], _P),
+    "mvd_event_record": ([_P, _P, _I], _I),
+    "mvd_event_elapsed_ms": ([_P, _P, ctypes.POINTER(ctypes.c_float)], _I),
+    "mvd_event_destroy": ([_P], _I),
     "mvd_adam_step": ([_P] * 4 + [_LL] + [_F] * 6 + [_P], _I),
 }
 

@@ -100,4 +100,30 @@ int mvd_version(void) { return MVD_ABI_VERSION; }
 const char* mvd_last_error_string(void) { return mvd::err_buf(); }
 int mvd_sm_count(void) { return mvd::sm_count(); }
 
+void* mvd_event_create(void) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDefault) != cudaSuccess) return nullptr;
+    return e;
+}
+
+int mvd_event_elapsed_ms(void* start, void* stop, float* ms) {
+    MVD_REQUIRE(start && stop && ms, "null argument");
+    cudaError_t e = cudaEventElapsedTime(ms, reinterpret_cast<cudaEvent_t>(start), reinterpret_cast<cudaEvent_t>(stop));
+    if (e != cudaSuccess) return mvd::fail(static_cast<int>(e), "cudaEventElapsedTime: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int mvd_event_destroy(void* event) {
+    if (event) cudaEventDestroy(reinterpret_cast<cudaEvent_t>(event));
+    return 0;
+}
+
+int mvd_event_record(void* event, void* stream, int external) {
+    MVD_REQUIRE(event != nullptr, "null event");
+    cudaError_t e = cudaEventRecordWithFlags(reinterpret_cast<cudaEvent_t>(event), mvd::as_stream(stream),
+                                             external ? cudaEventRecordExternal : cudaEventRecordDefault);
+    if (e != cudaSuccess) return mvd::fail(static_cast<int>(e), "cudaEventRecordWithFlags: %s", cudaGetErrorString(e));
+    return 0;
+}
+
 }

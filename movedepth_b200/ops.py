@@ -25,6 +25,28 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class TimingEvent:
+    """CUDA timing event that can also be recorded inside a captured graph (cudaEventRecordExternal): the record
+    then fires at every replay, and `elapsed_ms` reads the pair after a synchronize."""
+
+    def __init__(self):
+        self.handle = ctypes.c_void_p(_lib.lib().mvd_event_create())
+        if not self.handle:
+            raise RuntimeError("cudaEventCreate failed")
+
+    def record(self):
+        _lib.check(_lib.lib().mvd_event_record(self.handle, _stream(), 1 if torch.cuda.is_current_stream_capturing() else 0),
+                   "mvd_event_record")
+
+    def elapsed_ms(self, stop):
+        ms = ctypes.c_float(0)
+        _lib.check(_lib.lib().mvd_event_elapsed_ms(self.handle, stop.handle, ctypes.byref(ms)), "mvd_event_elapsed_ms")
+        return ms.value
+
+    def elapsed_time(self, stop):            # torch.cuda.Event spelling
+        return self.elapsed_ms(stop)
+
+
 def _p(t):
     if t is None:
         return ctypes.c_void_p(0)
@@ -68,7 +90,7 @@ class _CostVolumeGrouped(torch.autograd.Function):
         out = torch.empty((B, groups, D, h, w), device=ref.device, dtype=torch.float32, memory_format=fmt)
         ev = None
         if costvol_events is not None:
-            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev = (TimingEvent(), TimingEvent())
             ev[0].record()
         rc = _lib.lib().mvd_costvol_grouped_fwd(_p(ref_cl), _p(src_cl), _p(prior_c), _p(ratio_c), _p(hyps), _p(K),
                                                 _p(invK), _p(T), _p(out), B, C, groups, h, w, D, layout, flags, _stream())

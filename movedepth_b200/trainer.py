@@ -185,6 +185,7 @@ class Trainer:
         if o.ddp:
             o.log_frequency = max(1, o.log_frequency // self.world_size)
         self._aug_box = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self._static_inputs, self._graphs, self._graph_warm, self._graph_pool, self._graph_stream = None, {}, {}, None, None
         self.set_train()
 
     # ------------------------------------------------------------------ mode switches
@@ -231,13 +232,22 @@ class Trainer:
             self.step += 1
 
     def train_step(self, inputs, noise=None, mask_xy=None):
-        """process_batch + zero_grad + backward + optimizer.step (movedepth/trainer.py:269-272)."""
+        """process_batch + zero_grad + backward + optimizer.step (movedepth/trainer.py:269-272).
+        With `--b200_cuda_graph` (and no test overrides) the whole forward + backward + gradient exchange is one
+        CUDA graph replayed per step: `inputs` are copied into static device buffers first."""
+        if getattr(self.opt, "b200_cuda_graph", False) and noise is None and mask_xy is None:
+            return self._graph_step(inputs)
+        outputs, losses = self._forward_backward(inputs, noise, mask_xy)
+        self._optimizer_step()
+        return outputs, losses
+
+    def _forward_backward(self, inputs, noise=None, mask_xy=None):
         for a in self.arenas:
             a.grad.zero_()
         outputs, losses = self.process_batch(inputs, is_train=True, noise=noise, mask_xy=mask_xy)
         multi = self.opt.ddp and self.world_size > 1
         # the two graphs share nothing but detached tensors: back-propagate them separately so the
-        # cost-volume branch keeps fp32 convolutions and its gradients can be reduced early
+        # cost-volume branch's gradients can be reduced while the mono/pose branch is still running
         self._tf32("mvs")
         losses["_mvs_total"].backward()
         work = dist.all_reduce(self.arenas[1].grad, async_op=True) if multi else None
@@ -246,9 +256,61 @@ class Trainer:
         if multi:
             dist.all_reduce(self.arenas[0].grad)
             work.wait()
+        return outputs, losses
+
+    def _optimizer_step(self):
         self.opt_step += 1
         for a, lr in zip(self.arenas, self.current_lrs()):
             ops.adam_step(a.data, a.grad, a.exp_avg, a.exp_avg_sq, self.opt_step, lr, grad_scale=1.0 / self.world_size)
+
+    # ------------------------------------------------------------------ CUDA-graph step
+    GRAPH_WARMUP = 3          # eager steps before capture (cuDNN autotuning, lazy initialisation, NCCL warm-up)
+
+    def _stage_inputs(self, inputs):
+        """host (pinned) or device item dict -> the static device buffers the graph reads."""
+        if self._static_inputs is None:
+            self._static_inputs = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device)
+                                   for k, v in inputs.items() if torch.is_tensor(v)}
+            self._aug_box_host = torch.zeros(2, dtype=torch.int64).pin_memory()
+        for k, buf in self._static_inputs.items():
+            buf.copy_(inputs[k], non_blocking=True)
+        o = self.opt
+        fh, fw = o.height // 3, o.width // 3
+        self._aug_box_host[0] = np.random.randint(0, o.width - fw)        # x first, as the reference (layers.py:64-65)
+        self._aug_box_host[1] = np.random.randint(0, o.height - fh)
+        self._aug_box.copy_(self._aug_box_host, non_blocking=True)
+        return dict(self._static_inputs)
+
+    def _graph_step(self, inputs):
+        static = self._stage_inputs(inputs)
+        key = self.epoch > self.opt.ztrans_start_epc      # the only data-independent branch of the step (trainer.py:336)
+        g = self._graphs.get(key)
+        if g is None:
+            # Warm-up and capture both run on one side stream: autograd's AccumulateGrad nodes remember the stream they
+            # were created on, and a node created on the legacy default stream would invalidate the capture.
+            if self._graph_stream is None:
+                self._graph_stream = torch.cuda.Stream()
+            side, cur = self._graph_stream, torch.cuda.current_stream()
+            side.wait_stream(cur)
+            if self._graph_warm.get(key, 0) < self.GRAPH_WARMUP:
+                self._graph_warm[key] = self._graph_warm.get(key, 0) + 1
+                with torch.cuda.stream(side):
+                    outputs, losses = self._forward_backward(static, mask_xy="preset")
+                    self._optimizer_step()
+                cur.wait_stream(side)
+                return outputs, losses
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = ops.launch_counter["n"]
+            with torch.cuda.graph(graph, pool=self._graph_pool, stream=side):
+                outputs, losses = self._forward_backward(static, mask_xy="preset")
+            g = self._graphs[key] = (graph, outputs, losses, ops.launch_counter["n"] - n0)
+            if self._graph_pool is None:
+                self._graph_pool = graph.pool()
+        graph, outputs, losses, launches = g
+        graph.replay()
+        ops.launch_counter["n"] += launches
+        self._optimizer_step()
         return outputs, losses
 
     # ------------------------------------------------------------------ forward + losses
@@ -330,7 +392,8 @@ class Trainer:
         fh, fw = o.height // 3, o.width // 3
         if mask_xy is None:
             mask_xy = (np.random.randint(0, o.width - fw), np.random.randint(0, o.height - fh))   # x first, as the reference
-        self._aug_box.copy_(torch.tensor(mask_xy, dtype=torch.int64), non_blocking=True)
+        if mask_xy != "preset":              # "preset": the caller already wrote the box corner into self._aug_box (graph step)
+            self._aug_box.copy_(torch.tensor(mask_xy, dtype=torch.int64), non_blocking=True)
         ys = torch.arange(o.height, device=self.device).view(1, 1, -1, 1)
         xs = torch.arange(o.width, device=self.device).view(1, 1, 1, -1)
         inside = (xs >= self._aug_box[0]) & (xs < self._aug_box[0] + fw) & (ys >= self._aug_box[1]) & (ys < self._aug_box[1] + fh)

@@ -302,3 +302,39 @@ def test_step_under_default_3xtf32_policy_stays_within_the_depth_bar():
     assert frac > 0.97, frac
     for k in ("loss/0", "fuse_reproj_loss"):
         assert abs(float(losses[k]) - float(gold["loss/" + k])) < 1e-2 * abs(float(gold["loss/" + k])), k
+
+
+def test_cuda_graph_step_tracks_the_eager_step():
+    """`--b200_cuda_graph`: forward + backward replayed as one CUDA graph.  Before every step the graphed trainer is
+    given the eager trainer's parameters and Adam moments (training from random init is chaotic: argmax flips amplify
+    the 1e-5 * N(0,1) auto-mask tie-break noise, which comes from a different generator offset), then both take the
+    step on the same batch and augmentation box: loss within 1e-3 relative, updated parameters equal to 1e-5."""
+    from movedepth_b200.options import MonodepthOptions
+    from movedepth_b200.trainer import Trainer, SyntheticKITTI
+    cfg = C.STEP_CASES["r18_2f"]
+    base = ["--height", str(cfg["H"]), "--width", str(cfg["W"]), "--num_depth_bins", str(cfg["D"]), "--batch_size", "2",
+            "--weights_init", "scratch", "--convex_up", "--learning_rate", "2e-4", "--b200_conv_precision", "fp32",
+            "--log_dir", "/tmp/mvd_test", "--frame_ids", "0", "-1"]
+    trainers = []
+    for extra in ([], ["--b200_cuda_graph"]):
+        tr = Trainer(MonodepthOptions().parse(base + extra))
+        for k, m in tr.models.items():
+            fill_deterministic(m, salt=k + "/")
+        trainers.append(tr)
+    eager, graphed = trainers
+    for i, batch in enumerate(SyntheticKITTI(eager.opt, 2, 6, seed=3)):
+        for a, b in zip(eager.arenas, graphed.arenas):
+            b.data.copy_(a.data)
+            b.exp_avg.copy_(a.exp_avg)
+            b.exp_avg_sq.copy_(a.exp_avg_sq)
+        for m_e, m_g in zip(eager.models.values(), graphed.models.values()):
+            for be, bg in zip(m_e.buffers(), m_g.buffers()):
+                bg.copy_(be)                                          # BatchNorm running statistics
+        losses = []
+        for tr in (eager, graphed):
+            np.random.seed(100 + i)
+            losses.append(float(tr.train_step(batch)[1]["loss"].detach()))
+        assert abs(losses[1] - losses[0]) <= 1e-3 * abs(losses[0]), (i, losses)
+        for a, b in zip(eager.arenas, graphed.arenas):
+            torch.testing.assert_close(b.data, a.data, atol=1e-5, rtol=1e-3)
+    assert len(graphed._graphs) == 1, "the graph was never captured"
