@@ -111,6 +111,21 @@ def run_reference(args):
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def shutdown(tr, world):
+    """Orderly multi-rank exit: drop the captured graphs (they hold NCCL work), meet at a barrier, then leave without
+    running interpreter teardown (a captured communicator can block in its destructor)."""
+    import torch
+    import torch.distributed as dist
+    torch.cuda.synchronize()
+    if world > 1:
+        tr._graphs.clear()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def run_own(args):
     import torch
     import torch.distributed as dist
@@ -192,6 +207,7 @@ def run_own(args):
     sampler.join(timeout=2)
 
     if rank != 0:
+        shutdown(tr, world)
         return
     frames = BATCH * world * args.steps
     pk, pk_src = peaks()
@@ -220,9 +236,8 @@ def run_own(args):
         fps, sec, cores = time_oracle(3, 1, batch=1)
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                                 "sample": "1 frame of the workload per step (same shapes, D=96), 3 timed steps after 1 warm-up"}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    shutdown(tr, world)
 
 
 def main():

@@ -33,6 +33,8 @@ extern "C" {
 /* flags */
 #define MVD_FLAG_NO_TMA 1   /* no TMA staging: taps are gathered from global memory (debug / parity isolation) */
 #define MVD_FLAG_NO_TABLE 2 /* forward: no per-pixel tap-correlation table, recompute each bilinear cell directly */
+#define MVD_FLAG_DBG_NO_STORE 4  /* forward, profiling only: compute everything but do not issue the TMA stores */
+#define MVD_FLAG_PLAIN_STORE 16  /* forward: TMA-staged loads, but plain st.global instead of TMA stores */
 
 int mvd_version(void);
 const char* mvd_last_error_string(void);

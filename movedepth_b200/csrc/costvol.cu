@@ -56,6 +56,7 @@ struct CvArgs {
     int layout;
     int use_tma;
     int use_table;
+    int dbg_nostore;
     int tma_store;
     int tiles_x, tiles_y, num_tiles;
     int DC;              // hypotheses per chunk
@@ -328,15 +329,20 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// ---- forward, v3 ---------------------------------------------------------------------------------
+// ---- forward, v4 ---------------------------------------------------------------------------------
 // Tile = one row of 32 reference pixels x all D; warp = chunk of D/8 hypotheses, lane = pixel.
-// Over the whole hypothesis range a pixel's epipolar segment is only a few source pixels long, so
-// the per-tap group correlations  P_tap[g] = 1/2 * sum_{c in {g,g+16}} ref[c] * src_tap[c]  of
-// every tap the pixel can touch are computed ONCE per tile (8 warps share the taps of a pixel) into
-// a shared-memory table; the hypothesis loop refills its register-resident bilinear cell from
-// that table with 16 LDS.128 instead of recomputing 128 products whenever one lane of the warp
-// crosses a cell boundary.  Pixels whose footprint does not fit the table (degenerate poses)
-// fall back to the direct computation from the staged source box / global memory.
+//  * Over the whole hypothesis range a pixel's epipolar segment is only a few source pixels long, so
+//    the per-tap group correlations  P_tap[g] = 1/2 * sum_{c in {g,g+16}} ref[c] * src_tap[c]  of
+//    every tap the pixel can touch are computed ONCE per tile (8 warps share the taps of a pixel) into
+//    a shared-memory table; the hypothesis loop refills its register-resident bilinear cell from that
+//    table with 16 LDS.128 instead of recomputing 128 products whenever one lane of the warp crosses
+//    a cell boundary.  Pixels whose footprint does not fit the table (degenerate poses) fall back to
+//    the direct computation from global memory.
+//  * The persistent tile loop is software pipelined: while the warps run the hypothesis loop of tile
+//    i, the source box and reference row of tile i+1 are already in flight (their footprints are
+//    computed right after the table of tile i is finished, warp 0 issues the TMA loads from behind a
+//    named barrier the other warps only arrive at), and the prior / ratio values of tile i+1 are
+//    prefetched into registers one stage earlier.
 namespace f3 {
 constexpr int TW = 32;
 constexpr int NCH = 8;                      // hypothesis chunks = warps per CTA
@@ -347,6 +353,8 @@ constexpr int BOX_H = 6;
 constexpr int NT = 16;                      // table capacity: taps per pixel
 constexpr int PT_STRIDE = NT * 64 + 16;     // bytes per pixel; the 16 B pad makes 8 consecutive lanes hit 8 bank groups
 constexpr int STAGE_ROW = CV_G * TW * 4;    // one hypothesis of the tile row: 16 groups x 32 pixels
+constexpr int MAXB = 16;                    // batch items per launch (their geometry lives in shared memory)
+constexpr int GEO_STRIDE = 24;              // floats per batch item: (K@T)[:3,:4] row-major, then inv_K[:3,:3]
 
 struct Smem {
     static constexpr int SRC_BYTES = BOX_W * BOX_H * 128;
@@ -356,25 +364,29 @@ struct Smem {
     static constexpr int OFF_PTAB = OFF_REF + REF_BYTES;
     static constexpr int OFF_STAGE = OFF_PTAB + TW * PT_STRIDE;         // per-warp double-buffered output rows
     static constexpr int OFF_FOOT = OFF_STAGE + WARPS * 2 * STAGE_ROW;  // [2][WARPS][32] short4 cell ranges
-    static constexpr int OFF_GEO = OFF_FOOT + 2 * WARPS * 32 * 8;       // [2][32] floats
-    static constexpr int OFF_RED = OFF_GEO + 2 * 32 * 4;                // [2][WARPS][4] ints
-    static constexpr int OFF_BAR = OFF_RED + 2 * WARPS * 4 * 4;
+    static constexpr int OFF_RED = OFF_FOOT + 2 * WARPS * 32 * 8;       // [2][WARPS][8] ints
+    static constexpr int OFF_GEO = OFF_RED + 2 * WARPS * 8 * 4;         // [MAXB][GEO_STRIDE] floats
+    static constexpr int OFF_BAR = OFF_GEO + MAXB * GEO_STRIDE * 4;
     static constexpr int TOTAL = OFF_BAR + 16;
     static constexpr int ALLOC = TOTAL + 1024;                          // slack for manual 1024 B alignment
 };
 static_assert(Smem::OFF_REF % 1024 == 0 && Smem::OFF_STAGE % 512 == 0, "TMA alignment");
+static_assert(2 * (Smem::ALLOC + 1024) <= 233472, "two CTAs per SM");
 
-// Direct computation of the four per-tap group correlations of cell (cx,cy) (no table).
-__device__ __forceinline__ void load_cell_direct(const CvArgs& a, int b, const unsigned char* sbox,
-                                                 const unsigned char* rbox, int ref_pix, bool boxed, int ox, int oy,
-                                                 int cx, int cy, uint64_t (&P2)[4][8]) {
-    const int rx = cx - ox, ry = cy - oy;
-    const bool in_box = boxed && rx >= 0 && rx <= BOX_W - 2 && ry >= 0 && ry <= BOX_H - 2;
-    const int rel = ry * BOX_W + rx;
+__device__ __forceinline__ float rcp_approx(float x) {       // MUFU.RCP, 1 ulp
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Direct computation of the four per-tap group correlations of cell (cx,cy) from global memory (no table).
+__device__ __forceinline__ void load_cell_direct(const CvArgs& a, int b, int ref_pix_global, int cx, int cy,
+                                                 uint64_t (&P2)[4][8]) {
+    const ulonglong2* rg = reinterpret_cast<const ulonglong2*>(a.ref + static_cast<size_t>(ref_pix_global) * CV_C);
     const uint64_t half2 = pk2(0.5f, 0.5f);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        ulonglong2 rl = lds128p(rbox, ref_pix, j), rh = lds128p(rbox, ref_pix, j + 4);
+        ulonglong2 rl = __ldg(rg + j), rh = __ldg(rg + j + 4);
         rl.x = mul2(rl.x, half2);
         rl.y = mul2(rl.y, half2);
         rh.x = mul2(rh.x, half2);
@@ -382,19 +394,12 @@ __device__ __forceinline__ void load_cell_direct(const CvArgs& a, int b, const u
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const int px = cx + (t & 1), py = cy + (t >> 1);
-            ulonglong2 lo, hi;
-            if (in_box) {
-                const int rp = rel + (t & 1) + (t >> 1) * BOX_W;
-                lo = lds128p(sbox, rp, j);
-                hi = lds128p(sbox, rp, j + 4);
-            } else if (px >= 0 && px < a.w && py >= 0 && py < a.h) {
+            ulonglong2 lo = make_ulonglong2(0ull, 0ull), hi = lo;
+            if (px >= 0 && px < a.w && py >= 0 && py < a.h) {
                 const ulonglong2* g =
                     reinterpret_cast<const ulonglong2*>(a.src + (static_cast<size_t>(b * a.h + py) * a.w + px) * CV_C);
                 lo = __ldg(g + j);
                 hi = __ldg(g + j + 4);
-            } else {
-                lo = make_ulonglong2(0ull, 0ull);
-                hi = lo;
             }
             P2[t][2 * j] = fma2(rl.x, lo.x, mul2(rh.x, hi.x));
             P2[t][2 * j + 1] = fma2(rl.y, lo.y, mul2(rh.y, hi.y));
@@ -415,6 +420,143 @@ __device__ __forceinline__ void load_cell_table(const unsigned char* ptab_pix, i
         }
     }
 }
+
+struct Geom {
+    float mrx, mry, mrz, tx, ty, tz;   // p(depth) = depth * mr + t
+};
+
+// r = inv_K[:3,:3] (x,y,1);  mr = (K T)[:3,:3] r;  t = (K T)[:3,3]    (movedepth/layers.py:581-586, 601-621)
+__device__ __forceinline__ Geom pixel_geom(const float* geo, int x, int y) {
+    const float xf = static_cast<float>(x), yf = static_cast<float>(y);
+    const float rx = fmaf(geo[12], xf, fmaf(geo[13], yf, geo[14]));
+    const float ry = fmaf(geo[15], xf, fmaf(geo[16], yf, geo[17]));
+    const float rz = fmaf(geo[18], xf, fmaf(geo[19], yf, geo[20]));
+    Geom c;
+    c.mrx = fmaf(geo[0], rx, fmaf(geo[1], ry, geo[2] * rz));
+    c.mry = fmaf(geo[4], rx, fmaf(geo[5], ry, geo[6] * rz));
+    c.mrz = fmaf(geo[8], rx, fmaf(geo[9], ry, geo[10] * rz));
+    c.tx = geo[3];
+    c.ty = geo[7];
+    c.tz = geo[11];
+    return c;
+}
+
+struct TileXY {
+    int b, y, tx0;
+};
+__device__ __forceinline__ TileXY tile_xy(const CvArgs& a, int tile) {
+    const int per_b = a.tiles_x * a.h;
+    TileXY t;
+    t.b = tile / per_b;
+    const int trem = tile - t.b * per_b;
+    t.y = trem / a.tiles_x;
+    t.tx0 = (trem - t.y * a.tiles_x) * TW;
+    return t;
+}
+
+// Tile box / per-pixel table footprint, derived identically by every thread from the per-warp
+// reductions (`red`) and per-(chunk, pixel) cell ranges (`foot`) that footprint_stage left in shared memory.
+struct Footprint {
+    int fx0, fx1, fy0, fy1, nxp;   // cells the pixel can touch (inclusive); taps per table row
+    int ox, oy;                    // staged source box origin
+    bool boxed, tab_ok;
+    int ntaps;
+};
+__device__ __forceinline__ void tile_box(const CvArgs& a, const int* red, int& ox, int& oy, bool& boxed, bool& any_bad) {
+    int bx0 = 32767, bx1 = -32768, by0 = 32767, by1 = -32768, bad = 0;
+#pragma unroll
+    for (int wi = 0; wi < WARPS; ++wi) {
+        bx0 = min(bx0, red[wi * 8 + 0]);
+        bx1 = max(bx1, red[wi * 8 + 1]);
+        by0 = min(by0, red[wi * 8 + 2]);
+        by1 = max(by1, red[wi * 8 + 3]);
+        bad |= red[wi * 8 + 4];
+    }
+    any_bad = bad != 0;
+    boxed = a.use_tma && !any_bad && (bx1 >= bx0) && (bx1 - bx0 + 2 <= BOX_W) && (by1 - by0 + 2 <= BOX_H);
+    ox = bx0;
+    oy = by0;
+}
+
+// Stage F of the pipeline: which source cells can (pixel, chunk) touch?  The projection of a depth
+// interval is the segment between the projections of its end points as long as z stays positive.
+__device__ __forceinline__ void footprint_stage(const CvArgs& a, const CUtensorMap* map_src, const CUtensorMap* map_ref,
+                                                unsigned char* smem, int tile, int par, float prior_v, float ra, float rb) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const TileXY t = tile_xy(a, tile);
+    const int x = t.tx0 + lane;
+    const bool lane_ok = x < a.w;
+    const int d0 = warp * a.DC, d1 = min(a.D, d0 + a.DC);
+    short4* foot = reinterpret_cast<short4*>(smem + Smem::OFF_FOOT) + par * WARPS * 32;
+    int* red = reinterpret_cast<int*>(smem + Smem::OFF_RED) + par * WARPS * 8;
+    const Geom c = pixel_geom(reinterpret_cast<const float*>(smem + Smem::OFF_GEO) + t.b * GEO_STRIDE, x, t.y);
+
+    short4 ft = make_short4(32767, -32768, 32767, -32768);     // empty
+    int bad = 0;
+    if (lane_ok && d0 < d1) {
+        float dmin, dmax;
+        if (a.hyps != nullptr) {
+            const int hw = a.h * a.w;
+            const float* hp = a.hyps + static_cast<size_t>(t.b) * a.D * hw + t.y * a.w + x;
+            dmin = 3.0e38f;
+            dmax = -3.0e38f;
+            for (int d = d0; d < d1; ++d) {
+                const float dv = __ldg(hp + static_cast<size_t>(d) * hw);
+                dmin = fminf(dmin, dv);
+                dmax = fmaxf(dmax, dv);
+            }
+        } else {
+            const float d_a = prior_v * ra, d_b = prior_v * rb;
+            dmin = fminf(d_a, d_b);
+            dmax = fmaxf(d_a, d_b);
+        }
+        const float z0 = fmaf(dmin, c.mrz, c.tz) + 1e-7f, z1 = fmaf(dmax, c.mrz, c.tz) + 1e-7f;   // same arithmetic as the
+        const float i0 = rcp_approx(z0), i1 = rcp_approx(z1);                                     // hypothesis loop
+        const float u0 = fmaf(dmin, c.mrx, c.tx) * i0, v0 = fmaf(dmin, c.mry, c.ty) * i0;
+        const float u1 = fmaf(dmax, c.mrx, c.tx) * i1, v1 = fmaf(dmax, c.mry, c.ty) * i1;
+        if (!(z0 > 1e-6f) || !(z1 > 1e-6f) || !(fabsf(u0) < 1e8f) || !(fabsf(u1) < 1e8f) || !(fabsf(v0) < 1e8f) ||
+            !(fabsf(v1) < 1e8f)) {
+            bad = 1;
+        } else {
+            const float wf = static_cast<float>(a.w), hf = static_cast<float>(a.h);
+            const float mnu = fminf(u0, u1), mxu = fmaxf(u0, u1), mnv = fminf(v0, v1), mxv = fmaxf(v0, v1);
+            if (mxu > -1.f && mnu < wf && mxv > -1.f && mnv < hf) {   // segment touches the image
+                ft.x = static_cast<short>(floorf(fmaxf(mnu, -1.f)));
+                ft.y = static_cast<short>(min(static_cast<int>(floorf(mxu)), a.w - 1));
+                ft.z = static_cast<short>(floorf(fmaxf(mnv, -1.f)));
+                ft.w = static_cast<short>(min(static_cast<int>(floorf(mxv)), a.h - 1));
+            }
+        }
+    }
+    foot[warp * 32 + lane] = ft;
+    const int lo_x = __reduce_min_sync(0xffffffffu, static_cast<int>(ft.x));
+    const int hi_x = __reduce_max_sync(0xffffffffu, static_cast<int>(ft.y));
+    const int lo_y = __reduce_min_sync(0xffffffffu, static_cast<int>(ft.z));
+    const int hi_y = __reduce_max_sync(0xffffffffu, static_cast<int>(ft.w));
+    const int wbad = __any_sync(0xffffffffu, bad);
+    if (lane == 0) {
+        red[warp * 8 + 0] = lo_x;
+        red[warp * 8 + 1] = hi_x;
+        red[warp * 8 + 2] = lo_y;
+        red[warp * 8 + 3] = hi_y;
+        red[warp * 8 + 4] = wbad;
+    }
+    // Hand-off: warps 1..7 only arrive at named barrier 1 and go on; warp 0 waits for all of them and issues the loads.
+    if (warp != 0) {
+        asm volatile("bar.arrive 1, %0;" ::"n"(THREADS) : "memory");
+    } else {
+        asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+        int ox, oy;
+        bool boxed, any_bad;
+        tile_box(a, red, ox, oy, boxed, any_bad);
+        if (lane == 0) {
+            uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Smem::OFF_BAR);
+            mbar_expect_tx(bar, Smem::REF_BYTES + (boxed ? Smem::SRC_BYTES : 0));
+            tma_load_4d(smem + Smem::OFF_REF, map_ref, bar, 0, t.tx0, t.y, t.b);
+            if (boxed) tma_load_4d(smem + Smem::OFF_SRC, map_src, bar, 0, ox, oy, t.b);
+        }
+    }
+}
 }  // namespace f3
 
 __global__ void __launch_bounds__(f3::THREADS, 2)
@@ -426,9 +568,30 @@ costvol_grouped_fwd_kernel(const __grid_constant__ CUtensorMap map_src, const __
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + Smem::OFF_BAR);
     const unsigned char* sbox = smem + Smem::OFF_SRC;
     const unsigned char* rbox = smem + Smem::OFF_REF;
+    float* geo_all = reinterpret_cast<float*>(smem + Smem::OFF_GEO);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned char* ptab_pix = smem + Smem::OFF_PTAB + lane * PT_STRIDE;
     float* stage = reinterpret_cast<float*>(smem + Smem::OFF_STAGE + warp * 2 * STAGE_ROW);
+    const int hw = a.h * a.w;
+    const int d0 = warp * a.DC, d1 = min(a.D, d0 + a.DC), n = d1 - d0;
+
+    // ---- geometry of every batch item, once per CTA
+    for (int e = tid; e < a.B * 21; e += THREADS) {
+        const int bb = e / 21, q = e - bb * 21;
+        float v;
+        if (q < 12) {                        // P = (K @ T)[:3, :]   (movedepth/layers.py:609)
+            const int i = q >> 2, j = q & 3;
+            const float* Kb = a.K + bb * 16;
+            const float* Tb = a.T + bb * 16;
+            v = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v = fmaf(Kb[i * 4 + k], Tb[k * 4 + j], v);
+        } else {                             // inv_K[:3,:3]   (movedepth/layers.py:582)
+            const int r = q - 12;
+            v = a.invK[bb * 16 + (r / 3) * 4 + (r % 3)];
+        }
+        geo_all[bb * GEO_STRIDE + q] = v;
+    }
     if (tid == 0) {
         tma_prefetch_desc(&map_src);
         tma_prefetch_desc(&map_ref);
@@ -437,139 +600,61 @@ costvol_grouped_fwd_kernel(const __grid_constant__ CUtensorMap map_src, const __
         mbar_fence_init();
     }
     __syncthreads();
+
+    // prior / chunk-end ratios of a tile, fetched one pipeline stage ahead of their use
+    float pf_prior = 0.f, pf_ra = 0.f, pf_rb = 0.f;
+    auto prefetch = [&](int tile) {
+        if (a.hyps != nullptr || n <= 0) return;
+        const TileXY t = tile_xy(a, tile);
+        const int xx = min(t.tx0 + lane, a.w - 1);
+        pf_prior = __ldg(a.prior + static_cast<size_t>(t.b) * hw + t.y * a.w + xx);
+        pf_ra = __ldg(a.ratio + static_cast<size_t>(t.b) * a.D + d0);
+        pf_rb = __ldg(a.ratio + static_cast<size_t>(t.b) * a.D + d1 - 1);
+    };
+
+    int tile = blockIdx.x;
+    if (tile < a.num_tiles) {
+        prefetch(tile);
+        footprint_stage(a, &map_src, &map_ref, smem, tile, 0, pf_prior, pf_ra, pf_rb);
+    }
+    __syncthreads();
+
     uint32_t phase = 0, sbuf = 0;
-    const int hw = a.h * a.w;
-    const int per_b = a.tiles_x * a.h;
-    int iter = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++iter) {
-        const int b = tile / per_b;
-        const int trem = tile - b * per_b;
-        const int y = trem / a.tiles_x, txi = trem - y * a.tiles_x;
-        const int tx0 = txi * TW, x = tx0 + lane;
+    for (int iter = 0; tile < a.num_tiles; tile += gridDim.x, ++iter) {
+        const int par = iter & 1;
+        const int next = tile + gridDim.x;
+        const TileXY t = tile_xy(a, tile);
+        const int b = t.b, y = t.y, tx0 = t.tx0, x = tx0 + lane;
         const bool lane_ok = x < a.w;
-        const int d0 = warp * a.DC, d1 = min(a.D, d0 + a.DC);
-        const int par = iter & 1;            // geo / foot / red are double buffered: no barrier against the previous tile
-        float* geo = reinterpret_cast<float*>(smem + Smem::OFF_GEO) + par * 32;
-        short4* foot = reinterpret_cast<short4*>(smem + Smem::OFF_FOOT) + par * WARPS * 32;
-        int* red = reinterpret_cast<int*>(smem + Smem::OFF_RED) + par * WARPS * 4;
-
-        if (tid < 12) {                      // P = (K @ T)[:3, :]   (movedepth/layers.py:609)
-            const int i = tid >> 2, j = tid & 3;
-            const float* Kb = a.K + b * 16;
-            const float* Tb = a.T + b * 16;
-            float s = 0.f;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) s = fmaf(Kb[i * 4 + k], Tb[k * 4 + j], s);
-            geo[tid] = s;
-        } else if (tid < 21) {               // inv_K[:3,:3]   (movedepth/layers.py:582)
-            const int q = tid - 12;
-            geo[12 + q] = a.invK[b * 16 + (q / 3) * 4 + (q % 3)];
-        }
-        __syncthreads();
-
-        PixelCtx c;
-        c.b = b;
-        c.x = x;
-        c.y = y;
-        c.d0 = d0;
-        c.d1 = d1;
-        {
-            const float xf = static_cast<float>(x), yf = static_cast<float>(y);
-            const float rx = fmaf(geo[12], xf, fmaf(geo[13], yf, geo[14]));
-            const float ry = fmaf(geo[15], xf, fmaf(geo[16], yf, geo[17]));
-            const float rz = fmaf(geo[18], xf, fmaf(geo[19], yf, geo[20]));
-            c.mrx = fmaf(geo[0], rx, fmaf(geo[1], ry, geo[2] * rz));
-            c.mry = fmaf(geo[4], rx, fmaf(geo[5], ry, geo[6] * rz));
-            c.mrz = fmaf(geo[8], rx, fmaf(geo[9], ry, geo[10] * rz));
-            c.tx = geo[3];
-            c.ty = geo[7];
-            c.tz = geo[11];
-        }
         const int pix = y * a.w + (lane_ok ? x : a.w - 1);
-        const float prior_v = (a.hyps == nullptr) ? __ldg(a.prior + static_cast<size_t>(b) * hw + pix) : 0.f;
+        const float prior_v = pf_prior;
+        if (next < a.num_tiles) prefetch(next);
+        const Geom c = pixel_geom(geo_all + b * GEO_STRIDE, x, y);
         const float* hp = (a.hyps != nullptr) ? a.hyps + static_cast<size_t>(b) * a.D * hw + pix : nullptr;
         const float* rp = (a.hyps == nullptr) ? a.ratio + static_cast<size_t>(b) * a.D : nullptr;
 
-        // ---- cells this (pixel, chunk) can touch: the projection of a depth interval is the segment
-        // between the projections of its end points as long as z stays positive.
-        short4 ft = make_short4(32767, -32768, 32767, -32768);     // empty
-        int bad = 0;
-        if (lane_ok && d0 < d1) {
-            float dmin, dmax;
-            if (hp != nullptr) {
-                dmin = 3.0e38f;
-                dmax = -3.0e38f;
-                for (int d = d0; d < d1; ++d) {
-                    const float dv = __ldg(hp + static_cast<size_t>(d) * hw);
-                    dmin = fminf(dmin, dv);
-                    dmax = fmaxf(dmax, dv);
-                }
-            } else {
-                const float d_a = prior_v * __ldg(rp + d0), d_b = prior_v * __ldg(rp + d1 - 1);
-                dmin = fminf(d_a, d_b);
-                dmax = fmaxf(d_a, d_b);
-            }
-            float u0, v0, z0, u1, v1, z1;
-            project_uv(c, dmin, u0, v0, z0);
-            project_uv(c, dmax, u1, v1, z1);
-            if (!(z0 > 1e-6f) || !(z1 > 1e-6f) || !(fabsf(u0) < 1e8f) || !(fabsf(u1) < 1e8f) || !(fabsf(v0) < 1e8f) ||
-                !(fabsf(v1) < 1e8f)) {
-                bad = 1;
-            } else {
-                const float wf = static_cast<float>(a.w), hf = static_cast<float>(a.h);
-                const float mnu = fminf(u0, u1), mxu = fmaxf(u0, u1), mnv = fminf(v0, v1), mxv = fmaxf(v0, v1);
-                if (mxu > -1.f && mnu < wf && mxv > -1.f && mnv < hf) {   // segment touches the image
-                    ft.x = static_cast<short>(floorf(fmaxf(mnu, -1.f)));
-                    ft.y = static_cast<short>(min(static_cast<int>(floorf(mxu)), a.w - 1));
-                    ft.z = static_cast<short>(floorf(fmaxf(mnv, -1.f)));
-                    ft.w = static_cast<short>(min(static_cast<int>(floorf(mxv)), a.h - 1));
-                }
-            }
-        }
-        foot[warp * 32 + lane] = ft;
-        {
-            const int lo_x = __reduce_min_sync(0xffffffffu, static_cast<int>(ft.x));
-            const int hi_x = __reduce_max_sync(0xffffffffu, static_cast<int>(ft.y));
-            const int lo_y = __reduce_min_sync(0xffffffffu, static_cast<int>(ft.z));
-            const int hi_y = __reduce_max_sync(0xffffffffu, static_cast<int>(ft.w));
-            if (lane == 0) {
-                red[warp * 4 + 0] = lo_x;
-                red[warp * 4 + 1] = hi_x;
-                red[warp * 4 + 2] = lo_y;
-                red[warp * 4 + 3] = hi_y;
-            }
-        }
-        const int any_bad = __syncthreads_or(bad);
-
-        // ---- tile box (TMA) and this pixel's table footprint (union over the 8 chunks)
-        int bx0 = 32767, bx1 = -32768, by0 = 32767, by1 = -32768;
+        // ---- this tile's box and this pixel's table footprint (union over the 8 chunks)
+        int ox, oy;
+        bool boxed, any_bad;
+        tile_box(a, reinterpret_cast<const int*>(smem + Smem::OFF_RED) + par * WARPS * 8, ox, oy, boxed, any_bad);
         int fx0 = 32767, fx1 = -32768, fy0 = 32767, fy1 = -32768;
+        {
+            const short4* foot = reinterpret_cast<const short4*>(smem + Smem::OFF_FOOT) + par * WARPS * 32;
 #pragma unroll
-        for (int wi = 0; wi < WARPS; ++wi) {
-            bx0 = min(bx0, red[wi * 4 + 0]);
-            bx1 = max(bx1, red[wi * 4 + 1]);
-            by0 = min(by0, red[wi * 4 + 2]);
-            by1 = max(by1, red[wi * 4 + 3]);
-            const short4 f = foot[wi * 32 + lane];
-            fx0 = min(fx0, static_cast<int>(f.x));
-            fx1 = max(fx1, static_cast<int>(f.y));
-            fy0 = min(fy0, static_cast<int>(f.z));
-            fy1 = max(fy1, static_cast<int>(f.w));
+            for (int wi = 0; wi < WARPS; ++wi) {
+                const short4 f = foot[wi * 32 + lane];
+                fx0 = min(fx0, static_cast<int>(f.x));
+                fx1 = max(fx1, static_cast<int>(f.y));
+                fy0 = min(fy0, static_cast<int>(f.z));
+                fy1 = max(fy1, static_cast<int>(f.w));
+            }
         }
-        const bool box_empty = bx1 < bx0;
-        const bool boxed = a.use_tma && !any_bad && !box_empty && (bx1 - bx0 + 2 <= BOX_W) && (by1 - by0 + 2 <= BOX_H);
-        const int ox = bx0, oy = by0;
         const int nxp = fx1 - fx0 + 2, nyp = fy1 - fy0 + 2;
         const bool foot_empty = fx1 < fx0;
         const bool tab_ok = a.use_table && !any_bad && (foot_empty || nxp * nyp <= NT);
         const int ntaps = (tab_ok && !foot_empty && lane_ok) ? nxp * nyp : 0;
 
-        if (tid == 0) {
-            mbar_expect_tx(bar, Smem::REF_BYTES + (boxed ? Smem::SRC_BYTES : 0));
-            tma_load_4d(smem + Smem::OFF_REF, &map_ref, bar, 0, tx0, y, b);
-            if (boxed) tma_load_4d(smem + Smem::OFF_SRC, &map_src, bar, 0, ox, oy, b);
-        }
-        mbar_wait(bar, phase);
+        mbar_wait(bar, phase);               // reference row (+ source box) of this tile have landed
         phase ^= 1u;
 
         // ---- build the table: warp w computes taps w, w+8 of every pixel
@@ -585,15 +670,15 @@ costvol_grouped_fwd_kernel(const __grid_constant__ CUtensorMap map_src, const __
                 rh[j].x = mul2(rh[j].x, half2);
                 rh[j].y = mul2(rh[j].y, half2);
             }
-            for (int t = warp; t < ntaps; t += WARPS) {
-                const int ty = t / nxp, tx = t - ty * nxp;
+            for (int tp = warp; tp < ntaps; tp += WARPS) {
+                const int ty = tp / nxp, tx = tp - ty * nxp;
                 const int sx = fx0 + tx, sy = fy0 + ty;
                 const int rx = sx - ox, ry = sy - oy;
                 const bool in_box = boxed && rx >= 0 && rx < BOX_W && ry >= 0 && ry < BOX_H;
                 const bool in_img = sx >= 0 && sx < a.w && sy >= 0 && sy < a.h;
                 const ulonglong2* g = reinterpret_cast<const ulonglong2*>(
                     a.src + (static_cast<size_t>(b * a.h + (in_img ? sy : 0)) * a.w + (in_img ? sx : 0)) * CV_C);
-                ulonglong2* dst = reinterpret_cast<ulonglong2*>(ptab_pix + t * 64);
+                ulonglong2* dst = reinterpret_cast<ulonglong2*>(ptab_pix + tp * 64);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     ulonglong2 lo, hi;
@@ -611,81 +696,99 @@ costvol_grouped_fwd_kernel(const __grid_constant__ CUtensorMap map_src, const __
                 }
             }
         }
-        __syncthreads();
-        if (d0 >= d1) continue;                                   // warp-uniform (idle chunk: D < 8 * DC)
+        __syncthreads();                     // table complete; source box and reference row are free again
 
-        uint64_t P2[4][8];
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-#pragma unroll
-            for (int k = 0; k < 8; ++k) P2[t][k] = 0ull;
-        int cx = INT_MIN, cy = INT_MIN;
-        float* obase = a.out + static_cast<size_t>(b) * CV_G * a.D * hw;
+        // ---- stage F for the next tile: its loads fly while this tile's hypothesis loop runs
+        if (next < a.num_tiles) footprint_stage(a, &map_src, &map_ref, smem, next, par ^ 1, pf_prior, pf_ra, pf_rb);
 
-        for (int d = d0; d < d1; ++d) {
-            const float depth = hp ? __ldg(hp + static_cast<size_t>(d) * hw) : prior_v * __ldg(rp + d);
-            float u, v, pz;
-            project_uv(c, depth, u, v, pz);
-            const Bilinear s = bilinear_at(a, u, v);
-            if (s.ok && (s.ix != cx || s.iy != cy)) {
-                cx = s.ix;
-                cy = s.iy;
-                if (tab_ok && cx >= fx0 && cx <= fx1 && cy >= fy0 && cy <= fy1)
-                    load_cell_table(ptab_pix, (cy - fy0) * nxp + (cx - fx0), nxp, P2);
-                else
-                    load_cell_direct(a, b, sbox, rbox, lane, boxed, ox, oy, cx, cy, P2);
-            }
-            const uint64_t w00 = pk2(s.w00, s.w00), w01 = pk2(s.w01, s.w01), w10 = pk2(s.w10, s.w10),
-                           w11 = pk2(s.w11, s.w11);
-            uint64_t o2[8];
+        if (n > 0) {                         // warp-uniform (idle chunk when D < 8 * DC)
+            uint64_t P2[4][8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) o2[k] = fma2(w11, P2[3][k], fma2(w10, P2[2][k], fma2(w01, P2[1][k], mul2(w00, P2[0][k]))));
+            for (int tt = 0; tt < 4; ++tt)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) P2[tt][k] = 0ull;
+            int cx = INT_MIN, cy = INT_MIN;
+            float* obase = a.out + static_cast<size_t>(b) * CV_G * a.D * hw;
+            const float cu = 0.5f * static_cast<float>(a.w - 1), ru = 0.5f * static_cast<float>(a.w + 1);
+            const float cv = 0.5f * static_cast<float>(a.h - 1), rv = 0.5f * static_cast<float>(a.h + 1);
+            float ratio_l = 0.f;             // lane l holds the ratio of hypothesis d0 + (i & ~31) + l
 
-            if (a.tma_store) {
-                float* buf = stage + sbuf * (STAGE_ROW / 4);
-                if (lane == 0) bulk_wait_read<1>();          // the store issued two hypotheses ago has drained this buffer
-                __syncwarp();
-                if (a.layout == MVD_LAYOUT_BGDHW) {           // buf[g][lane]
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        float e, f;
-                        unpk2(o2[k], e, f);
-                        buf[(2 * k) * TW + lane] = e;
-                        buf[(2 * k + 1) * TW + lane] = f;
-                    }
-                } else {                                      // buf[lane][g], 64B-swizzled like the output descriptor
-                    ulonglong2* bp = reinterpret_cast<ulonglong2*>(buf + lane * CV_G);
-                    const int sw = (lane >> 1) & 3;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) bp[q ^ sw] = make_ulonglong2(o2[2 * q], o2[2 * q + 1]);
+            for (int i = 0; i < n; ++i) {
+                const int d = d0 + i;
+                if (hp == nullptr && (i & 31) == 0) ratio_l = (i + lane < n) ? __ldg(rp + d + lane) : 0.f;
+                const float depth = hp ? __ldg(hp + static_cast<size_t>(d) * hw) : prior_v * __shfl_sync(0xffffffffu, ratio_l, i & 31);
+                // p = depth * (KT K^-1 x) + t ;  u = p.x / (p.z + 1e-7)   (movedepth/layers.py:601-621)
+                const float inv = rcp_approx(fmaf(depth, c.mrz, c.tz) + 1e-7f);
+                const float u = fmaf(depth, c.mrx, c.tx) * inv, v = fmaf(depth, c.mry, c.ty) * inv;
+                // ATen grid_sampler_2d (bilinear, zeros, align_corners=True): taps outside the image contribute 0; a
+                // sample at u <= -1 or u >= w has no in-image tap.  |u - (w-1)/2| < (w+1)/2  <=>  -1 < u < w.
+                const bool ok = (fabsf(u - cu) < ru) && (fabsf(v - cv) < rv);
+                const float x0 = floorf(u), y0 = floorf(v);
+                const float wx1 = u - x0, wx0 = (x0 + 1.f) - u, wy1 = v - y0, wy0 = (y0 + 1.f) - v;
+                const int ix = static_cast<int>(x0), iy = static_cast<int>(y0);
+                if (ok && (ix != cx || iy != cy)) {
+                    cx = ix;
+                    cy = iy;
+                    if (tab_ok && cx >= fx0 && cx <= fx1 && cy >= fy0 && cy <= fy1)
+                        load_cell_table(ptab_pix, (cy - fy0) * nxp + (cx - fx0), nxp, P2);
+                    else
+                        load_cell_direct(a, b, b * hw + pix, cx, cy, P2);
                 }
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    if (a.layout == MVD_LAYOUT_BGDHW) tma_store_5d(&map_out, buf, tx0, y, d, 0, b);
-                    else tma_store_5d(&map_out, buf, 0, tx0, y, d, b);
-                    bulk_commit();
-                }
-                sbuf ^= 1u;
-            } else if (lane_ok) {
-                if (a.layout == MVD_LAYOUT_BGDHW) {
-                    const int off = d * hw + pix, gs = a.D * hw;
+                const float a00 = ok ? wx0 * wy0 : 0.f, a01 = ok ? wx1 * wy0 : 0.f, a10 = ok ? wx0 * wy1 : 0.f,
+                            a11 = ok ? wx1 * wy1 : 0.f;
+                const uint64_t w00 = pk2(a00, a00), w01 = pk2(a01, a01), w10 = pk2(a10, a10), w11 = pk2(a11, a11);
+                uint64_t o2[8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        float e, f;
-                        unpk2(o2[k], e, f);
-                        obase[off + (2 * k) * gs] = e;
-                        obase[off + (2 * k + 1) * gs] = f;
+                for (int k = 0; k < 8; ++k)
+                    o2[k] = fma2(w11, P2[3][k], fma2(w10, P2[2][k], fma2(w01, P2[1][k], mul2(w00, P2[0][k]))));
+
+                if (a.tma_store) {
+                    float* buf = stage + sbuf * (STAGE_ROW / 4);
+                    if (lane == 0) bulk_wait_read<1>();          // the store issued two hypotheses ago has drained this buffer
+                    __syncwarp();
+                    if (a.layout == MVD_LAYOUT_BGDHW) {           // buf[g][lane]
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            float p, q;
+                            unpk2(o2[k], p, q);
+                            buf[(2 * k) * TW + lane] = p;
+                            buf[(2 * k + 1) * TW + lane] = q;
+                        }
+                    } else {                                      // buf[lane][g], 64B-swizzled like the output descriptor
+                        ulonglong2* bp = reinterpret_cast<ulonglong2*>(buf + lane * CV_G);
+                        const int sw = (lane >> 1) & 3;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) bp[q ^ sw] = make_ulonglong2(o2[2 * q], o2[2 * q + 1]);
                     }
-                } else {
-                    ulonglong2* op = reinterpret_cast<ulonglong2*>(obase + (static_cast<size_t>(d) * hw + pix) * CV_G);
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0 && !a.dbg_nostore) {
+                        if (a.layout == MVD_LAYOUT_BGDHW) tma_store_5d(&map_out, buf, tx0, y, d, 0, b);
+                        else tma_store_5d(&map_out, buf, 0, tx0, y, d, b);
+                        bulk_commit();
+                    }
+                    sbuf ^= 1u;
+                } else if (lane_ok) {
+                    if (a.layout == MVD_LAYOUT_BGDHW) {
+                        const int off = d * hw + pix, gs = a.D * hw;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) op[q] = make_ulonglong2(o2[2 * q], o2[2 * q + 1]);
+                        for (int k = 0; k < 8; ++k) {
+                            float p, q;
+                            unpk2(o2[k], p, q);
+                            obase[off + (2 * k) * gs] = p;
+                            obase[off + (2 * k + 1) * gs] = q;
+                        }
+                    } else {
+                        ulonglong2* op = reinterpret_cast<ulonglong2*>(obase + (static_cast<size_t>(d) * hw + pix) * CV_G);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) op[q] = make_ulonglong2(o2[2 * q], o2[2 * q + 1]);
+                    }
                 }
             }
         }
+        __syncthreads();                     // everyone is done with this tile's table; next tile's footprints are visible
     }
-    if (lane == 0) bulk_wait_read<0>();                       // shared memory must outlive the in-flight stores
+    if (lane == 0) bulk_wait_read<0>();       // shared memory must outlive the in-flight stores
 }
 
 // ------------------------------------------------------------------------------------------ backward
@@ -845,7 +948,27 @@ static int costvol_grouped_launch(bool bwd, CvArgs a, int C, int G, int flags, c
         return check_launch("costvol_grouped_bwd");
     }
 
-    // forward: one tile = one row of 32 pixels, 8 hypothesis chunks
+    // forward: the kernel keeps the geometry of every batch item in shared memory -> at most MAXB items per launch
+    if (a.B > f3::MAXB) {
+        for (int b0 = 0; b0 < a.B; b0 += f3::MAXB) {
+            CvArgs s = a;
+            s.B = min(f3::MAXB, a.B - b0);
+            const size_t hw = static_cast<size_t>(a.h) * a.w;
+            s.ref = a.ref + b0 * hw * CV_C;
+            s.src = a.src + b0 * hw * CV_C;
+            s.prior = a.prior ? a.prior + b0 * hw : nullptr;
+            s.ratio = a.ratio ? a.ratio + static_cast<size_t>(b0) * a.D : nullptr;
+            s.hyps = a.hyps ? a.hyps + b0 * hw * a.D : nullptr;
+            s.K = a.K + b0 * 16;
+            s.invK = a.invK + b0 * 16;
+            s.T = a.T + b0 * 16;
+            s.out = a.out + b0 * hw * a.D * CV_G;
+            const int r = costvol_grouped_launch(false, s, C, G, flags, st);
+            if (r) return r;
+        }
+        return 0;
+    }
+    // one tile = one row of 32 pixels, 8 hypothesis chunks
     a.tiles_y = a.h;
     a.num_tiles = a.tiles_x * a.h * a.B;
     a.DC = (a.D + f3::NCH - 1) / f3::NCH;
@@ -856,7 +979,8 @@ static int costvol_grouped_launch(bool bwd, CvArgs a, int C, int G, int flags, c
     // output descriptor for the per-warp TMA stores (one hypothesis x one tile row x 16 groups per store)
     CUtensorMap map_out;
     const uint64_t W = a.w, H = a.h, Dd = a.D;
-    a.tma_store = a.use_tma;
+    a.tma_store = a.use_tma && !(flags & MVD_FLAG_PLAIN_STORE);
+    a.dbg_nostore = (flags & MVD_FLAG_DBG_NO_STORE) ? 1 : 0;
     if (a.layout == MVD_LAYOUT_BGDHW) {
         if (a.w % 4 != 0) a.tma_store = 0;      // TMA needs 16-byte global strides; ragged widths use plain stores
         const uint64_t dims[5] = {W, H, Dd, CV_G, static_cast<uint64_t>(a.B)};
