@@ -145,6 +145,26 @@ int mvd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
 int mvd_split_tf32(const float* x, float* out, long long n, int C, int pattern, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * reg3d output head: Conv3d(16 -> 1, 3x3x3, stride 1, zero padding 1, no bias) on the
+ * channels-last full-resolution volume, exact fp32 (CUDA cores; an HBM-bound stencil).
+ * Replaces: `self.prob = nn.Conv3d(base_channels, 1, 3, stride=1, padding=1, bias=False)`
+ * movedepth/networks/resnet_encoder.py:254 and its call at 279 (cuDNN fprop/dgrad/wgrad).
+ *   x  : [B,D,H,W,16] (channels-last-3d storage of the logical [B,16,D,H,W] tensor)
+ *   w  : [16,3,3,3]   (= weight[0] of the module, contiguous)
+ *   y, gy : [B,D,H,W];  gx : [B,D,H,W,16] OVERWRITTEN;  gw : [16,3,3,3] OVERWRITTEN
+ *   wgrad needs a caller-owned workspace of mvd_conv3d_c16o1_wgrad_workspace_bytes(B,D,H,W).
+ * The weights are staged in constant memory by fwd/dgrad (stream-ordered copy): concurrent
+ * calls with DIFFERENT weights on different streams are not supported.
+ * ------------------------------------------------------------------------------------- */
+int mvd_conv3d_c16o1_fwd(const float* x, const float* w, float* y, int B, int D, int H, int W,
+                         void* stream);
+int mvd_conv3d_c16o1_dgrad(const float* gy, const float* w, float* gx, int B, int D, int H, int W,
+                           void* stream);
+long long mvd_conv3d_c16o1_wgrad_workspace_bytes(int B, int D, int H, int W);
+int mvd_conv3d_c16o1_wgrad(const float* gy, const float* x, float* gw, void* workspace,
+                           long long workspace_bytes, int B, int D, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Measurement helpers (bench.py's live cost-volume roofline): CUDA timing events that also
  * work INSIDE a captured CUDA graph.  mvd_event_record with external != 0 uses
  * cudaEventRecordExternal, i.e. the record becomes an event-record NODE when the stream is

@@ -33,6 +33,10 @@ SIGNATURES = {
     "mvd_photometric_fwd": ([_P] * 8 + [_I] * 3 + [_F, _I, _P], _I),
     "mvd_photometric_bwd": ([_P] * 10 + [_I] * 3 + [_F, _P], _I),
     "mvd_split_tf32": ([_P, _P, _LL, _I, _I, _P], _I),
+    "mvd_conv3d_c16o1_fwd": ([_P] * 3 + [_I] * 4 + [_P], _I),
+    "mvd_conv3d_c16o1_dgrad": ([_P] * 3 + [_I] * 4 + [_P], _I),
+    "mvd_conv3d_c16o1_wgrad_workspace_bytes": ([_I] * 4, _LL),
+    "mvd_conv3d_c16o1_wgrad": ([_P] * 4 + [_LL] + [_I] * 4 + [_P], _I),
     "mvd_event_create": ([], _P),
     "mvd_event_record": ([_P, _P, _I], _I),
     "mvd_event_elapsed_ms": ([_P, _P, ctypes.POINTER(ctypes.c_float)], _I),

@@ -153,6 +153,20 @@ def _up3d(cin, cout, k=3, p=1, op=1, s=2):
                          nn.BatchNorm3d(cout), nn.ReLU(inplace=True))
 
 
+class ProbConv3d(PR.Conv3d):
+    """reg3d's output head.  Conv3d(16 -> 1, 3x3x3, pad 1, no bias) on a CUDA volume runs the hand-written exact-fp32
+    stencil kernels (ops.conv3d_c16_to_1); any other shape follows the precision policy like every other conv.
+    Same parameters / state-dict keys as nn.Conv3d."""
+
+    def forward(self, x):
+        if (x.is_cuda and self.in_channels == 16 and self.out_channels == 1 and self.bias is None
+                and tuple(self.kernel_size) == (3, 3, 3) and tuple(self.stride) == (1, 1, 1)
+                and tuple(self.padding) == (1, 1, 1) and tuple(self.dilation) == (1, 1, 1) and self.groups == 1):
+            from .. import ops
+            return ops.conv3d_c16_to_1(x, self.weight)
+        return super().forward(x)
+
+
 class _UNet3D(nn.Module):
     def _unet(self, x):
         c0 = self.conv0(x)
@@ -192,7 +206,7 @@ class reg3d(_UNet3D):
         self.conv7 = _up3d(8 * b, 4 * b)
         self.conv9 = _up3d(4 * b, 2 * b)
         self.conv11 = _up3d(2 * b, b)
-        self.prob = PR.Conv3d(b, 1, 3, stride=1, padding=1, bias=False)
+        self.prob = ProbConv3d(b, 1, 3, stride=1, padding=1, bias=False)
 
 
 class reg2d(_UNet3D):

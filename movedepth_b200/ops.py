@@ -237,6 +237,49 @@ def convex_upsample(depth, mask, scale=2):
     return _ConvexUp.apply(depth, mask, 2 ** scale)
 
 
+# ------------------------------------------------------------------------------------- reg3d output head
+class _Conv3dC16O1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight):
+        B, C, D, H, W = x.shape
+        assert C == 16 and tuple(weight.shape) == (1, 16, 3, 3, 3), (x.shape, weight.shape)
+        x = _f32(x).contiguous(memory_format=torch.channels_last_3d)
+        w = _f32(weight).contiguous()
+        y = torch.empty((B, 1, D, H, W), device=x.device, dtype=torch.float32)
+        rc = _lib.lib().mvd_conv3d_c16o1_fwd(_p(x), _p(w), _p(y), B, D, H, W, _stream())
+        _lib.check(rc, "mvd_conv3d_c16o1_fwd")
+        launch_counter["n"] += 1
+        ctx.save_for_backward(x, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        B, _, D, H, W = x.shape
+        gy = _f32(gy).contiguous()
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)                      # channels-last-3d
+            rc = _lib.lib().mvd_conv3d_c16o1_dgrad(_p(gy), _p(w), _p(gx), B, D, H, W, _stream())
+            _lib.check(rc, "mvd_conv3d_c16o1_dgrad")
+            launch_counter["n"] += 1
+        if ctx.needs_input_grad[1]:
+            nbytes = _lib.lib().mvd_conv3d_c16o1_wgrad_workspace_bytes(B, D, H, W)
+            ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32)
+            gw = torch.empty_like(w)
+            rc = _lib.lib().mvd_conv3d_c16o1_wgrad(_p(gy), _p(x), _p(gw), _p(ws), nbytes, B, D, H, W, _stream())
+            _lib.check(rc, "mvd_conv3d_c16o1_wgrad")
+            launch_counter["n"] += 2
+        return gx, gw
+
+
+def conv3d_c16_to_1(x, weight):
+    """Conv3d(16 -> 1, k=3, stride 1, padding 1, no bias) on a channels-last-3d volume, exact fp32.
+    x: logical [B,16,D,H,W]; weight: [1,16,3,3,3]; returns [B,1,D,H,W].
+    Reference: reg3d.prob, movedepth/networks/resnet_encoder.py:254, 279."""
+    return _Conv3dC16O1.apply(x, weight)
+
+
 # ------------------------------------------------------------------------------------- Adam
 def adam_step(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
     """One fused Adam update over flat fp32 arenas (torch.optim.Adam semantics)."""

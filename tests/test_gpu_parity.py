@@ -352,3 +352,49 @@ def test_cuda_graph_step_tracks_the_eager_step():
         for a, b in zip(eager.arenas, graphed.arenas):           # gradients (a few auto-mask pixels may flip: 5e-3 of the max)
             torch.testing.assert_close(b.grad, a.grad, atol=5e-3 * float(a.grad.abs().max()), rtol=1e-2)
     assert len(graphed._graphs) == 1, "the graph was never captured"
+
+
+# ---------------------------------------------------------------------------------------------- reg3d output head
+@pytest.mark.parametrize("shape", [(2, 8, 8, 32), (1, 5, 11, 45), (2, 24, 24, 80)], ids=["aligned", "ragged", "multi-tile"])
+def test_prob_conv3d_matches_torch_conv3d(ops, shape):
+    """Conv3d(16->1, 3x3x3, pad 1): hand-written stencil kernels (fwd, dgrad, wgrad) vs torch's CPU conv3d in fp64.
+    fp32 accumulation of 432 products: 1e-5 relative to the output scale."""
+    import torch.nn.functional as F
+    B, D, H, W = shape
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(B, 16, D, H, W, generator=gen)
+    w = torch.randn(1, 16, 3, 3, 3, generator=gen) * 0.1
+    gy = torch.randn(B, 1, D, H, W, generator=gen)
+    xo, wo = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    yo = F.conv3d(xo, wo, padding=1)
+    (yo * gy.double()).sum().backward()
+    xg = g(x).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+    wg = g(w).requires_grad_(True)
+    y = ops.conv3d_c16_to_1(xg, wg)
+    assert y.shape == (B, 1, D, H, W)
+    (y * g(gy)).sum().backward()
+    for got, want in ((y, yo), (xg.grad, xo.grad), (wg.grad, wo.grad)):
+        want = want.detach().float()
+        torch.testing.assert_close(got.detach().cpu(), want, atol=1e-5 * float(want.abs().max()), rtol=1e-5)
+
+
+def test_reg3d_uses_the_stencil_head_and_matches_the_oracle(ops):
+    """movedepth_b200 reg3d (fp32 policy) vs the oracle's reg3d on the same weights: logits and input gradient."""
+    from movedepth_b200 import networks as PN, precision as PR
+    from oracle import networks as ON
+    PR.set_policy("fp32")
+    gen = torch.Generator().manual_seed(5)
+    vol = torch.randn(1, 16, 8, 16, 32, generator=gen)
+    a, b = PN.reg3d(16, 16, 3), ON.Reg3d(16, 16, 3)
+    fill_deterministic(a)
+    fill_deterministic(b)
+    a.to(DEV)
+    xa = g(vol).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+    xb = vol.clone().requires_grad_(True)
+    ya, yb = a.forward_volume(xa), b(xb.permute(0, 2, 1, 3, 4))
+    torch.testing.assert_close(ya.detach().cpu(), yb.detach(), atol=1e-4 * float(yb.abs().max()), rtol=1e-4)
+    gy = torch.randn(yb.shape, generator=gen)
+    (ya * g(gy)).sum().backward()
+    (yb * gy).sum().backward()
+    torch.testing.assert_close(xa.grad.cpu(), xb.grad, atol=1e-3 * float(xb.grad.abs().max()), rtol=1e-3)
+    torch.testing.assert_close(a.prob.weight.grad.cpu(), b.prob.weight.grad, atol=1e-3 * float(b.prob.weight.grad.abs().max()), rtol=1e-3)
