@@ -165,6 +165,25 @@ int mvd_conv3d_c16o1_wgrad(const float* gy, const float* x, float* gw, void* wor
                            long long workspace_bytes, int B, int D, int H, int W, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * reg3d first layer: Conv3d(16 -> 16, 3x3x3, stride 1, zero padding 1, no bias) on the
+ * channels-last full-resolution volume as a tensor-core implicit GEMM (TMA-staged slices).
+ * Replaces: ConvBnReLU3D.conv of `conv0`, movedepth/networks/resnet_encoder.py:178, 231, 258
+ * (cuDNN fprop) and its data gradient (cuDNN dgrad).
+ *   in, out : [B,D,H,W,16];  w : [16,16,3,3,3] (co, ci, kd, kh, kw), contiguous
+ *   mode 0  : out = conv(in, w)            (forward)
+ *   mode 1  : out = d loss / d input given in = d loss / d output   (data gradient)
+ *   passes 3: 3xTF32 operand split (near-fp32, the forward policy); passes 1: single-pass TF32
+ * ------------------------------------------------------------------------------------- */
+int mvd_conv3d_c16c16(const float* in, const float* w, float* out, int B, int D, int H, int W,
+                      int mode, int passes, void* stream);
+/* Weight gradient of the same layer, exact fp32 (packed FFMA2 on the CUDA cores):
+ *   gy, x : [B,D,H,W,16];  gw : [16,16,3,3,3] OVERWRITTEN;  workspace of
+ *   mvd_conv3d_c16c16_wgrad_workspace_bytes(B,D,H,W) bytes (per-tile partials, reduced deterministically). */
+long long mvd_conv3d_c16c16_wgrad_workspace_bytes(int B, int D, int H, int W);
+int mvd_conv3d_c16c16_wgrad(const float* gy, const float* x, float* gw, void* workspace,
+                            long long workspace_bytes, int B, int D, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Measurement helpers (bench.py's live cost-volume roofline): CUDA timing events that also
  * work INSIDE a captured CUDA graph.  mvd_event_record with external != 0 uses
  * cudaEventRecordExternal, i.e. the record becomes an event-record NODE when the stream is

@@ -37,6 +37,9 @@ SIGNATURES = {
     "mvd_conv3d_c16o1_dgrad": ([_P] * 3 + [_I] * 4 + [_P], _I),
     "mvd_conv3d_c16o1_wgrad_workspace_bytes": ([_I] * 4, _LL),
     "mvd_conv3d_c16o1_wgrad": ([_P] * 4 + [_LL] + [_I] * 4 + [_P], _I),
+    "mvd_conv3d_c16c16": ([_P] * 3 + [_I] * 6 + [_P], _I),
+    "mvd_conv3d_c16c16_wgrad_workspace_bytes": ([_I] * 4, _LL),
+    "mvd_conv3d_c16c16_wgrad": ([_P] * 4 + [_LL] + [_I] * 4 + [_P], _I),
     "mvd_event_create": ([], _P),
     "mvd_event_record": ([_P, _P, _I], _I),
     "mvd_event_elapsed_ms": ([_P, _P, ctypes.POINTER(ctypes.c_float)], _I),

@@ -312,6 +312,330 @@ __global__ void __launch_bounds__(128) conv3d_c16o1_wgrad_reduce_kernel(const fl
     if (lane == 0) gw[o] = red[0] + red[1] + red[2] + red[3];
 }
 
+// ================================================================================================
+// reg3d's first layer: Conv3d(16 -> 16, 3x3x3, pad 1) on the full-resolution volume, as an implicit GEMM on
+// the warp-level tensor-core path (mma.sync m16n8k8 TF32; the tcgen05 version of this layer is the next step,
+// DESIGN.md section 7).  One kernel serves the forward (3xTF32 operand split in registers: hi*hi + lo*hi + hi*lo,
+// the precision policy of movedepth_b200/precision.py) and the data gradient (single-pass TF32 with the
+// flipped / transposed filter).  Same slice-marching structure as the 16->1 head: the current input slice of a
+// 8x32 tile (+halo) sits in shared memory (TMA, 64B swizzle), each warp owns 2 rows x 32 columns = four m16
+// tiles and keeps the accumulators of the three output slices the input slice contributes to in registers,
+// so an A fragment (16 B per lane, both k-steps) is loaded once per (kh,kw) and used for the three kd taps.
+// The K (channel) order inside a k-step is permuted so that a lane's four channels are contiguous.
+constexpr int G_WARPS = 4, G_THREADS = 32 * G_WARPS;
+constexpr int BF_BYTES = 27 * 2 * 32 * 16;          // B fragments: [tap][k-step][lane] x float4
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct GArgs {
+    const float* w;      // [16][16][27]  (co, ci, tap)
+    float* out;          // [B,D,H,W,16]
+    int mode;            // 0: forward, 1: data gradient
+    int B, D, H, W;
+    int tiles_h, tiles_w, dsplit, dlen;
+};
+
+template <int PASSES>
+struct GState {
+    float acc[3][4][2][4];
+};
+
+template <int PASSES, int R>
+__device__ __forceinline__ void igemm_slice(GState<PASSES>& st, const unsigned char* buf, const float4* bfrag, int warp, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            uint32_t ahi[4][2][4], alo[PASSES == 3 ? 4 : 1][2][4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const int row = 2 * warp + (m >> 1), col = (m & 1) * 16;
+                const int p0 = (row + kh) * HW + col + kw + g;
+                const float4 v = lds_x(buf, p0, t), v2 = lds_x(buf, p0 + 8, t);
+                const float e[2][4] = {{v.x, v2.x, v.y, v2.y}, {v.z, v2.z, v.w, v2.w}};
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        ahi[m][ks][q] = to_tf32(e[ks][q]);
+                        if (PASSES == 3) alo[m][ks][q] = to_tf32(e[ks][q] - __uint_as_float(ahi[m][ks][q]));
+                    }
+            }
+#pragma unroll
+            for (int kd = 0; kd < 3; ++kd) {
+                const int tap = kd * 9 + kh * 3 + kw;
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int slot = (R + 1 - kd + 3) % 3;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const float4 bf = bfrag[(tap * 2 + ks) * 32 + lane];
+                    const float bv[4] = {bf.x, bf.y, bf.z, bf.w};
+                    uint32_t bhi[4], blo[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        bhi[q] = to_tf32(bv[q]);
+                        if (PASSES == 3) blo[q] = to_tf32(bv[q] - __uint_as_float(bhi[q]));
+                    }
+#pragma unroll
+                    for (int m = 0; m < 4; ++m)
+#pragma unroll
+                        for (int n = 0; n < 2; ++n) {
+                            mma_tf32(st.acc[slot][m][n], ahi[m][ks], bhi[2 * n], bhi[2 * n + 1]);
+                            if (PASSES == 3) {
+                                mma_tf32(st.acc[slot][m][n], alo[m][ks], bhi[2 * n], bhi[2 * n + 1]);
+                                mma_tf32(st.acc[slot][m][n], ahi[m][ks], blo[2 * n], blo[2 * n + 1]);
+                            }
+                        }
+                }
+            }
+        }
+}
+
+// write the finished output slice (accumulator set `slot`) and clear it
+template <int PASSES>
+__device__ __forceinline__ void igemm_store(GState<PASSES>& st, int slot, const GArgs& a, const Item& it, int d, int warp, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int h = it.h0 + 2 * warp + (m >> 1), w0 = it.w0 + (m & 1) * 16 + g;
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+            float (&c)[4] = slot == 0 ? st.acc[0][m][n] : (slot == 1 ? st.acc[1][m][n] : st.acc[2][m][n]);
+            if (d >= it.d0 && h < a.H) {
+                float* op = a.out + (((static_cast<size_t>(it.b) * a.D + d) * a.H + h) * a.W) * C + n * 8 + 2 * t;
+                if (w0 < a.W) *reinterpret_cast<float2*>(op + static_cast<size_t>(w0) * C) = make_float2(c[0], c[1]);
+                if (w0 + 8 < a.W) *reinterpret_cast<float2*>(op + static_cast<size_t>(w0 + 8) * C) = make_float2(c[2], c[3]);
+            }
+            c[0] = c[1] = c[2] = c[3] = 0.f;
+        }
+    }
+}
+
+template <int PASSES>
+__global__ void __launch_bounds__(G_THREADS, 2)
+conv3d_c16c16_kernel(const __grid_constant__ CUtensorMap map_in, const GArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    float4* bfrag = reinterpret_cast<float4*>(smem + NBUF * SLICE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NBUF * SLICE_BYTES + BF_BYTES);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    Args pa{};
+    pa.B = a.B; pa.D = a.D; pa.H = a.H; pa.W = a.W;
+    pa.tiles_h = a.tiles_h; pa.tiles_w = a.tiles_w; pa.dsplit = a.dsplit; pa.dlen = a.dlen;
+    const Item it = decode_item(pa, blockIdx.x);
+    const int count = it.d1 - it.d0 + 2;
+    if (tid == 0) {
+        tma_prefetch_desc(&map_in);
+        for (int i = 0; i < NBUF; ++i) mbar_init(full + i, 1);
+        mbar_fence_init();
+        for (int i = 0; i < NBUF && i < count; ++i) issue_slice(&map_in, smem + i * SLICE_BYTES, full + i, it, it.d0 - 1 + i);
+    }
+    // B fragments.  lane (g,t), k-step ks: k = t -> channel 4t+2ks, k = t+4 -> channel 4t+2ks+1; n = g (tile 0), g+8 (tile 1)
+    for (int e = tid; e < 27 * 2 * 32; e += G_THREADS) {
+        const int ln = e & 31, ks = (e >> 5) & 1, tap = e >> 6;
+        const int g = ln >> 2, t = ln & 3;
+        const int k0 = 4 * t + 2 * ks, k1 = k0 + 1;
+        float v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = (q & 1) ? k1 : k0, n = g + ((q >> 1) ? 8 : 0);
+            // forward: B[k=ci][n=co] = W[co][ci][tap];  data gradient: B[k=co][n=ci] = W[co][ci][26 - tap]
+            v[q] = (a.mode == 0) ? __ldg(a.w + (n * 16 + k) * 27 + tap) : __ldg(a.w + (k * 16 + n) * 27 + (26 - tap));
+        }
+        bfrag[e] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    __syncthreads();
+
+    GState<PASSES> st;
+#pragma unroll
+    for (int s3 = 0; s3 < 3; ++s3)
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int n = 0; n < 2; ++n)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) st.acc[s3][m][n][q] = 0.f;
+
+    // slice i (x slice s = d0-1+i) adds tap kd to output slice s+1-kd, kept in accumulator set (i+1-kd) mod 3;
+    // afterwards output slice s-1 (set (i+2) mod 3) is complete.
+    for (int i0 = 0; i0 < count; i0 += 3) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const int i = i0 + r;
+            if (i < count) {
+                const int s = it.d0 - 1 + i, bi = i % NBUF;
+                mbar_wait(full + bi, (i / NBUF) & 1);
+                const unsigned char* buf = smem + bi * SLICE_BYTES;
+                if (r == 0) igemm_slice<PASSES, 0>(st, buf, bfrag, warp, lane);
+                else if (r == 1) igemm_slice<PASSES, 1>(st, buf, bfrag, warp, lane);
+                else igemm_slice<PASSES, 2>(st, buf, bfrag, warp, lane);
+                igemm_store<PASSES>(st, (r + 2) % 3, a, it, s - 1, warp, lane);
+                __syncthreads();
+                if (tid == 0 && i + NBUF < count) issue_slice(&map_in, smem + bi * SLICE_BYTES, full + bi, it, s + NBUF);
+            }
+        }
+    }
+}
+
+constexpr int G_SMEM = NBUF * SLICE_BYTES + BF_BYTES + 64 + 1024;
+
+// ================================================================================================
+// Weight gradient of the 16 -> 16 layer on the CUDA cores, exact fp32 with packed FFMA2:
+//   gw[co,ci,kd,kh,kw] = sum_{b,d,h,w} gy[b,d,h,w,co] * x[b,d+kd-1,h+kh-1,w+kw-1,ci]
+// (measured here: mma.sync TF32 m16n8k8 sustains ~130 MAC/clk/SM on this part, no more than the FP32 pipe, and
+// cuDNN's legacy sm80 wgrad kernel needs 2.6 ms for this layer.)
+// thread role = (4 co) x (4 ci) x (kd,kh); it keeps the 3 kw taps x 16 products in 24 packed accumulators and
+// walks 4 rows x 32 columns of the tile per depth slice: 2 LDS.128 + 24 FFMA2 per position.  x slices march
+// through a 2-deep TMA ring, gy slices through a 4-deep one (x slice s pairs with gy slice s+1-kd).
+constexpr int WG_ROLES = 144, WG_GROUPS = 2, WG_THREADS = WG_ROLES * WG_GROUPS;   // 288
+constexpr int WG_XBUF = 2, WG_GBUF = 4;
+constexpr int GY_BYTES = TH * TW * 64;                // 16 KB, multiple of 512
+constexpr int NW16 = 16 * 16 * 27;                    // 6912
+
+__device__ __forceinline__ uint64_t pk2f(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ ulonglong2 lds_x2(const unsigned char* buf, int p, int q) {
+    return *reinterpret_cast<const ulonglong2*>(buf + p * 64 + ((q ^ ((p >> 1) & 3)) << 4));
+}
+
+struct WArgs {
+    float* part;         // [items][6912]
+    int B, D, H, W;
+    int tiles_h, tiles_w, dsplit, dlen;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 2)
+conv3d_c16c16_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_gy, const WArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* xs = smem;                                      // [WG_XBUF][SLICE_BYTES]
+    unsigned char* gs = smem + WG_XBUF * SLICE_BYTES;              // [WG_GBUF][GY_BYTES]
+    uint64_t* xfull = reinterpret_cast<uint64_t*>(gs + WG_GBUF * GY_BYTES);
+    uint64_t* gfull = xfull + WG_XBUF;
+    const int tid = threadIdx.x;
+    Args pa{};
+    pa.B = a.B; pa.D = a.D; pa.H = a.H; pa.W = a.W;
+    pa.tiles_h = a.tiles_h; pa.tiles_w = a.tiles_w; pa.dsplit = a.dsplit; pa.dlen = a.dlen;
+    const Item it = decode_item(pa, blockIdx.x);
+    const int count = it.d1 - it.d0 + 2;                           // x slices d0-1 .. d1
+
+    auto issue_gy = [&](int d) {                                   // gy slice d (only this item's own slices are ever used)
+        if (d >= it.d0 && d < it.d1) {
+            uint64_t* bar = gfull + (d & 3);
+            mbar_expect_tx(bar, GY_BYTES);
+            tma_load_5d(gs + (d & 3) * GY_BYTES, &map_gy, bar, 0, it.w0, it.h0, d, it.b);
+        }
+    };
+    if (tid == 0) {
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_gy);
+        for (int i = 0; i < WG_XBUF; ++i) mbar_init(xfull + i, 1);
+        for (int i = 0; i < WG_GBUF; ++i) mbar_init(gfull + i, 1);
+        mbar_fence_init();
+        for (int i = 0; i < WG_XBUF && i < count; ++i) issue_slice(&map_x, xs + i * SLICE_BYTES, xfull + i, it, it.d0 - 1 + i);
+        issue_gy(it.d0);
+        issue_gy(it.d0 + 1);
+    }
+    __syncthreads();
+
+    const int grp = tid / WG_ROLES, role = tid - grp * WG_ROLES;
+    const int co4 = role & 3, ci4 = (role >> 2) & 3, kdkh = role >> 4;
+    const int kd = kdkh / 3, kh = kdkh - kd * 3;
+    uint64_t acc[3][4][2];                                         // [kw][co][ci pair]
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0ull;
+
+    for (int i = 0; i < count; ++i) {
+        const int s = it.d0 - 1 + i, xb = i % WG_XBUF;
+        mbar_wait(xfull + xb, (i / WG_XBUF) & 1);
+        const int d = s + 1 - kd;                                  // the gy slice this thread's kd pairs with x slice s
+        if (d >= it.d0 && d < it.d1) {
+            const int first = it.d0 + (((d & 3) - (it.d0 & 3)) & 3);   // first slice of this item that used ring slot d&3
+            mbar_wait(gfull + (d & 3), ((d - first) >> 2) & 1);
+            const unsigned char* xbuf = xs + xb * SLICE_BYTES;
+            const unsigned char* gbuf = gs + (d & 3) * GY_BYTES;
+#pragma unroll 1
+            for (int rr = 0; rr < 4; ++rr) {
+                const int r = grp * 4 + rr;                        // tile row
+                const int xrow = (r + kh) * HW;                    // halo row r+kh; halo column = c + kw
+                ulonglong2 xw0 = lds_x2(xbuf, xrow, ci4), xw1 = lds_x2(xbuf, xrow + 1, ci4);
+#pragma unroll 4
+                for (int c = 0; c < TW; ++c) {
+                    const ulonglong2 xw2 = lds_x2(xbuf, xrow + c + 2, ci4);
+                    const float4 g = lds_x(gbuf, r * TW + c, co4);
+                    const uint64_t g2[4] = {pk2f(g.x, g.x), pk2f(g.y, g.y), pk2f(g.z, g.z), pk2f(g.w, g.w)};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        acc[0][j][0] = ffma2(g2[j], xw0.x, acc[0][j][0]);
+                        acc[0][j][1] = ffma2(g2[j], xw0.y, acc[0][j][1]);
+                        acc[1][j][0] = ffma2(g2[j], xw1.x, acc[1][j][0]);
+                        acc[1][j][1] = ffma2(g2[j], xw1.y, acc[1][j][1]);
+                        acc[2][j][0] = ffma2(g2[j], xw2.x, acc[2][j][0]);
+                        acc[2][j][1] = ffma2(g2[j], xw2.y, acc[2][j][1]);
+                    }
+                    xw0 = xw1;
+                    xw1 = xw2;
+                }
+            }
+        }
+        __syncthreads();                                           // x buffer xb and gy slice s-1 are free
+        if (tid == 0) {
+            if (i + WG_XBUF < count) issue_slice(&map_x, xs + xb * SLICE_BYTES, xfull + xb, it, s + WG_XBUF);
+            issue_gy(s + 3);
+        }
+    }
+    // ---- reduce the two position groups, write this item's partial
+    float* part = reinterpret_cast<float*>(smem);                  // [WG_GROUPS][6912] over the dead rings
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int pr = 0; pr < 2; ++pr) {
+                float lo, hi;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[kw][j][pr]));
+                const int co = co4 * 4 + j, ci = ci4 * 4 + 2 * pr, tap = kd * 9 + kh * 3 + kw;
+                part[grp * NW16 + (co * 16 + ci) * 27 + tap] = lo;
+                part[grp * NW16 + (co * 16 + ci + 1) * 27 + tap] = hi;
+            }
+    __syncthreads();
+    for (int o = tid; o < NW16; o += WG_THREADS) a.part[static_cast<size_t>(blockIdx.x) * NW16 + o] = part[o] + part[NW16 + o];
+}
+
+__global__ void __launch_bounds__(128) conv3d_c16c16_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ gw,
+                                                                          int items) {
+    const int o = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;    // one warp per output
+    if (o >= NW16) return;
+    float s = 0.f;
+    for (int i = lane; i < items; i += 32) s += part[static_cast<size_t>(i) * NW16 + o];
+    s = warp_sum(s);
+    if (lane == 0) gw[o] = s;
+}
+
+constexpr int WG_SMEM = WG_XBUF * SLICE_BYTES + WG_GBUF * GY_BYTES + 64 + 1024;
+static_assert(WG_GROUPS * NW16 * 4 <= WG_XBUF * SLICE_BYTES + WG_GBUF * GY_BYTES, "wgrad scratch fits the rings");
+
 // ------------------------------------------------------------------------------------------ host
 static int plan(Args& a) {
     a.tiles_h = (a.H + TH - 1) / TH;
@@ -420,6 +744,80 @@ int mvd_conv3d_c16o1_wgrad(const float* gy, const float* x, float* gw, void* wor
     if (int rc = mvd::check_launch("conv3d_c16o1_wgrad")) return rc;
     conv3d_c16o1_wgrad_reduce_kernel<<<NW, 128, 0, st>>>(a.part, gw, items);
     return mvd::check_launch("conv3d_c16o1_wgrad_reduce");
+}
+
+
+int mvd_conv3d_c16c16(const float* in, const float* w, float* out, int B, int D, int H, int W, int mode, int passes,
+                      void* stream) {
+    using namespace mvd::c16;
+    MVD_REQUIRE(in && w && out, "null pointer argument");
+    if (int rc = check_shape(B, D, H, W)) return rc;
+    MVD_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (forward) or 1 (data gradient), got %d", mode);
+    MVD_REQUIRE(passes == 1 || passes == 3, "passes must be 1 (TF32) or 3 (3xTF32), got %d", passes);
+    MVD_REQUIRE(mvd::aligned16(in) && mvd::aligned16(out), "activation pointers must be 16-byte aligned");
+    cudaStream_t st = mvd::as_stream(stream);
+    Args pa{};
+    pa.B = B; pa.D = D; pa.H = H; pa.W = W;
+    const int items = plan(pa);
+    GArgs a{};
+    a.w = w; a.out = out; a.mode = mode; a.B = B; a.D = D; a.H = H; a.W = W;
+    a.tiles_h = pa.tiles_h; a.tiles_w = pa.tiles_w; a.dsplit = pa.dsplit; a.dlen = pa.dlen;
+    pa.x = in;
+    CUtensorMap map;
+    if (int rc = make_x_map(&map, in, pa)) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(conv3d_c16c16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
+        cudaFuncSetAttribute(conv3d_c16c16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
+        attr_done = true;
+    }
+    if (passes == 3) conv3d_c16c16_kernel<3><<<items, G_THREADS, G_SMEM, st>>>(map, a);
+    else conv3d_c16c16_kernel<1><<<items, G_THREADS, G_SMEM, st>>>(map, a);
+    return mvd::check_launch("conv3d_c16c16");
+}
+
+
+long long mvd_conv3d_c16c16_wgrad_workspace_bytes(int B, int D, int H, int W) {
+    using namespace mvd::c16;
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
+    Args a{};
+    a.B = B; a.D = D; a.H = H; a.W = W;
+    return static_cast<long long>(plan(a)) * NW16 * sizeof(float);
+}
+
+int mvd_conv3d_c16c16_wgrad(const float* gy, const float* x, float* gw, void* workspace, long long workspace_bytes, int B,
+                            int D, int H, int W, void* stream) {
+    using namespace mvd::c16;
+    MVD_REQUIRE(gy && x && gw && workspace, "null pointer argument");
+    if (int rc = check_shape(B, D, H, W)) return rc;
+    MVD_REQUIRE(mvd::aligned16(x) && mvd::aligned16(gy), "activation pointers must be 16-byte aligned");
+    cudaStream_t st = mvd::as_stream(stream);
+    Args pa{};
+    pa.B = B; pa.D = D; pa.H = H; pa.W = W;
+    const int items = plan(pa);
+    MVD_REQUIRE(workspace_bytes >= static_cast<long long>(items) * NW16 * 4, "workspace too small: %lld < %lld", workspace_bytes,
+                static_cast<long long>(items) * NW16 * 4);
+    WArgs a{};
+    a.part = static_cast<float*>(workspace); a.B = B; a.D = D; a.H = H; a.W = W;
+    a.tiles_h = pa.tiles_h; a.tiles_w = pa.tiles_w; a.dsplit = pa.dsplit; a.dlen = pa.dlen;
+    CUtensorMap map_x, map_gy;
+    if (int rc = make_x_map(&map_x, x, pa)) return rc;
+    {
+        const uint64_t Wd = W, Hd = H, Dd = D;
+        const uint64_t dims[5] = {C, Wd, Hd, Dd, static_cast<uint64_t>(B)};
+        const uint64_t str[4] = {C * 4, Wd * C * 4, Wd * Hd * C * 4, Wd * Hd * Dd * C * 4};
+        const uint32_t box[5] = {C, TW, TH, 1, 1};
+        if (int rc = mvd::make_f32_tensor_map(&map_gy, gy, 5, dims, str, box, 64)) return rc;
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(conv3d_c16c16_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+        attr_done = true;
+    }
+    conv3d_c16c16_wgrad_kernel<<<items, WG_THREADS, WG_SMEM, st>>>(map_x, map_gy, a);
+    if (int rc = mvd::check_launch("conv3d_c16c16_wgrad")) return rc;
+    conv3d_c16c16_wgrad_reduce_kernel<<<(NW16 + 3) / 4, 128, 0, st>>>(a.part, gw, items);
+    return mvd::check_launch("conv3d_c16c16_wgrad_reduce");
 }
 
 }

@@ -280,6 +280,56 @@ def conv3d_c16_to_1(x, weight):
     return _Conv3dC16O1.apply(x, weight)
 
 
+# ------------------------------------------------------------------------------------- reg3d first layer
+def c16c16_conv(inp, weight, mode, passes):
+    """Raw launch: mode 0 = forward, 1 = data gradient; inp logical [B,16,D,H,W] channels-last-3d, weight [16,16,3,3,3]."""
+    B, C, D, H, W = inp.shape
+    assert C == 16 and tuple(weight.shape) == (16, 16, 3, 3, 3), (inp.shape, weight.shape)
+    inp = _f32(inp).contiguous(memory_format=torch.channels_last_3d)
+    w = _f32(weight).contiguous()
+    out = torch.empty_like(inp)
+    rc = _lib.lib().mvd_conv3d_c16c16(_p(inp), _p(w), _p(out), B, D, H, W, mode, passes, _stream())
+    _lib.check(rc, "mvd_conv3d_c16c16")
+    launch_counter["n"] += 1
+    return out
+
+
+def c16c16_wgrad(gy, x):
+    """Exact-fp32 weight gradient [16,16,3,3,3] of the 16->16 layer; gy, x logical [B,16,D,H,W] channels-last-3d."""
+    B, C, D, H, W = x.shape
+    gy = _f32(gy).contiguous(memory_format=torch.channels_last_3d)
+    x = _f32(x).contiguous(memory_format=torch.channels_last_3d)
+    nbytes = _lib.lib().mvd_conv3d_c16c16_wgrad_workspace_bytes(B, D, H, W)
+    ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32)
+    gw = torch.empty((16, 16, 3, 3, 3), device=x.device, dtype=torch.float32)
+    rc = _lib.lib().mvd_conv3d_c16c16_wgrad(_p(gy), _p(x), _p(gw), _p(ws), nbytes, B, D, H, W, _stream())
+    _lib.check(rc, "mvd_conv3d_c16c16_wgrad")
+    launch_counter["n"] += 2
+    return gw
+
+
+class _Conv3dC16C16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, passes):
+        y = c16c16_conv(x, weight, 0, passes)
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gx = c16c16_conv(gy, w, 1, 1) if ctx.needs_input_grad[0] else None      # single-pass TF32 data gradient
+        gw = c16c16_wgrad(gy, x) if ctx.needs_input_grad[1] else None           # exact fp32 weight gradient
+        return gx, gw, None
+
+
+def conv3d_c16_to_16(x, weight, passes=3):
+    """Conv3d(16 -> 16, k=3, stride 1, padding 1, no bias) on a channels-last-3d volume, all three passes hand-written:
+    tensor-core implicit GEMM forward (3xTF32 split with passes=3, plain TF32 with passes=1), TF32 data gradient,
+    exact-fp32 weight gradient.  Reference: reg3d.conv0.conv, movedepth/networks/resnet_encoder.py:178, 231."""
+    return _Conv3dC16C16.apply(x, weight, passes)
+
+
 # ------------------------------------------------------------------------------------- Adam
 def adam_step(param, grad, exp_avg, exp_avg_sq, step, lr, beta1=0.9, beta2=0.999, eps=1e-8, grad_scale=1.0):
     """One fused Adam update over flat fp32 arenas (torch.optim.Adam semantics)."""

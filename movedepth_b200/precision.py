@@ -102,7 +102,13 @@ class _SplitConv(torch.autograd.Function):
         gx = gw = None
         try:
             need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-            if not _policy["split_backward"]:
+            if (nd == 3 and not transposed and x.is_cuda and tuple(w.shape) == (16, 16, 3, 3, 3) and tuple(stride) == (1, 1, 1)
+                    and tuple(padding) == (1, 1, 1) and not _policy["split_backward"]):
+                # reg3d's full-resolution 16->16 layer: hand-written gradients (cuDNN needs 1.6 ms + 2.6 ms here)
+                from . import ops
+                gx = ops.c16c16_conv(gy, w, 1, 1) if need_x else None
+                gw = ops.c16c16_wgrad(gy, x) if need_w else None
+            elif not _policy["split_backward"]:
                 gx, gw, _ = torch.ops.aten.convolution_backward(gy, x, w.contiguous(memory_format=_fmt(w)), None, stride,
                                                                 padding, (1,) * nd, transposed, output_padding, 1,
                                                                 [need_x, need_w, False])

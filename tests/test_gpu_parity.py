@@ -398,3 +398,33 @@ def test_reg3d_uses_the_stencil_head_and_matches_the_oracle(ops):
     (yb * gy).sum().backward()
     torch.testing.assert_close(xa.grad.cpu(), xb.grad, atol=1e-3 * float(xb.grad.abs().max()), rtol=1e-3)
     torch.testing.assert_close(a.prob.weight.grad.cpu(), b.prob.weight.grad, atol=1e-3 * float(b.prob.weight.grad.abs().max()), rtol=1e-3)
+
+
+@pytest.mark.parametrize("shape", [(1, 6, 8, 32), (1, 5, 11, 45), (2, 26, 24, 80)], ids=["aligned", "ragged", "multi-tile"])
+def test_conv3d_16_to_16_matches_torch_conv3d(ops, shape):
+    """Conv3d(16->16, 3x3x3, pad 1) tensor-core implicit GEMM vs torch's CPU conv3d in fp64: the 3xTF32 forward within
+    2e-5 of the output scale (fp32-class), the single-pass TF32 forward and data gradient within 2e-3 (TF32-class)."""
+    import torch.nn.functional as F
+    B, D, H, W = shape
+    gen = torch.Generator().manual_seed(4)
+    x = torch.randn(B, 16, D, H, W, generator=gen)
+    w = torch.randn(16, 16, 3, 3, 3, generator=gen) * 0.1
+    gy = torch.randn(B, 16, D, H, W, generator=gen)
+    xo = x.double().requires_grad_(True)
+    yo = F.conv3d(xo, w.double(), padding=1)
+    (yo * gy.double()).sum().backward()
+    yo = yo.detach().float()
+    xg = g(x).contiguous(memory_format=torch.channels_last_3d).requires_grad_(True)
+    wg = g(w).requires_grad_(True)
+    y3 = ops.conv3d_c16_to_16(xg, wg, 3)
+    torch.testing.assert_close(y3.detach().cpu(), yo, atol=2e-5 * float(yo.abs().max()), rtol=0)
+    y1 = ops.conv3d_c16_to_16(xg, wg, 1)
+    torch.testing.assert_close(y1.detach().cpu(), yo, atol=2e-3 * float(yo.abs().max()), rtol=0)
+    (y3 * g(gy)).sum().backward()
+    gxo = xo.grad.float()
+    torch.testing.assert_close(xg.grad.cpu(), gxo, atol=2e-3 * float(gxo.abs().max()), rtol=0)
+    gwo = None
+    wo = w.double().requires_grad_(True)
+    (F.conv3d(x.double(), wo, padding=1) * gy.double()).sum().backward()
+    gwo = wo.grad.float()
+    torch.testing.assert_close(wg.grad.cpu(), gwo, atol=2e-5 * float(gwo.abs().max()), rtol=0)     # exact-fp32 weight gradient
