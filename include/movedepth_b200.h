@@ -184,6 +184,33 @@ int mvd_conv3d_c16c16_wgrad(const float* gy, const float* x, float* gw, void* wo
                             long long workspace_bytes, int B, int D, int H, int W, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Training-mode BatchNorm on a channels-last activation viewed as a row-major [M, C] matrix
+ * (M = N*D*H*W, C a power of two in [4,1024]), fused with ReLU and the residual add.
+ * Replaces: nn.BatchNorm3d + F.relu in ConvBnReLU3D (movedepth/networks/resnet_encoder.py:175-182),
+ * nn.BatchNorm2d + F.relu in Conv2d (453-475), bn/relu/add of the torchvision ResNet blocks
+ * (74-121) and, under data-parallel training, nn.SyncBatchNorm (movedepth/trainer.py:69-129):
+ * the caller all-reduces `sums` / `sums2` (2C doubles) between the two kernels of a pass.
+ *   mvd_bn_stats      sums = [sum x (C), sum x^2 (C)]                      (zeroed inside)
+ *   mvd_bn_finalize   stats = [mean, invstd, scale = w*invstd, shift = b - mean*scale] (4C floats),
+ *                     running_mean/var updated in place (unbiased variance), count = rows over all ranks
+ *   mvd_bn_apply      y = relu?(x*scale + shift (+ residual))
+ *   mvd_bn_bwd_reduce sums2 = [sum g (C), sum g*xhat (C)],  g = gy * (y > 0) when relu
+ *   mvd_bn_bwd_apply  gx = w*invstd*(g - sum g/count - xhat * sum g*xhat/count); gres = g (nullable);
+ *                     gw = sum g*xhat, gb = sum g (nullable; pass NULL when sums2 was all-reduced)
+ * ------------------------------------------------------------------------------------- */
+int mvd_bn_stats(const float* x, long long M, int C, double* sums, void* stream);
+int mvd_bn_finalize(const double* sums, double count, const float* weight, const float* bias,
+                    float* running_mean, float* running_var, float momentum, float eps, float* stats,
+                    int C, void* stream);
+int mvd_bn_apply(const float* x, const float* residual, const float* stats, float* y, long long M,
+                 int C, int relu, void* stream);
+int mvd_bn_bwd_reduce(const float* gy, const float* x, const float* y, const float* stats,
+                      double* sums2, long long M, int C, int relu, void* stream);
+int mvd_bn_bwd_apply(const float* gy, const float* x, const float* y, const float* stats,
+                     const float* weight, const double* sums2, double count, float* gx, float* gres,
+                     float* gw, float* gb, long long M, int C, int relu, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Measurement helpers (bench.py's live cost-volume roofline): CUDA timing events that also
  * work INSIDE a captured CUDA graph.  mvd_event_record with external != 0 uses
  * cudaEventRecordExternal, i.e. the record becomes an event-record NODE when the stream is

@@ -16,6 +16,7 @@ _P = ctypes.c_void_p
 _I = ctypes.c_int
 _F = ctypes.c_float
 _LL = ctypes.c_longlong
+_D = ctypes.c_double
 
 # argument types per entry point, in header order
 SIGNATURES = {
@@ -40,6 +41,11 @@ SIGNATURES = {
     "mvd_conv3d_c16c16": ([_P] * 3 + [_I] * 6 + [_P], _I),
     "mvd_conv3d_c16c16_wgrad_workspace_bytes": ([_I] * 4, _LL),
     "mvd_conv3d_c16c16_wgrad": ([_P] * 4 + [_LL] + [_I] * 4 + [_P], _I),
+    "mvd_bn_stats": ([_P, _LL, _I, _P, _P], _I),
+    "mvd_bn_finalize": ([_P, _D, _P, _P, _P, _P, _F, _F, _P, _I, _P], _I),
+    "mvd_bn_apply": ([_P, _P, _P, _P, _LL, _I, _I, _P], _I),
+    "mvd_bn_bwd_reduce": ([_P, _P, _P, _P, _P, _LL, _I, _I, _P], _I),
+    "mvd_bn_bwd_apply": ([_P] * 6 + [_D] + [_P] * 4 + [_LL, _I, _I, _P], _I),
     "mvd_event_create": ([], _P),
     "mvd_event_record": ([_P, _P, _I], _I),
     "mvd_event_elapsed_ms": ([_P, _P, ctypes.POINTER(ctypes.c_float)], _I),

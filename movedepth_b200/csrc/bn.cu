@@ -1,0 +1,265 @@
+// Training-mode BatchNorm for channels-last activations, fused with what surrounds it in the reference's conv
+// blocks: ReLU (ConvBnReLU3D movedepth/networks/resnet_encoder.py:175-182, Conv2d 453-475, ResNet blocks) and the
+// residual add of the ResNet basic block.  The activation is a row-major [M, C] matrix (M = N*D*H*W, C contiguous).
+//
+//   forward : stats   (1 read)          per-channel sum / sum of squares, fp32 per thread, fp64 across the grid
+//             [multi-GPU: the 2C fp64 sums are all-reduced between the two kernels == SyncBatchNorm]
+//             finalize                  mean, invstd, running statistics, scale/shift
+//             apply   (1 read, 1 write) y = relu(x*scale + shift (+ residual))
+//   backward: reduce  (2-3 reads)       sum(g), sum(g*xhat)  with g = gy * (y > 0)
+//             apply   (2-3 reads, 1-2 writes)  gx = scale*(g - mean(g) - xhat*mean(g*xhat)), gres = g; gw, gb
+// cuDNN's NHWC BatchNorm kernels move the 283 MB full-resolution reg3d activations at ~1.4 TB/s and need separate
+// ReLU / add passes; these are plain HBM-bound float4 streams.
+#include "common.cuh"
+#include "../../include/movedepth_b200.h"
+
+namespace mvd {
+namespace bn {
+
+constexpr int THREADS = 256;
+
+__device__ __forceinline__ void add4(float (&s)[4], const float4& v) {
+    s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+}
+
+// blockDim = 256 threads, q = C/4 channel quads; thread t handles quad t % q of rows t / q + k * (256 / q).
+struct Map {
+    int q, rows_per_iter, quad, row0;
+};
+__device__ __forceinline__ Map make_map(int C) {
+    Map m;
+    m.q = C >> 2;
+    m.rows_per_iter = THREADS / m.q;
+    m.quad = threadIdx.x % m.q;
+    m.row0 = threadIdx.x / m.q;
+    return m;
+}
+
+// reduce 8 per-thread partials over the threads that share a channel quad, then one fp64 atomic per channel per CTA
+__device__ __forceinline__ void block_reduce_to_global(const float (&a)[4], const float (&b)[4], const Map& m, double* out, int C) {
+    __shared__ float red[THREADS][8];
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        red[t][k] = a[k];
+        red[t][4 + k] = b[k];
+    }
+    __syncthreads();
+    // thread (quad, j) for j < 8 sums column j of its quad over the rows_per_iter threads
+    for (int o = t; o < m.q * 8; o += THREADS) {
+        const int quad = o >> 3, j = o & 7;
+        double s = 0.0;
+        for (int r = 0; r < m.rows_per_iter; ++r) s += static_cast<double>(red[r * m.q + quad][j]);
+        const int ch = quad * 4 + (j & 3);
+        atomicAdd(out + (j < 4 ? ch : C + ch), s);
+    }
+}
+
+// ---- forward
+__global__ void __launch_bounds__(THREADS) bn_stats_kernel(const float* __restrict__ x, long long M, int C, double* __restrict__ sums) {
+    const Map m = make_map(C);
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+    const float4* xp = reinterpret_cast<const float4*>(x);
+    for (long long r = static_cast<long long>(blockIdx.x) * m.rows_per_iter + m.row0; r < M;
+         r += static_cast<long long>(gridDim.x) * m.rows_per_iter) {
+        const float4 v = __ldg(xp + r * m.q + m.quad);
+        add4(s, v);
+        ss[0] = fmaf(v.x, v.x, ss[0]); ss[1] = fmaf(v.y, v.y, ss[1]); ss[2] = fmaf(v.z, v.z, ss[2]); ss[3] = fmaf(v.w, v.w, ss[3]);
+    }
+    block_reduce_to_global(s, ss, m, sums, C);
+}
+
+// one thread per channel.  stats: [mean C][invstd C][scale C][shift C]
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ weight,
+                                   const float* __restrict__ bias, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float momentum, float eps, float* __restrict__ stats, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double mean = sums[c] / count;
+    double var = sums[C + c] / count - mean * mean;
+    var = var < 0.0 ? 0.0 : var;
+    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float w = weight ? weight[c] : 1.f, b = bias ? bias[c] : 0.f;
+    const float scale = w * invstd;
+    stats[c] = static_cast<float>(mean);
+    stats[C + c] = invstd;
+    stats[2 * C + c] = scale;
+    stats[3 * C + c] = b - static_cast<float>(mean) * scale;
+    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+    if (running_var) {
+        const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+    }
+}
+
+__global__ void __launch_bounds__(THREADS) bn_apply_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                                                           const float* __restrict__ stats, float* __restrict__ y, long long M,
+                                                           int C, int relu) {
+    const Map m = make_map(C);
+    const float4 sc = *reinterpret_cast<const float4*>(stats + 2 * C + 4 * m.quad);
+    const float4 sh = *reinterpret_cast<const float4*>(stats + 3 * C + 4 * m.quad);
+    const float4* xp = reinterpret_cast<const float4*>(x);
+    const float4* rp = reinterpret_cast<const float4*>(res);
+    float4* yp = reinterpret_cast<float4*>(y);
+    for (long long r = static_cast<long long>(blockIdx.x) * m.rows_per_iter + m.row0; r < M;
+         r += static_cast<long long>(gridDim.x) * m.rows_per_iter) {
+        const long long i = r * m.q + m.quad;
+        const float4 v = __ldg(xp + i);
+        float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+        if (rp) {
+            const float4 rv = __ldg(rp + i);
+            o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
+        }
+        if (relu) {
+            o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+        }
+        yp[i] = o;
+    }
+}
+
+// ---- backward
+__device__ __forceinline__ float4 masked(const float4& g, const float4& y, int relu) {
+    if (!relu) return g;
+    return make_float4(y.x > 0.f ? g.x : 0.f, y.y > 0.f ? g.y : 0.f, y.z > 0.f ? g.z : 0.f, y.w > 0.f ? g.w : 0.f);
+}
+
+// sums2: [sum g (C)][sum g*xhat (C)]
+__global__ void __launch_bounds__(THREADS) bn_bwd_reduce_kernel(const float* __restrict__ gy, const float* __restrict__ x,
+                                                                const float* __restrict__ y, const float* __restrict__ stats,
+                                                                double* __restrict__ sums2, long long M, int C, int relu) {
+    const Map m = make_map(C);
+    const float4 mean = *reinterpret_cast<const float4*>(stats + 4 * m.quad);
+    const float4 istd = *reinterpret_cast<const float4*>(stats + C + 4 * m.quad);
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, sx[4] = {0.f, 0.f, 0.f, 0.f};
+    const float4* gp = reinterpret_cast<const float4*>(gy);
+    const float4* xp = reinterpret_cast<const float4*>(x);
+    const float4* yp = reinterpret_cast<const float4*>(y);
+    for (long long r = static_cast<long long>(blockIdx.x) * m.rows_per_iter + m.row0; r < M;
+         r += static_cast<long long>(gridDim.x) * m.rows_per_iter) {
+        const long long i = r * m.q + m.quad;
+        float4 g = __ldg(gp + i);
+        if (relu) g = masked(g, __ldg(yp + i), 1);
+        const float4 v = __ldg(xp + i);
+        add4(s, g);
+        sx[0] = fmaf(g.x, (v.x - mean.x) * istd.x, sx[0]);
+        sx[1] = fmaf(g.y, (v.y - mean.y) * istd.y, sx[1]);
+        sx[2] = fmaf(g.z, (v.z - mean.z) * istd.z, sx[2]);
+        sx[3] = fmaf(g.w, (v.w - mean.w) * istd.w, sx[3]);
+    }
+    block_reduce_to_global(s, sx, m, sums2, C);
+}
+
+__global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const float* __restrict__ gy, const float* __restrict__ x,
+                                                               const float* __restrict__ y, const float* __restrict__ stats,
+                                                               const float* __restrict__ weight, const double* __restrict__ sums2,
+                                                               double count, float* __restrict__ gx, float* __restrict__ gres,
+                                                               float* __restrict__ gw, float* __restrict__ gb, long long M, int C,
+                                                               int relu) {
+    const Map m = make_map(C);
+    const float4 mean = *reinterpret_cast<const float4*>(stats + 4 * m.quad);
+    const float4 istd = *reinterpret_cast<const float4*>(stats + C + 4 * m.quad);
+    float k[4], mg[4], mgx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = 4 * m.quad + j;
+        const float w = weight ? weight[c] : 1.f;
+        k[j] = w * reinterpret_cast<const float*>(&istd)[j];
+        mg[j] = static_cast<float>(sums2[c] / count);
+        mgx[j] = static_cast<float>(sums2[C + c] / count);
+    }
+    if (blockIdx.x == 0) {                                 // parameter gradients (NULL when sums2 was all-reduced: the
+        for (int c = threadIdx.x; c < C; c += THREADS) {   // caller then takes them from its local sums)
+            if (gw) gw[c] = static_cast<float>(sums2[C + c]);
+            if (gb) gb[c] = static_cast<float>(sums2[c]);
+        }
+    }
+    const float4* gp = reinterpret_cast<const float4*>(gy);
+    const float4* xp = reinterpret_cast<const float4*>(x);
+    const float4* yp = reinterpret_cast<const float4*>(y);
+    float4* gxp = reinterpret_cast<float4*>(gx);
+    float4* grp = reinterpret_cast<float4*>(gres);
+    for (long long r = static_cast<long long>(blockIdx.x) * m.rows_per_iter + m.row0; r < M;
+         r += static_cast<long long>(gridDim.x) * m.rows_per_iter) {
+        const long long i = r * m.q + m.quad;
+        float4 g = __ldg(gp + i);
+        if (relu) g = masked(g, __ldg(yp + i), 1);
+        const float4 v = __ldg(xp + i);
+        float4 o;
+        o.x = k[0] * (g.x - mg[0] - (v.x - mean.x) * istd.x * mgx[0]);
+        o.y = k[1] * (g.y - mg[1] - (v.y - mean.y) * istd.y * mgx[1]);
+        o.z = k[2] * (g.z - mg[2] - (v.z - mean.z) * istd.z * mgx[2]);
+        o.w = k[3] * (g.w - mg[3] - (v.w - mean.w) * istd.w * mgx[3]);
+        gxp[i] = o;
+        if (grp) grp[i] = g;
+    }
+}
+
+static int grid_for(long long M, int C) {
+    const int rows_per_iter = THREADS / (C >> 2);
+    const long long blocks = (M + rows_per_iter - 1) / rows_per_iter;
+    const long long cap = static_cast<long long>(sm_count()) * 8;
+    return static_cast<int>(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
+static int check(long long M, int C) {
+    MVD_REQUIRE(M > 0 && C >= 4 && C <= 1024 && (C & (C - 1)) == 0, "BatchNorm kernels need C a power of two in [4,1024] (got M=%lld C=%d)", M, C);
+    return 0;
+}
+
+}  // namespace bn
+}  // namespace mvd
+
+extern "C" {
+
+int mvd_bn_stats(const float* x, long long M, int C, double* sums, void* stream) {
+    using namespace mvd::bn;
+    MVD_REQUIRE(x && sums, "null pointer argument");
+    if (int rc = check(M, C)) return rc;
+    cudaStream_t st = mvd::as_stream(stream);
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
+    if (e != cudaSuccess) return mvd::fail(static_cast<int>(e), "bn_stats memset: %s", cudaGetErrorString(e));
+    bn_stats_kernel<<<grid_for(M, C), THREADS, 0, st>>>(x, M, C, sums);
+    return mvd::check_launch("bn_stats");
+}
+
+int mvd_bn_finalize(const double* sums, double count, const float* weight, const float* bias, float* running_mean,
+                    float* running_var, float momentum, float eps, float* stats, int C, void* stream) {
+    using namespace mvd::bn;
+    MVD_REQUIRE(sums && stats && count > 0, "bad argument");
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, mvd::as_stream(stream)>>>(sums, count, weight, bias, running_mean, running_var,
+                                                                            momentum, eps, stats, C);
+    return mvd::check_launch("bn_finalize");
+}
+
+int mvd_bn_apply(const float* x, const float* residual, const float* stats, float* y, long long M, int C, int relu, void* stream) {
+    using namespace mvd::bn;
+    MVD_REQUIRE(x && stats && y, "null pointer argument");
+    if (int rc = check(M, C)) return rc;
+    bn_apply_kernel<<<grid_for(M, C), THREADS, 0, mvd::as_stream(stream)>>>(x, residual, stats, y, M, C, relu);
+    return mvd::check_launch("bn_apply");
+}
+
+int mvd_bn_bwd_reduce(const float* gy, const float* x, const float* y, const float* stats, double* sums2, long long M, int C,
+                      int relu, void* stream) {
+    using namespace mvd::bn;
+    MVD_REQUIRE(gy && x && stats && sums2 && (!relu || y), "null pointer argument");
+    if (int rc = check(M, C)) return rc;
+    cudaStream_t st = mvd::as_stream(stream);
+    cudaError_t e = cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * C, st);
+    if (e != cudaSuccess) return mvd::fail(static_cast<int>(e), "bn_bwd_reduce memset: %s", cudaGetErrorString(e));
+    bn_bwd_reduce_kernel<<<grid_for(M, C), THREADS, 0, st>>>(gy, x, y, stats, sums2, M, C, relu);
+    return mvd::check_launch("bn_bwd_reduce");
+}
+
+int mvd_bn_bwd_apply(const float* gy, const float* x, const float* y, const float* stats, const float* weight,
+                     const double* sums2, double count, float* gx, float* gres, float* gw, float* gb, long long M, int C,
+                     int relu, void* stream) {
+    using namespace mvd::bn;
+    MVD_REQUIRE(gy && x && stats && sums2 && gx && (!relu || y) && count > 0, "bad argument");
+    if (int rc = check(M, C)) return rc;
+    bn_bwd_apply_kernel<<<grid_for(M, C), THREADS, 0, mvd::as_stream(stream)>>>(gy, x, y, stats, weight, sums2, count, gx, gres, gw,
+                                                                                 gb, M, C, relu);
+    return mvd::check_launch("bn_bwd_apply");
+}
+
+}

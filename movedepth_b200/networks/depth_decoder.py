@@ -10,6 +10,7 @@ import torch.nn.functional as F
 
 from .. import precision as PR
 from ..layers import ConvBlock, Conv3x3, upsample
+from .resnet_encoder import ConvBnReLUSeq
 
 
 class DepthDecoder(nn.Module):
@@ -61,8 +62,8 @@ class UncertNet(nn.Module):
 
     def __init__(self):
         super().__init__()
-        self.conv1 = nn.Sequential(PR.Conv2d(1, 8, 3, 1, 1, bias=False), nn.BatchNorm2d(8), nn.ReLU(inplace=True))
-        self.conv2 = nn.Sequential(PR.Conv2d(8, 8, 3, 1, 1, bias=False), nn.BatchNorm2d(8), nn.ReLU(inplace=True))
+        self.conv1 = ConvBnReLUSeq(PR.Conv2d(1, 8, 3, 1, 1, bias=False), nn.BatchNorm2d(8), nn.ReLU(inplace=True))
+        self.conv2 = ConvBnReLUSeq(PR.Conv2d(8, 8, 3, 1, 1, bias=False), nn.BatchNorm2d(8), nn.ReLU(inplace=True))
         self.head_convs = PR.Conv2d(8, 1, 3, 1, 1, bias=False)
 
     def forward(self, x):

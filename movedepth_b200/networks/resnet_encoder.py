@@ -16,6 +16,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 import torchvision.models as tvm
 
+from .. import norm as NM
 from .. import precision as PR
 
 
@@ -63,14 +64,14 @@ class ResnetEncoder(nn.Module):
             _load_imagenet(net, num_layers, num_input_images)
         del net.fc
         del net.avgpool
-        self.encoder = net
+        self.encoder = NM.adopt(net)             # residual blocks: conv -> fused BN(+ReLU, +residual) kernels
         if num_layers > 34:
             self.num_ch_enc[1:] *= 4
 
     def forward(self, input_image):
         e = self.encoder
         x = (input_image - 0.45) / 0.225
-        f0 = e.relu(e.bn1(e.conv1(x)))
+        f0 = NM.bn_act(e.bn1, e.conv1(x), relu=True)
         f1 = e.layer1(e.maxpool(f0))
         f2 = e.layer2(f1)
         f3 = e.layer3(f2)
@@ -91,7 +92,7 @@ class Conv2d(nn.Module):
     def forward(self, x):
         x = self.conv(x)
         if self.bn is not None:
-            x = self.bn(x)
+            return NM.bn_act(self.bn, x, relu=self.relu)
         return F.relu(x, inplace=True) if self.relu else x
 
 
@@ -145,11 +146,19 @@ class ConvBnReLU3D(nn.Module):
         self.bn = nn.BatchNorm3d(out_channels)
 
     def forward(self, x):
-        return F.relu(self.bn(self.conv(x)), inplace=True)
+        return NM.bn_act(self.bn, self.conv(x), relu=True)
+
+
+class ConvBnReLUSeq(nn.Sequential):
+    """nn.Sequential(conv, BatchNorm, ReLU) -- the reference's container and state-dict keys (`{0,1}.*`) -- whose forward
+    runs the fused BN+ReLU kernels."""
+
+    def forward(self, x):
+        return NM.bn_act(self[1], self[0](x), relu=True)
 
 
 def _up3d(cin, cout, k=3, p=1, op=1, s=2):
-    return nn.Sequential(PR.ConvTranspose3d(cin, cout, kernel_size=k, padding=p, output_padding=op, stride=s, bias=False),
+    return ConvBnReLUSeq(PR.ConvTranspose3d(cin, cout, kernel_size=k, padding=p, output_padding=op, stride=s, bias=False),
                          nn.BatchNorm3d(cout), nn.ReLU(inplace=True))
 
 

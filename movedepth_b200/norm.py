@@ -1,0 +1,138 @@
+"""Training-mode BatchNorm (+ReLU, + residual add) on the hand-written channels-last kernels of csrc/bn.cu.
+
+`bn_act(bn, x, relu=False, residual=None)` is what the conv blocks call instead of `relu(bn(x) [+ residual])`.
+The BatchNorm modules themselves stay stock `nn.BatchNorm{2,3}d` / `nn.SyncBatchNorm` objects (same parameters,
+buffers and state-dict keys as the reference: movedepth/networks/resnet_encoder.py:175-182, 453-475; torchvision
+ResNet blocks).  Under `nn.SyncBatchNorm` (data-parallel training, movedepth/trainer.py:69-129) the per-channel
+fp64 sums are all-reduced between the statistics and the apply kernels -- one small NCCL call per direction instead of
+SyncBatchNorm's all_gather + gather_stats pipeline.  Evaluation mode and CPU tensors use torch's own batch_norm.
+"""
+import ctypes
+import types
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib
+
+enabled = True            # set False to route everything through torch's batch_norm (A/B measurements)
+
+
+def _p(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _fmt(t):
+    return torch.channels_last_3d if t.dim() == 5 else torch.channels_last
+
+
+def _count_launch(n):
+    from . import ops
+    ops.launch_counter["n"] += n
+
+
+class _BNAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, running_mean, running_var, momentum, eps, relu, sync):
+        L = _lib.lib()
+        C = x.shape[1]
+        xc = x.contiguous(memory_format=_fmt(x))
+        M = xc.numel() // C
+        rc_ = residual.contiguous(memory_format=_fmt(x)) if residual is not None else None
+        sums = torch.empty(2 * C, device=x.device, dtype=torch.float64)
+        _lib.check(L.mvd_bn_stats(_p(xc), M, C, _p(sums), _stream()), "mvd_bn_stats")
+        count = float(M)
+        if sync:
+            dist.all_reduce(sums)
+            count *= dist.get_world_size()
+        stats = torch.empty(4 * C, device=x.device, dtype=torch.float32)
+        _lib.check(L.mvd_bn_finalize(_p(sums), count, _p(weight), _p(bias), _p(running_mean), _p(running_var), float(momentum),
+                                     float(eps), _p(stats), C, _stream()), "mvd_bn_finalize")
+        y = torch.empty_like(xc)
+        _lib.check(L.mvd_bn_apply(_p(xc), _p(rc_), _p(stats), _p(y), M, C, int(relu), _stream()), "mvd_bn_apply")
+        _count_launch(4)
+        ctx.save_for_backward(xc, y if relu else None, stats, weight)
+        ctx.cfg = (M, C, count, bool(relu), bool(sync), residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        xc, y, stats, weight = ctx.saved_tensors
+        M, C, count, relu, sync, has_res = ctx.cfg
+        L = _lib.lib()
+        gy = gy.contiguous(memory_format=_fmt(xc))
+        sums2 = torch.empty(2 * C, device=xc.device, dtype=torch.float64)
+        _lib.check(L.mvd_bn_bwd_reduce(_p(gy), _p(xc), _p(y), _p(stats), _p(sums2), M, C, int(relu), _stream()), "mvd_bn_bwd_reduce")
+        gw = gb = None
+        if sync:                                  # parameter gradients are this rank's own sums (DDP averages them later)
+            gb, gw = sums2[:C].float(), sums2[C:].float()
+            dist.all_reduce(sums2)
+        else:
+            gw = torch.empty(C, device=xc.device, dtype=torch.float32)
+            gb = torch.empty(C, device=xc.device, dtype=torch.float32)
+        gx = torch.empty_like(xc)
+        gres = torch.empty_like(xc) if (has_res and ctx.needs_input_grad[3]) else None
+        _lib.check(L.mvd_bn_bwd_apply(_p(gy), _p(xc), _p(y), _p(stats), _p(weight), _p(sums2), count, _p(gx), _p(gres),
+                                      _p(None if sync else gw), _p(None if sync else gb), M, C, int(relu), _stream()),
+                   "mvd_bn_bwd_apply")
+        _count_launch(3)
+        if weight is None or not ctx.needs_input_grad[1]:
+            gw = None
+        if not ctx.needs_input_grad[2]:
+            gb = None
+        return gx, gw, gb, gres, None, None, None, None, None, None
+
+
+def _fusable(bn, x):
+    C = x.shape[1]
+    return (enabled and bn.training and x.is_cuda and x.dtype == torch.float32 and x.dim() in (4, 5) and bn.track_running_stats
+            and bn.momentum is not None and 4 <= C <= 1024 and (C & (C - 1)) == 0 and x.numel() > 0)
+
+
+def bn_act(bn, x, relu=False, residual=None):
+    """relu(bn(x) + residual) with `bn` a BatchNorm2d / BatchNorm3d / SyncBatchNorm module."""
+    if not _fusable(bn, x):
+        y = bn(x)
+        if residual is not None:
+            y = y + residual
+        return F.relu(y, inplace=True) if relu else y
+    sync = isinstance(bn, nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    bn.num_batches_tracked += 1
+    return _BNAct.apply(x, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu, sync)
+
+
+# ---- torchvision ResNet blocks: same modules / parameters, forward routed through bn_act -----------------------------
+def _basic_block_forward(self, x):
+    identity = x if self.downsample is None else _downsample(self.downsample, x)
+    out = bn_act(self.bn1, self.conv1(x), relu=True)
+    return bn_act(self.bn2, self.conv2(out), relu=True, residual=identity)
+
+
+def _bottleneck_forward(self, x):
+    identity = x if self.downsample is None else _downsample(self.downsample, x)
+    out = bn_act(self.bn1, self.conv1(x), relu=True)
+    out = bn_act(self.bn2, self.conv2(out), relu=True)
+    return bn_act(self.bn3, self.conv3(out), relu=True, residual=identity)
+
+
+def _downsample(seq, x):
+    if len(seq) == 2 and isinstance(seq[1], nn.modules.batchnorm._BatchNorm):
+        return bn_act(seq[1], seq[0](x))
+    return seq(x)
+
+
+def adopt(module):
+    """Route the residual blocks of a torchvision ResNet through bn_act (in place; parameters untouched)."""
+    from torchvision.models.resnet import BasicBlock, Bottleneck
+    for m in module.modules():
+        if isinstance(m, BasicBlock):
+            m.forward = types.MethodType(_basic_block_forward, m)
+        elif isinstance(m, Bottleneck):
+            m.forward = types.MethodType(_bottleneck_forward, m)
+    return module

@@ -428,3 +428,98 @@ def test_conv3d_16_to_16_matches_torch_conv3d(ops, shape):
     (F.conv3d(x.double(), wo, padding=1) * gy.double()).sum().backward()
     gwo = wo.grad.float()
     torch.testing.assert_close(wg.grad.cpu(), gwo, atol=2e-5 * float(gwo.abs().max()), rtol=0)     # exact-fp32 weight gradient
+
+
+# ---------------------------------------------------------------------------------------------- BatchNorm kernels
+@pytest.mark.parametrize("shape,relu,res", [((3, 16, 5, 6, 7), True, False), ((4, 64, 9, 11), True, True), ((2, 8, 6, 10), False, False),
+                                            ((2, 512, 3, 5), True, True)], ids=["3d-relu", "2d-relu-res", "2d-plain", "c512"])
+def test_fused_batchnorm_matches_torch(shape, relu, res):
+    """csrc/bn.cu (stats / finalize / apply, backward reduce / apply) vs torch's batch_norm + add + relu in fp64:
+    outputs, input / residual / weight / bias gradients and the running statistics."""
+    import torch.nn as nn
+    from movedepth_b200 import norm as NM
+    gen = torch.Generator().manual_seed(9)
+    C = shape[1]
+    cls = nn.BatchNorm3d if len(shape) == 5 else nn.BatchNorm2d
+    fmt = torch.channels_last_3d if len(shape) == 5 else torch.channels_last
+    x = torch.randn(shape, generator=gen) * 2 + 0.5
+    r = torch.randn(shape, generator=gen) if res else None
+    gy = torch.randn(shape, generator=gen)
+    ref = cls(C).double()
+    mine = cls(C).to(DEV)
+    with torch.no_grad():
+        ref.weight.copy_(1 + 0.2 * torch.randn(C, generator=gen))
+        ref.bias.copy_(0.1 * torch.randn(C, generator=gen))
+        mine.weight.copy_(ref.weight.float())
+        mine.bias.copy_(ref.bias.float())
+    xo = x.double().requires_grad_(True)
+    ro = r.double().requires_grad_(True) if res else None
+    yo = ref(xo)
+    if res:
+        yo = yo + ro
+    if relu:
+        yo = torch.relu(yo)
+    (yo * gy.double()).sum().backward()
+    xg = g(x).contiguous(memory_format=fmt).requires_grad_(True)
+    rg = g(r).contiguous(memory_format=fmt).requires_grad_(True) if res else None
+    y = NM.bn_act(mine, xg, relu=relu, residual=rg)
+    (y * g(gy)).sum().backward()
+
+    def close(a, b, tol=2e-5):
+        b = b.detach().float()
+        torch.testing.assert_close(a.detach().cpu(), b, atol=tol * max(1.0, float(b.abs().max())), rtol=tol)
+    close(y, yo)
+    close(xg.grad, xo.grad, 1e-4)
+    if res:
+        close(rg.grad, ro.grad)
+    close(mine.weight.grad, ref.weight.grad, 1e-4)
+    close(mine.bias.grad, ref.bias.grad, 1e-4)
+    close(mine.running_mean, ref.running_mean)
+    close(mine.running_var, ref.running_var)
+    assert int(mine.num_batches_tracked) == 1
+
+
+def _sync_bn_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import torch.nn as nn
+    from movedepth_b200 import norm as NM
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)      # gloo stages the 2C fp64 sums through the host
+    torch.cuda.set_device(0)
+    gen = torch.Generator().manual_seed(21)
+    x = torch.randn(4, 16, 6, 10, generator=gen) * 1.5 + 0.3
+    gy = torch.randn(4, 16, 6, 10, generator=gen)
+    bn = nn.SyncBatchNorm(16).to("cuda:0")
+    xs = x[rank * 2:rank * 2 + 2].to("cuda:0").contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = NM.bn_act(bn, xs, relu=True)
+    (y * gy[rank * 2:rank * 2 + 2].to("cuda:0")).sum().backward()
+    q.put((rank, y.detach().cpu(), xs.grad.cpu(), bn.weight.grad.cpu(), bn.running_var.cpu()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sync_batchnorm_statistics_are_exchanged_across_ranks():
+    """nn.SyncBatchNorm semantics (movedepth/trainer.py:69-129): two ranks, each with half of the batch, must produce
+    what one BatchNorm over the whole batch produces; the weight gradients of the ranks add up to the full one."""
+    import torch.multiprocessing as mp
+    import torch.nn as nn
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sync_bn_worker, args=(r, 2, 29533, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict((r, rest) for r, *rest in [q.get(timeout=120) for _ in range(2)])
+    for p in procs:
+        p.join(timeout=60)
+    gen = torch.Generator().manual_seed(21)
+    x = (torch.randn(4, 16, 6, 10, generator=gen) * 1.5 + 0.3).double().requires_grad_(True)
+    gy = torch.randn(4, 16, 6, 10, generator=gen).double()
+    bn = nn.BatchNorm2d(16).double()
+    y = torch.relu(bn(x))
+    (y * gy).sum().backward()
+    for r in range(2):
+        yr, gxr, gwr, rvr = got[r]
+        torch.testing.assert_close(yr, y[r * 2:r * 2 + 2].detach().float(), atol=2e-5, rtol=2e-5)
+        torch.testing.assert_close(gxr, x.grad[r * 2:r * 2 + 2].float(), atol=1e-4, rtol=1e-4)
+        torch.testing.assert_close(rvr, bn.running_var.float(), atol=1e-5, rtol=1e-5)
+    torch.testing.assert_close(got[0][2] + got[1][2], bn.weight.grad.float(), atol=1e-4, rtol=1e-4)
