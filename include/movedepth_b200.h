@@ -176,6 +176,10 @@ int mvd_conv3d_c16o1_wgrad(const float* gy, const float* x, float* gw, void* wor
  * ------------------------------------------------------------------------------------- */
 int mvd_conv3d_c16c16(const float* in, const float* w, float* out, int B, int D, int H, int W,
                       int mode, int passes, void* stream);
+/* The same contract on the 5th-generation tensor cores: tcgen05.mma kind::tf32, accumulators in TMEM, every tap's
+ * A operand = the TMA-staged slice at a shifted start address.  flags: reserved, pass 0. */
+int mvd_conv3d_c16c16_tc(const float* in, const float* w, float* out, int B, int D, int H, int W,
+                         int mode, int passes, int flags, void* stream);
 /* Weight gradient of the same layer, exact fp32 (packed FFMA2 on the CUDA cores):
  *   gy, x : [B,D,H,W,16];  gw : [16,16,3,3,3] OVERWRITTEN;  workspace of
  *   mvd_conv3d_c16c16_wgrad_workspace_bytes(B,D,H,W) bytes (per-tile partials, reduced deterministically). */

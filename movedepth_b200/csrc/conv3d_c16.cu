@@ -636,6 +636,243 @@ __global__ void __launch_bounds__(128) conv3d_c16c16_wgrad_reduce_kernel(const f
 constexpr int WG_SMEM = WG_XBUF * SLICE_BYTES + WG_GBUF * GY_BYTES + 64 + 1024;
 static_assert(WG_GROUPS * NW16 * 4 <= WG_XBUF * SLICE_BYTES + WG_GBUF * GY_BYTES, "wgrad scratch fits the rings");
 
+// ================================================================================================
+// The 16 -> 16 layer on the 5th-generation tensor cores: tcgen05.mma (kind::tf32) with TMEM accumulators.
+//   D[128 positions x 16 out-ch] += A_tap[128 x 16 in-ch] * B_tap[16 x 16]   for the 27 taps
+// * The input slice of a 7x32 tile (+halo = 9x34 positions x 64 B) is TMA-loaded with the 64B swizzle.  Output
+//   positions are flattened with the halo pitch, v = r*34 + c, so that EVERY tap's A operand is the same shared
+//   memory tile at a start address shifted by (kh*34 + kw) rows -- a K-major SWIZZLE_64B canonical layout (rows 64 B
+//   apart, 8-row groups 512 B apart); the two garbage columns per row are computed and dropped (2 M-blocks of 128
+//   rows cover the 238 flattened positions).
+// * Slice marching as before: input slice s adds tap kd to output slice s+1-kd; four TMEM accumulator slots
+//   (slot = output slice & 3) x 2 M-blocks x 16 columns = 128 TMEM columns.
+// * 3xTF32: the slice is split in place into hi = x & ~0x1fff and lo = x - hi (second buffer); the filter bank is
+//   kept as hi / lo K-major tiles; D += hi*hi + lo*hi + hi*lo.  passes == 1: plain TF32 (data gradient).
+// * One thread issues the MMAs (54 or 162 per slice and M-block), tcgen05.commit signals an mbarrier, the four warps
+//   read their TMEM lane quadrant with tcgen05.ld (one position = 16 channels = 64 B per thread) and store it.
+namespace tc {
+constexpr int TH = 7, TW = 32, HH = TH + 2, HW = TW + 2;     // 9 x 34 halo tile
+constexpr int SLICE_POS = HH * HW;                            // 306 positions written by TMA
+constexpr int SLICE_BYTES = 21504;                            // >= (255 + 2*34 + 2 + 1) * 64 = 20864, multiple of 512
+constexpr int NBUF = 3;
+constexpr int THREADS = 128;
+constexpr int B_TAP_BYTES = 1024;                             // 16 rows x 64 B
+constexpr int B_BYTES = 27 * B_TAP_BYTES;
+constexpr uint32_t TMEM_COLS = 128;
+
+template <int PASSES>
+struct Smem {
+    static constexpr int OFF_A = 0;
+    static constexpr int OFF_LO = OFF_A + NBUF * SLICE_BYTES;                        // [2] lo halves of the slice (3xTF32 only)
+    static constexpr int OFF_BHI = OFF_LO + (PASSES == 3 ? 2 * SLICE_BYTES : 0);
+    static constexpr int OFF_BLO = OFF_BHI + B_BYTES;
+    static constexpr int OFF_BAR = OFF_BLO + (PASSES == 3 ? B_BYTES : 0);            // full[NBUF], done[2], tmem base
+    static constexpr int TOTAL = OFF_BAR + 64;
+    static constexpr int ALLOC = TOTAL + 1024;
+};
+
+// K-major, SWIZZLE_64B shared-memory matrix descriptor: LBO = 1 (16 B units, unused for swizzled K-major), SBO = 512 B
+// (8 rows x 64 B), version 1 (Blackwell), base offset 0 -- measured: the swizzle phase comes from the absolute
+// shared-memory address, so a start address shifted by whole 64 B rows needs NO base-offset correction (setting
+// (addr >> 7) & 7 there gives wrong results).  Advancing by `bytes` = adding bytes >> 4 to the low word.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(512 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(4) << 61;
+    return d;
+}
+// instruction descriptor: D = F32, A = B = TF32, both K-major, N = 16, M = 128
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+struct TArgs {
+    const float* w;
+    float* out;
+    int mode;
+    int B, D, H, W;
+    int tiles_h, tiles_w, dsplit, dlen;
+};
+
+__device__ __forceinline__ Item tc_item(const TArgs& a, int item) {
+    Item it;
+    const int tw = item % a.tiles_w;
+    int r = item / a.tiles_w;
+    const int th = r % a.tiles_h;
+    r /= a.tiles_h;
+    const int dc = r % a.dsplit;
+    it.b = r / a.dsplit;
+    it.d0 = dc * a.dlen;
+    it.d1 = min(a.D, it.d0 + a.dlen);
+    it.h0 = th * TH;
+    it.w0 = tw * TW;
+    return it;
+}
+
+// all MMAs of one input slice: 27 taps x 2 M-blocks x 2 k-steps (x 3 operand combinations)
+template <int PASSES>
+__device__ __forceinline__ void issue_slice_mmas(uint32_t tmem_base, int s, uint64_t a_desc, uint64_t lo_desc, uint64_t bhi_desc,
+                                                 uint64_t blo_desc) {
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+        const uint32_t slot = static_cast<uint32_t>(s + 1 - kd) & 3u;                // output slice s+1-kd
+#pragma unroll
+        for (int khw = 0; khw < 9; ++khw) {
+            const int kh = khw / 3, kw = khw - kh * 3, tap = kd * 9 + khw;
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) {
+                const uint32_t d_addr = tmem_base + (slot * 2u + mb) * 16u;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const uint64_t ao = static_cast<uint64_t>(((kh * HW + kw) * 64 + mb * 128 * 64 + ks * 32) >> 4);
+                    const uint64_t bo = static_cast<uint64_t>((tap * B_TAP_BYTES + ks * 32) >> 4);
+                    const uint32_t acc = (kd == 0 && khw == 0 && ks == 0) ? 0u : 1u;   // first MMA into a new output slice
+                    umma_tf32(d_addr, a_desc + ao, bhi_desc + bo, acc);
+                    if (PASSES == 3) {
+                        umma_tf32(d_addr, lo_desc + ao, bhi_desc + bo, 1u);
+                        umma_tf32(d_addr, a_desc + ao, blo_desc + bo, 1u);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int PASSES>
+__global__ void __launch_bounds__(THREADS, PASSES == 3 ? 1 : 2)
+conv3d_c16c16_tc_kernel(const __grid_constant__ CUtensorMap map_in, const TArgs a) {
+    using SM = Smem<PASSES>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
+    uint64_t* done = full + NBUF;                                // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + NBUF + 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const Item it = tc_item(a, blockIdx.x);
+    const int count = it.d1 - it.d0 + 2;
+
+    auto issue = [&](int i) {                                   // TMA load of x slice d0-1+i into ring buffer i % NBUF
+        uint64_t* bar = full + (i % NBUF);
+        mbar_expect_tx(bar, SLICE_POS * 64);
+        tma_load_5d(smem + SM::OFF_A + (i % NBUF) * SLICE_BYTES, &map_in, bar, 0, it.w0 - 1, it.h0 - 1, it.d0 - 1 + i, it.b);
+    };
+    if (tid == 0) {
+        tma_prefetch_desc(&map_in);
+        for (int i = 0; i < NBUF; ++i) mbar_init(full + i, 1);
+        mbar_init(done, 1);
+        mbar_init(done + 1, 1);
+        mbar_fence_init();
+        for (int i = 0; i < NBUF && i < count; ++i) issue(i);
+    }
+    if (warp == 0) {                                            // TMEM: 4 slots x 2 M-blocks x 16 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // filter bank as K-major SWIZZLE_64B tiles: element (n, k) of tap t at t*1024 + n*64 + ((k/4) ^ ((n>>1)&3))*16 + (k%4)*4
+    for (int e = tid; e < 27 * 256; e += THREADS) {
+        const int tap = e >> 8, n = (e >> 4) & 15, k = e & 15;
+        // forward: B[n=co][k=ci] = W[co][ci][tap];  data gradient: B[n=ci][k=co] = W[co][ci][26 - tap]
+        const float v = (a.mode == 0) ? __ldg(a.w + (n * 16 + k) * 27 + tap) : __ldg(a.w + (k * 16 + n) * 27 + (26 - tap));
+        const int off = tap * B_TAP_BYTES + n * 64 + (((k >> 2) ^ ((n >> 1) & 3)) << 4) + ((k & 3) << 2);
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        *reinterpret_cast<float*>(smem + SM::OFF_BHI + off) = (PASSES == 3) ? hi : v;
+        if (PASSES == 3) *reinterpret_cast<float*>(smem + SM::OFF_BLO + off) = v - hi;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the MMA's async proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint64_t bhi_desc = smem_desc(smem_u32(smem + SM::OFF_BHI)), blo_desc = smem_desc(smem_u32(smem + SM::OFF_BLO));
+
+    // epilogue of input slice j: output slice d = (d0-1+j) - 1 is complete (it received kd = 2 from slice j)
+    auto epilogue = [&](int j) {
+        const int d = it.d0 - 2 + j;
+        if (d < it.d0) return;
+        const uint32_t slot = static_cast<uint32_t>(d) & 3u;
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+            uint32_t r[16];
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + (slot * 2u + mb) * 16u;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int v = mb * 128 + tid, rr = v / HW, cc = v - rr * HW;
+            const int h = it.h0 + rr, w = it.w0 + cc;
+            if (rr < TH && cc < TW && h < a.H && w < a.W) {
+                uint4* op = reinterpret_cast<uint4*>(a.out + (((static_cast<size_t>(it.b) * a.D + d) * a.H + h) * a.W + w) * C);
+                op[0] = make_uint4(r[0], r[1], r[2], r[3]);
+                op[1] = make_uint4(r[4], r[5], r[6], r[7]);
+                op[2] = make_uint4(r[8], r[9], r[10], r[11]);
+                op[3] = make_uint4(r[12], r[13], r[14], r[15]);
+            }
+        }
+    };
+
+    // The MMAs of slice i run asynchronously while the four warps drain the accumulators finished by slice i-1.
+    for (int i = 0; i < count; ++i) {
+        const int s = it.d0 - 1 + i, bi = i % NBUF;
+        unsigned char* buf = smem + SM::OFF_A + bi * SLICE_BYTES;
+        unsigned char* lob = smem + SM::OFF_LO + (i & 1) * SLICE_BYTES;
+        mbar_wait(full + bi, (i / NBUF) & 1);
+        if (PASSES == 3) {                                       // split the slice: hi in place, lo into its own buffer
+            float4* hp = reinterpret_cast<float4*>(buf);
+            float4* lp = reinterpret_cast<float4*>(lob);
+            for (int e = tid; e < SLICE_POS * 4; e += THREADS) {
+                const float4 v = hp[e];
+                float4 h;
+                h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                hp[e] = h;
+                lp[e] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        tc_fence_before();
+        __syncthreads();                                         // slice i is ready; everyone is done with the epilogue of slice i-2
+        tc_fence_after();
+        if (tid == 0) {
+            issue_slice_mmas<PASSES>(tmem_base, s, smem_desc(smem_u32(buf)), smem_desc(smem_u32(lob)), bhi_desc, blo_desc);
+            umma_commit(done + (i & 1));                         // arrives when every MMA issued so far has completed
+        }
+        if (i >= 1) {
+            mbar_wait(done + ((i - 1) & 1), ((i - 1) >> 1) & 1);
+            tc_fence_after();
+            if (tid == 0 && i - 1 + NBUF < count) issue(i - 1 + NBUF);     // ring buffer of slice i-1 is free again
+            epilogue(i - 1);
+        }
+    }
+    mbar_wait(done + ((count - 1) & 1), ((count - 1) >> 1) & 1);
+    tc_fence_after();
+    epilogue(count - 1);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+}
+}  // namespace tc
+
 // ------------------------------------------------------------------------------------------ host
 static int plan(Args& a) {
     a.tiles_h = (a.H + TH - 1) / TH;
@@ -818,6 +1055,46 @@ int mvd_conv3d_c16c16_wgrad(const float* gy, const float* x, float* gw, void* wo
     if (int rc = mvd::check_launch("conv3d_c16c16_wgrad")) return rc;
     conv3d_c16c16_wgrad_reduce_kernel<<<(NW16 + 3) / 4, 128, 0, st>>>(a.part, gw, items);
     return mvd::check_launch("conv3d_c16c16_wgrad_reduce");
+}
+
+
+int mvd_conv3d_c16c16_tc(const float* in, const float* w, float* out, int B, int D, int H, int W, int mode, int passes,
+                         int flags, void* stream) {
+    using namespace mvd::c16;
+    MVD_REQUIRE(in && w && out, "null pointer argument");
+    if (int rc = check_shape(B, D, H, W)) return rc;
+    MVD_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (forward) or 1 (data gradient), got %d", mode);
+    MVD_REQUIRE(passes == 1 || passes == 3, "passes must be 1 (TF32) or 3 (3xTF32), got %d", passes);
+    MVD_REQUIRE(mvd::aligned16(in) && mvd::aligned16(out), "activation pointers must be 16-byte aligned");
+    cudaStream_t st = mvd::as_stream(stream);
+    tc::TArgs a{};
+    a.w = w; a.out = out; a.mode = mode; a.B = B; a.D = D; a.H = H; a.W = W;
+    (void)flags;
+    a.tiles_h = (H + tc::TH - 1) / tc::TH;
+    a.tiles_w = (W + tc::TW - 1) / tc::TW;
+    const int base = B * a.tiles_h * a.tiles_w, slots = mvd::sm_count();
+    int ds = 1;
+    while (base * ds < 4 * slots && D / (ds + 1) >= 8) ++ds;
+    a.dlen = (D + ds - 1) / ds;
+    a.dsplit = (D + a.dlen - 1) / a.dlen;
+    const int items = base * a.dsplit;
+    CUtensorMap map;
+    {
+        const uint64_t Wd = W, Hd = H, Dd = D;
+        const uint64_t dims[5] = {C, Wd, Hd, Dd, static_cast<uint64_t>(B)};
+        const uint64_t str[4] = {C * 4, Wd * C * 4, Wd * Hd * C * 4, Wd * Hd * Dd * C * 4};
+        const uint32_t box[5] = {C, tc::HW, tc::HH, 1, 1};
+        if (int rc = mvd::make_f32_tensor_map(&map, in, 5, dims, str, box, 64)) return rc;
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(tc::conv3d_c16c16_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<1>::ALLOC);
+        cudaFuncSetAttribute(tc::conv3d_c16c16_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<3>::ALLOC);
+        attr_done = true;
+    }
+    if (passes == 3) tc::conv3d_c16c16_tc_kernel<3><<<items, tc::THREADS, tc::Smem<3>::ALLOC, st>>>(map, a);
+    else tc::conv3d_c16c16_tc_kernel<1><<<items, tc::THREADS, tc::Smem<1>::ALLOC, st>>>(map, a);
+    return mvd::check_launch("conv3d_c16c16_tc");
 }
 
 }

@@ -294,6 +294,19 @@ def c16c16_conv(inp, weight, mode, passes):
     return out
 
 
+def c16c16_conv_tc(inp, weight, mode, passes, flags=0):
+    """Same contract as c16c16_conv on tcgen05 / TMEM (csrc/conv3d_c16.cu, namespace tc)."""
+    B, C, D, H, W = inp.shape
+    assert C == 16 and tuple(weight.shape) == (16, 16, 3, 3, 3), (inp.shape, weight.shape)
+    inp = _f32(inp).contiguous(memory_format=torch.channels_last_3d)
+    w = _f32(weight).contiguous()
+    out = torch.empty_like(inp)
+    rc = _lib.lib().mvd_conv3d_c16c16_tc(_p(inp), _p(w), _p(out), B, D, H, W, mode, passes, flags, _stream())
+    _lib.check(rc, "mvd_conv3d_c16c16_tc")
+    launch_counter["n"] += 1
+    return out
+
+
 def c16c16_wgrad(gy, x):
     """Exact-fp32 weight gradient [16,16,3,3,3] of the 16->16 layer; gy, x logical [B,16,D,H,W] channels-last-3d."""
     B, C, D, H, W = x.shape
@@ -318,7 +331,7 @@ class _Conv3dC16C16(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
-        gx = c16c16_conv(gy, w, 1, 1) if ctx.needs_input_grad[0] else None      # single-pass TF32 data gradient
+        gx = c16c16_conv_tc(gy, w, 1, 1) if ctx.needs_input_grad[0] else None   # single-pass TF32 data gradient (tcgen05)
         gw = c16c16_wgrad(gy, x) if ctx.needs_input_grad[1] else None           # exact fp32 weight gradient
         return gx, gw, None
 

@@ -523,3 +523,23 @@ def test_sync_batchnorm_statistics_are_exchanged_across_ranks():
         torch.testing.assert_close(gxr, x.grad[r * 2:r * 2 + 2].float(), atol=1e-4, rtol=1e-4)
         torch.testing.assert_close(rvr, bn.running_var.float(), atol=1e-5, rtol=1e-5)
     torch.testing.assert_close(got[0][2] + got[1][2], bn.weight.grad.float(), atol=1e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("shape", [(1, 6, 7, 32), (1, 5, 11, 45), (2, 26, 24, 80)], ids=["aligned", "ragged", "multi-tile"])
+def test_conv3d_16_to_16_tcgen05_matches_torch_conv3d(ops, shape):
+    """The tcgen05 / TMEM version of the 16->16 layer (every tap = the TMA-staged slice at a shifted descriptor start
+    address) vs torch's CPU conv3d in fp64: 3xTF32 forward and data gradient within 2e-5 of the output scale, single-pass
+    TF32 (operands truncated to 10 mantissa bits by the tensor core) within 3e-3."""
+    import torch.nn.functional as F
+    B, D, H, W = shape
+    gen = torch.Generator().manual_seed(4)
+    x = torch.randn(B, 16, D, H, W, generator=gen)
+    w = torch.randn(16, 16, 3, 3, 3, generator=gen) * 0.1
+    yo = F.conv3d(x.double(), w.double(), padding=1).float()
+    go = torch.nn.grad.conv3d_input(x.shape, w.double(), x.double(), padding=1).float()      # data gradient with gy := x
+    xg, wg = g(x).contiguous(memory_format=torch.channels_last_3d), g(w)
+    for passes, tol in ((3, 2e-5), (1, 3e-3)):
+        y = ops.c16c16_conv_tc(xg, wg, 0, passes)
+        torch.testing.assert_close(y.cpu(), yo, atol=tol * float(yo.abs().max()), rtol=0)
+        gx = ops.c16c16_conv_tc(xg, wg, 1, passes)
+        torch.testing.assert_close(gx.cpu(), go, atol=tol * float(go.abs().max()), rtol=0)
