@@ -638,37 +638,46 @@ static_assert(WG_GROUPS * NW16 * 4 <= WG_XBUF * SLICE_BYTES + WG_GBUF * GY_BYTES
 
 // ================================================================================================
 // The 16 -> 16 layer on the 5th-generation tensor cores: tcgen05.mma (kind::tf32) with TMEM accumulators.
-//   D[128 positions x 16 out-ch] += A_tap[128 x 16 in-ch] * B_tap[16 x 16]   for the 27 taps
+//   D[128 positions x N] += A[128 x 16 in-ch] * B[16 x N]
 // * The input slice of a 7x32 tile (+halo = 9x34 positions x 64 B) is TMA-loaded with the 64B swizzle.  Output
-//   positions are flattened with the halo pitch, v = r*34 + c, so that EVERY tap's A operand is the same shared
-//   memory tile at a start address shifted by (kh*34 + kw) rows -- a K-major SWIZZLE_64B canonical layout (rows 64 B
-//   apart, 8-row groups 512 B apart); the two garbage columns per row are computed and dropped (2 M-blocks of 128
-//   rows cover the 238 flattened positions).
-// * Slice marching as before: input slice s adds tap kd to output slice s+1-kd; four TMEM accumulator slots
-//   (slot = output slice & 3) x 2 M-blocks x 16 columns = 128 TMEM columns.
-// * 3xTF32: the slice is split in place into hi = x & ~0x1fff and lo = x - hi (second buffer); the filter bank is
-//   kept as hi / lo K-major tiles; D += hi*hi + lo*hi + hi*lo.  passes == 1: plain TF32 (data gradient).
-// * One thread issues the MMAs (54 or 162 per slice and M-block), tcgen05.commit signals an mbarrier, the four warps
-//   read their TMEM lane quadrant with tcgen05.ld (one position = 16 channels = 64 B per thread) and store it.
+//   positions are flattened with the halo pitch, v = r*34 + c, so that EVERY (kh,kw) tap's A operand is the same
+//   shared-memory tile at a start address shifted by (kh*34 + kw) rows -- a K-major SWIZZLE_64B canonical layout (rows
+//   64 B apart, 8-row groups 512 B apart); the two garbage columns per row are computed and dropped (2 M-blocks of
+//   128 rows cover the 238 flattened positions).
+// * Slice marching: input slice s adds tap kd to output slice s+1-kd.  With N = 16 an MMA is bound by the shared-memory
+//   read of its A operand (4 KB per 8 tensor cycles), so the three kd taps -- same A, different filters, different
+//   output slices -- are folded into ONE MMA of N = 48: the filter bank is stored per (kh,kw) as 48 K-major rows
+//   [kd][out-ch], and the accumulators of consecutive output slices sit in consecutive TMEM column groups of a ring of
+//   four (slice d -> group (-d) & 3), so slices s+1, s, s-1 are a contiguous column range (split in two MMAs when the
+//   range wraps).  Every MMA accumulates; a group is zeroed (tcgen05.st) right after the epilogue drained it.
+// * 3xTF32 (forward): the slice is split in place into hi = x & ~0x1fff and lo = x - hi (own buffer).  A_hi meets the
+//   interleaved bank [kd][hi|lo][out-ch] (N = 96: hi*hi and hi*lo land in adjacent 16-column halves of a 32-column
+//   group), A_lo meets the hi bank (N = 48, second ring); the epilogue adds the three partial sums.  A is read from
+//   shared memory twice per (kh,kw) instead of nine times.
+// * One thread issues the MMAs; tcgen05.commit signals an mbarrier; the four warps drain their TMEM lane quadrant with
+//   tcgen05.ld (one position = 16 channels = 64 B per thread) while the MMAs of the next slice run.
 namespace tc {
 constexpr int TH = 7, TW = 32, HH = TH + 2, HW = TW + 2;     // 9 x 34 halo tile
 constexpr int SLICE_POS = HH * HW;                            // 306 positions written by TMA
 constexpr int SLICE_BYTES = 21504;                            // >= (255 + 2*34 + 2 + 1) * 64 = 20864, multiple of 512
 constexpr int NBUF = 3;
 constexpr int THREADS = 128;
-constexpr int B_TAP_BYTES = 1024;                             // 16 rows x 64 B
-constexpr int B_BYTES = 27 * B_TAP_BYTES;
-constexpr uint32_t TMEM_COLS = 128;
+constexpr int BH_KHW_BYTES = 48 * 64;                         // hi bank per (kh,kw): rows [kd][n]
+constexpr int BI_KHW_BYTES = 96 * 64;                         // interleaved bank per (kh,kw): rows [kd][hi|lo][n]
 
 template <int PASSES>
-struct Smem {
+struct Cfg {
     static constexpr int OFF_A = 0;
     static constexpr int OFF_LO = OFF_A + NBUF * SLICE_BYTES;                        // [2] lo halves of the slice (3xTF32 only)
-    static constexpr int OFF_BHI = OFF_LO + (PASSES == 3 ? 2 * SLICE_BYTES : 0);
-    static constexpr int OFF_BLO = OFF_BHI + B_BYTES;
-    static constexpr int OFF_BAR = OFF_BLO + (PASSES == 3 ? B_BYTES : 0);            // full[NBUF], done[2], tmem base
+    static constexpr int OFF_BH = OFF_LO + (PASSES == 3 ? 2 * SLICE_BYTES : 0);      // hi bank (raw fp32 when PASSES == 1)
+    static constexpr int OFF_BI = OFF_BH + 9 * BH_KHW_BYTES;                         // interleaved hi|lo bank (3xTF32 only)
+    static constexpr int OFF_BAR = OFF_BI + (PASSES == 3 ? 9 * BI_KHW_BYTES : 0);    // full[NBUF], done[2], tmem base
     static constexpr int TOTAL = OFF_BAR + 64;
     static constexpr int ALLOC = TOTAL + 1024;
+    // TMEM columns per M-block: ring 1 (4 groups of GW1 columns), ring 2 (4 groups of 16; 3xTF32 only)
+    static constexpr uint32_t GW1 = PASSES == 3 ? 32 : 16;
+    static constexpr uint32_t MB_COLS = 4 * GW1 + (PASSES == 3 ? 64 : 0);
+    static constexpr uint32_t TMEM_COLS = PASSES == 3 ? 512 : 128;
 };
 
 // K-major, SWIZZLE_64B shared-memory matrix descriptor: LBO = 1 (16 B units, unused for swizzled K-major), SBO = 512 B
@@ -684,28 +693,55 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
     d |= static_cast<uint64_t>(4) << 61;
     return d;
 }
-// instruction descriptor: D = F32, A = B = TF32, both K-major, N = 16, M = 128
-constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((16u >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor: D = F32, A = B = TF32, both K-major, M = 128, N = n
+__device__ __forceinline__ constexpr uint32_t idesc(uint32_t n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t id) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 p, 1, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(id)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// one lane of a fully converged warp; code dominated by this predicate is single-threaded, so the compiler can keep
+// descriptors / TMEM addresses in uniform registers instead of wrapping every UTCHMMA in an ELECT + R2UR.BROADCAST loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "@P mov.u32 %0, 1;\n\t"
+        "}\n"
+        : "+r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
+    const uint32_t z = 0u;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z)
+                 : "memory");
+}
 
 struct TArgs {
     const float* w;
     float* out;
-    int mode;
+    int mode, dbg;
     int B, D, H, W;
     int tiles_h, tiles_w, dsplit, dlen;
 };
@@ -725,29 +761,29 @@ __device__ __forceinline__ Item tc_item(const TArgs& a, int item) {
     return it;
 }
 
-// all MMAs of one input slice: 27 taps x 2 M-blocks x 2 k-steps (x 3 operand combinations)
-template <int PASSES>
-__device__ __forceinline__ void issue_slice_mmas(uint32_t tmem_base, int s, uint64_t a_desc, uint64_t lo_desc, uint64_t bhi_desc,
-                                                 uint64_t blo_desc) {
+// MMAs of one input slice for the kd range [KD0, KD0 + NKD) landing in ring group G (a contiguous TMEM column range)
+template <int PASSES, int KD0, int NKD, int G>
+__device__ __forceinline__ void issue_part(uint32_t tmem_base, uint64_t a_desc, uint64_t lo_desc, uint64_t bh_desc, uint64_t bi_desc,
+                                           int warp) {
+    using CF = Cfg<PASSES>;
 #pragma unroll
-    for (int kd = 0; kd < 3; ++kd) {
-        const uint32_t slot = static_cast<uint32_t>(s + 1 - kd) & 3u;                // output slice s+1-kd
+    for (int khw = 0; khw < 9; ++khw) {
+        if ((khw * 4) / 9 != warp) continue;                     // the (kh,kw) taps are dealt to the four issuing warps
+        const int kh = khw / 3, kw = khw - kh * 3;
 #pragma unroll
-        for (int khw = 0; khw < 9; ++khw) {
-            const int kh = khw / 3, kw = khw - kh * 3, tap = kd * 9 + khw;
+        for (int mb = 0; mb < 2; ++mb) {
 #pragma unroll
-            for (int mb = 0; mb < 2; ++mb) {
-                const uint32_t d_addr = tmem_base + (slot * 2u + mb) * 16u;
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                    const uint64_t ao = static_cast<uint64_t>(((kh * HW + kw) * 64 + mb * 128 * 64 + ks * 32) >> 4);
-                    const uint64_t bo = static_cast<uint64_t>((tap * B_TAP_BYTES + ks * 32) >> 4);
-                    const uint32_t acc = (kd == 0 && khw == 0 && ks == 0) ? 0u : 1u;   // first MMA into a new output slice
-                    umma_tf32(d_addr, a_desc + ao, bhi_desc + bo, acc);
-                    if (PASSES == 3) {
-                        umma_tf32(d_addr, lo_desc + ao, bhi_desc + bo, 1u);
-                        umma_tf32(d_addr, a_desc + ao, blo_desc + bo, 1u);
-                    }
+            for (int ks = 0; ks < 2; ++ks) {
+                const uint64_t ao = static_cast<uint64_t>(((kh * HW + kw) * 64 + mb * 128 * 64 + ks * 32) >> 4);
+                const uint32_t d1 = tmem_base + mb * CF::MB_COLS + G * CF::GW1;
+                if (PASSES == 3) {
+                    const uint64_t bio = static_cast<uint64_t>((khw * BI_KHW_BYTES + KD0 * 32 * 64 + ks * 32) >> 4);
+                    const uint64_t bho = static_cast<uint64_t>((khw * BH_KHW_BYTES + KD0 * 16 * 64 + ks * 32) >> 4);
+                    umma_tf32(d1, a_desc + ao, bi_desc + bio, idesc(32 * NKD));                    // hi * [hi | lo]
+                    umma_tf32(tmem_base + mb * CF::MB_COLS + 4 * CF::GW1 + G * 16, lo_desc + ao, bh_desc + bho, idesc(16 * NKD));   // lo * hi
+                } else {
+                    const uint64_t bho = static_cast<uint64_t>((khw * BH_KHW_BYTES + KD0 * 16 * 64 + ks * 32) >> 4);
+                    umma_tf32(d1, a_desc + ao, bh_desc + bho, idesc(16 * NKD));
                 }
             }
         }
@@ -757,10 +793,10 @@ __device__ __forceinline__ void issue_slice_mmas(uint32_t tmem_base, int s, uint
 template <int PASSES>
 __global__ void __launch_bounds__(THREADS, PASSES == 3 ? 1 : 2)
 conv3d_c16c16_tc_kernel(const __grid_constant__ CUtensorMap map_in, const TArgs a) {
-    using SM = Smem<PASSES>;
+    using CF = Cfg<PASSES>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::OFF_BAR);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + CF::OFF_BAR);
     uint64_t* done = full + NBUF;                                // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + NBUF + 2);
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -770,72 +806,97 @@ conv3d_c16c16_tc_kernel(const __grid_constant__ CUtensorMap map_in, const TArgs 
     auto issue = [&](int i) {                                   // TMA load of x slice d0-1+i into ring buffer i % NBUF
         uint64_t* bar = full + (i % NBUF);
         mbar_expect_tx(bar, SLICE_POS * 64);
-        tma_load_5d(smem + SM::OFF_A + (i % NBUF) * SLICE_BYTES, &map_in, bar, 0, it.w0 - 1, it.h0 - 1, it.d0 - 1 + i, it.b);
+        tma_load_5d(smem + CF::OFF_A + (i % NBUF) * SLICE_BYTES, &map_in, bar, 0, it.w0 - 1, it.h0 - 1, it.d0 - 1 + i, it.b);
     };
     if (tid == 0) {
         tma_prefetch_desc(&map_in);
         for (int i = 0; i < NBUF; ++i) mbar_init(full + i, 1);
-        mbar_init(done, 1);
-        mbar_init(done + 1, 1);
+        mbar_init(done, THREADS / 32);                          // one commit per issuing warp
+        mbar_init(done + 1, THREADS / 32);
         mbar_fence_init();
         for (int i = 0; i < NBUF && i < count; ++i) issue(i);
     }
-    if (warp == 0) {                                            // TMEM: 4 slots x 2 M-blocks x 16 columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS)
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(CF::TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // filter bank as K-major SWIZZLE_64B tiles: element (n, k) of tap t at t*1024 + n*64 + ((k/4) ^ ((n>>1)&3))*16 + (k%4)*4
+    // filter banks, K-major SWIZZLE_64B: row r, k -> r*64 + ((k/4) ^ ((r>>1)&3))*16 + (k%4)*4 (bank bases are 512 B aligned)
     for (int e = tid; e < 27 * 256; e += THREADS) {
         const int tap = e >> 8, n = (e >> 4) & 15, k = e & 15;
+        const int kd = tap / 9, khw = tap - kd * 9;
         // forward: B[n=co][k=ci] = W[co][ci][tap];  data gradient: B[n=ci][k=co] = W[co][ci][26 - tap]
         const float v = (a.mode == 0) ? __ldg(a.w + (n * 16 + k) * 27 + tap) : __ldg(a.w + (k * 16 + n) * 27 + (26 - tap));
-        const int off = tap * B_TAP_BYTES + n * 64 + (((k >> 2) ^ ((n >> 1) & 3)) << 4) + ((k & 3) << 2);
         const float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-        *reinterpret_cast<float*>(smem + SM::OFF_BHI + off) = (PASSES == 3) ? hi : v;
-        if (PASSES == 3) *reinterpret_cast<float*>(smem + SM::OFF_BLO + off) = v - hi;
+        auto put = [&](int base, int row, float val) {
+            *reinterpret_cast<float*>(smem + base + row * 64 + (((k >> 2) ^ ((row >> 1) & 3)) << 4) + ((k & 3) << 2)) = val;
+        };
+        put(CF::OFF_BH + khw * BH_KHW_BYTES, kd * 16 + n, PASSES == 3 ? hi : v);
+        if (PASSES == 3) {
+            put(CF::OFF_BI + khw * BI_KHW_BYTES, kd * 32 + n, hi);
+            put(CF::OFF_BI + khw * BI_KHW_BYTES, kd * 32 + 16 + n, v - hi);
+        }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic-proxy writes -> visible to the MMA's async proxy
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint64_t bhi_desc = smem_desc(smem_u32(smem + SM::OFF_BHI)), blo_desc = smem_desc(smem_u32(smem + SM::OFF_BLO));
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    for (uint32_t c = 0; c < 2 * CF::MB_COLS; c += 16) tmem_zero16(lane_addr + c);   // every MMA accumulates
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    const uint64_t bh_desc = smem_desc(smem_u32(smem + CF::OFF_BH)), bi_desc = smem_desc(smem_u32(smem + CF::OFF_BI));
 
     // epilogue of input slice j: output slice d = (d0-1+j) - 1 is complete (it received kd = 2 from slice j)
     auto epilogue = [&](int j) {
         const int d = it.d0 - 2 + j;
-        if (d < it.d0) return;
-        const uint32_t slot = static_cast<uint32_t>(d) & 3u;
+        const uint32_t grp = static_cast<uint32_t>(-d) & 3u;
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb) {
-            uint32_t r[16];
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + (slot * 2u + mb) * 16u;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int v = mb * 128 + tid, rr = v / HW, cc = v - rr * HW;
-            const int h = it.h0 + rr, w = it.w0 + cc;
-            if (rr < TH && cc < TW && h < a.H && w < a.W) {
-                uint4* op = reinterpret_cast<uint4*>(a.out + (((static_cast<size_t>(it.b) * a.D + d) * a.H + h) * a.W + w) * C);
-                op[0] = make_uint4(r[0], r[1], r[2], r[3]);
-                op[1] = make_uint4(r[4], r[5], r[6], r[7]);
-                op[2] = make_uint4(r[8], r[9], r[10], r[11]);
-                op[3] = make_uint4(r[12], r[13], r[14], r[15]);
+            const uint32_t t1 = lane_addr + mb * CF::MB_COLS + grp * CF::GW1;
+            const uint32_t t2 = lane_addr + mb * CF::MB_COLS + 4 * CF::GW1 + grp * 16;
+            if (d >= it.d0) {
+                uint32_t r[16];
+                tmem_ld16(t1, r);
+                float o[16];
+                if (PASSES == 3) {
+                    uint32_t r2[16], r3[16];
+                    tmem_ld16(t1 + 16, r2);
+                    tmem_ld16(t2, r3);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) o[q] = __uint_as_float(r[q]) + (__uint_as_float(r2[q]) + __uint_as_float(r3[q]));
+                } else {
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) o[q] = __uint_as_float(r[q]);
+                }
+                const int v = mb * 128 + tid, rr = v / HW, cc = v - rr * HW;
+                const int h = it.h0 + rr, w = it.w0 + cc;
+                if (rr < TH && cc < TW && h < a.H && w < a.W && !(a.dbg & 4)) {
+                    float4* op = reinterpret_cast<float4*>(a.out + (((static_cast<size_t>(it.b) * a.D + d) * a.H + h) * a.W + w) * C);
+                    op[0] = make_float4(o[0], o[1], o[2], o[3]);
+                    op[1] = make_float4(o[4], o[5], o[6], o[7]);
+                    op[2] = make_float4(o[8], o[9], o[10], o[11]);
+                    op[3] = make_float4(o[12], o[13], o[14], o[15]);
+                }
+            }
+            tmem_zero16(t1);                                     // the group is the fresh accumulator of output slice d + 4
+            if (PASSES == 3) {
+                tmem_zero16(t1 + 16);
+                tmem_zero16(t2);
             }
         }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     };
 
     // The MMAs of slice i run asynchronously while the four warps drain the accumulators finished by slice i-1.
     for (int i = 0; i < count; ++i) {
         const int s = it.d0 - 1 + i, bi = i % NBUF;
-        unsigned char* buf = smem + SM::OFF_A + bi * SLICE_BYTES;
-        unsigned char* lob = smem + SM::OFF_LO + (i & 1) * SLICE_BYTES;
+        unsigned char* buf = smem + CF::OFF_A + bi * SLICE_BYTES;
+        unsigned char* lob = smem + CF::OFF_LO + (i & 1) * SLICE_BYTES;
         mbar_wait(full + bi, (i / NBUF) & 1);
-        if (PASSES == 3) {                                       // split the slice: hi in place, lo into its own buffer
+        if (PASSES == 3 && !(a.dbg & 8)) {                       // split the slice: hi in place, lo into its own buffer
             float4* hp = reinterpret_cast<float4*>(buf);
             float4* lp = reinterpret_cast<float4*>(lob);
             for (int e = tid; e < SLICE_POS * 4; e += THREADS) {
@@ -853,9 +914,23 @@ conv3d_c16c16_tc_kernel(const __grid_constant__ CUtensorMap map_in, const TArgs 
         tc_fence_before();
         __syncthreads();                                         // slice i is ready; everyone is done with the epilogue of slice i-2
         tc_fence_after();
-        if (tid == 0) {
-            issue_slice_mmas<PASSES>(tmem_base, s, smem_desc(smem_u32(buf)), smem_desc(smem_u32(lob)), bhi_desc, blo_desc);
-            umma_commit(done + (i & 1));                         // arrives when every MMA issued so far has completed
+        if (elect_one()) {                                       // one lane per warp issues its share of the taps
+            const uint64_t ad = smem_desc(smem_u32(buf)), ld = smem_desc(smem_u32(lob));
+            // output slices s+1, s, s-1 (kd = 0,1,2) live in ring groups g0, g0+1, g0+2 (mod 4), g0 = (-(s+1)) & 3
+            switch ((a.dbg & 2) ? 99u : (static_cast<uint32_t>(-(s + 1)) & 3u)) {
+                case 99: break;
+                case 0: issue_part<PASSES, 0, 3, 0>(tmem_base, ad, ld, bh_desc, bi_desc, warp); break;
+                case 1: issue_part<PASSES, 0, 3, 1>(tmem_base, ad, ld, bh_desc, bi_desc, warp); break;
+                case 2:
+                    issue_part<PASSES, 0, 2, 2>(tmem_base, ad, ld, bh_desc, bi_desc, warp);
+                    issue_part<PASSES, 2, 1, 0>(tmem_base, ad, ld, bh_desc, bi_desc, warp);
+                    break;
+                default:
+                    issue_part<PASSES, 0, 1, 3>(tmem_base, ad, ld, bh_desc, bi_desc, warp);
+                    issue_part<PASSES, 1, 2, 0>(tmem_base, ad, ld, bh_desc, bi_desc, warp);
+                    break;
+            }
+            umma_commit(done + (i & 1));                         // arrives when every MMA this thread issued has completed
         }
         if (i >= 1) {
             mbar_wait(done + ((i - 1) & 1), ((i - 1) >> 1) & 1);
@@ -869,7 +944,7 @@ conv3d_c16c16_tc_kernel(const __grid_constant__ CUtensorMap map_in, const TArgs 
     epilogue(count - 1);
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(CF::TMEM_COLS) : "memory");
 }
 }  // namespace tc
 
@@ -1069,13 +1144,23 @@ int mvd_conv3d_c16c16_tc(const float* in, const float* w, float* out, int B, int
     cudaStream_t st = mvd::as_stream(stream);
     tc::TArgs a{};
     a.w = w; a.out = out; a.mode = mode; a.B = B; a.D = D; a.H = H; a.W = W;
-    (void)flags;
     a.tiles_h = (H + tc::TH - 1) / tc::TH;
     a.tiles_w = (W + tc::TW - 1) / tc::TW;
-    const int base = B * a.tiles_h * a.tiles_w, slots = mvd::sm_count();
-    int ds = 1;
-    while (base * ds < 4 * slots && D / (ds + 1) >= 8) ++ds;
-    a.dlen = (D + ds - 1) / ds;
+    a.dbg = flags;
+    // split the depth axis so that the work items fill whole waves of resident CTAs (each chunk re-reads 2 halo slices)
+    const int base = B * a.tiles_h * a.tiles_w, slots = mvd::sm_count() * (passes == 3 ? 1 : 2);
+    int best = 1;
+    double best_eff = 0.0;
+    for (int ds = 1; ds <= 16 && D / ds >= 8; ++ds) {
+        const int dlen = (D + ds - 1) / ds, items = base * ((D + dlen - 1) / dlen);
+        const double waves = static_cast<double>(items) / slots;
+        const double eff = waves / static_cast<double>((items + slots - 1) / slots) * dlen / (dlen + 2.0);
+        if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best = ds;
+        }
+    }
+    a.dlen = (D + best - 1) / best;
     a.dsplit = (D + a.dlen - 1) / a.dlen;
     const int items = base * a.dsplit;
     CUtensorMap map;
@@ -1088,12 +1173,12 @@ int mvd_conv3d_c16c16_tc(const float* in, const float* w, float* out, int B, int
     }
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(tc::conv3d_c16c16_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<1>::ALLOC);
-        cudaFuncSetAttribute(tc::conv3d_c16c16_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Smem<3>::ALLOC);
+        cudaFuncSetAttribute(tc::conv3d_c16c16_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<1>::ALLOC);
+        cudaFuncSetAttribute(tc::conv3d_c16c16_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<3>::ALLOC);
         attr_done = true;
     }
-    if (passes == 3) tc::conv3d_c16c16_tc_kernel<3><<<items, tc::THREADS, tc::Smem<3>::ALLOC, st>>>(map, a);
-    else tc::conv3d_c16c16_tc_kernel<1><<<items, tc::THREADS, tc::Smem<1>::ALLOC, st>>>(map, a);
+    if (passes == 3) tc::conv3d_c16c16_tc_kernel<3><<<items, tc::THREADS, tc::Cfg<3>::ALLOC, st>>>(map, a);
+    else tc::conv3d_c16c16_tc_kernel<1><<<items, tc::THREADS, tc::Cfg<1>::ALLOC, st>>>(map, a);
     return mvd::check_launch("conv3d_c16c16_tc");
 }
 

@@ -324,8 +324,8 @@ def c16c16_wgrad(gy, x):
 class _Conv3dC16C16(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, passes):
-        y = c16c16_conv(x, weight, 0, passes)
-        ctx.save_for_backward(x, weight)
+        y = c16c16_conv_tc(x, weight, 0, passes)                                # tcgen05 / TMEM implicit GEMM
+        ctx.save_for_backward(x.contiguous(memory_format=torch.channels_last_3d), weight)
         return y
 
     @staticmethod
@@ -338,8 +338,8 @@ class _Conv3dC16C16(torch.autograd.Function):
 
 def conv3d_c16_to_16(x, weight, passes=3):
     """Conv3d(16 -> 16, k=3, stride 1, padding 1, no bias) on a channels-last-3d volume, all three passes hand-written:
-    tensor-core implicit GEMM forward (3xTF32 split with passes=3, plain TF32 with passes=1), TF32 data gradient,
-    exact-fp32 weight gradient.  Reference: reg3d.conv0.conv, movedepth/networks/resnet_encoder.py:178, 231."""
+    tcgen05/TMEM implicit GEMM forward (3xTF32 split with passes=3, plain TF32 with passes=1) and TF32 data gradient,
+    exact-fp32 FFMA2 weight gradient.  Reference: reg3d.conv0.conv, movedepth/networks/resnet_encoder.py:178, 231."""
     return _Conv3dC16C16.apply(x, weight, passes)
 
 

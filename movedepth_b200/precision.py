@@ -140,6 +140,10 @@ class _PolicyMixin:
                 or any(d != 1 for d in _tup(self.dilation, x.dim() - 2)):
             return super().forward(x)
         nd = x.dim() - 2
+        if (nd == 3 and not self._transposed and x.is_cuda and self.bias is None and tuple(self.weight.shape) == (16, 16, 3, 3, 3)
+                and _tup(self.stride, 3) == (1, 1, 1) and _tup(self.padding, 3) == (1, 1, 1) and not _policy["split_backward"]):
+            from . import ops                 # reg3d's full-resolution 16->16 layer: hand-written tcgen05 implicit GEMM
+            return ops.conv3d_c16_to_16(x, self.weight, 3)
         y = _SplitConv.apply(x, self.weight, _tup(self.stride, nd), _tup(self.padding, nd),
                              _tup(getattr(self, "output_padding", 0), nd), self._transposed)
         if self.bias is not None:

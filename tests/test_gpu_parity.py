@@ -419,10 +419,12 @@ def test_conv3d_16_to_16_matches_torch_conv3d(ops, shape):
     y3 = ops.conv3d_c16_to_16(xg, wg, 3)
     torch.testing.assert_close(y3.detach().cpu(), yo, atol=2e-5 * float(yo.abs().max()), rtol=0)
     y1 = ops.conv3d_c16_to_16(xg, wg, 1)
-    torch.testing.assert_close(y1.detach().cpu(), yo, atol=2e-3 * float(yo.abs().max()), rtol=0)
+    torch.testing.assert_close(y1.detach().cpu(), yo, atol=3e-3 * float(yo.abs().max()), rtol=0)
+    ym = ops.c16c16_conv(xg, wg, 0, 3)                                     # the mma.sync variant of the same contract
+    torch.testing.assert_close(ym.cpu(), yo, atol=2e-5 * float(yo.abs().max()), rtol=0)
     (y3 * g(gy)).sum().backward()
     gxo = xo.grad.float()
-    torch.testing.assert_close(xg.grad.cpu(), gxo, atol=2e-3 * float(gxo.abs().max()), rtol=0)
+    torch.testing.assert_close(xg.grad.cpu(), gxo, atol=3e-3 * float(gxo.abs().max()), rtol=0)
     gwo = None
     wo = w.double().requires_grad_(True)
     (F.conv3d(x.double(), wo, padding=1) * gy.double()).sum().backward()

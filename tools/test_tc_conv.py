@@ -35,8 +35,12 @@ def main():
     x = torch.randn(6, 16, 96, 48, 160, device=dev).contiguous(memory_format=torch.channels_last_3d)
     w = torch.randn(16, 16, 3, 3, 3, device=dev) * 0.1
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for name, fn in (("tc 3-pass", lambda: ops.c16c16_conv_tc(x, w, 0, 3)), ("tc 1-pass", lambda: ops.c16c16_conv_tc(x, w, 1, 1)),
-                     ("mma.sync 1-pass", lambda: ops.c16c16_conv(x, w, 1, 1))):
+    cases = [("tc 3-pass", lambda: ops.c16c16_conv_tc(x, w, 0, 3)), ("tc 1-pass", lambda: ops.c16c16_conv_tc(x, w, 1, 1)),
+             ("mma.sync 1-pass", lambda: ops.c16c16_conv(x, w, 1, 1))]
+    for dbg, nm in ((2, "no MMA"), (4, "no stores"), (8, "no split"), (14, "TMA + sync only")):
+        cases.append(("tc 3-pass dbg %s" % nm, lambda dbg=dbg: ops.c16c16_conv_tc(x, w, 0, 3, dbg)))
+        cases.append(("tc 1-pass dbg %s" % nm, lambda dbg=dbg: ops.c16c16_conv_tc(x, w, 1, 1, dbg)))
+    for name, fn in cases:
         ts = []
         for i in range(8):
             flush.fill_(i & 1)
