@@ -226,7 +226,10 @@ def run_own(args):
                    "parallelism": "dp%d, flat-arena gradient all-reduce over NCCL" % world},
         "roofline": {"kernel": "costvol_grouped_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / pk["hbm_gbs"], "traffic": args.traffic, "peak_source": pk_src,
-                     "algorithmic_bytes": costvol_bytes(BATCH), "avg_launch_us": cv_ms * 1e3, "launches_timed": len(cv)},
+                     "algorithmic_bytes": costvol_bytes(BATCH), "avg_launch_us": cv_ms * 1e3, "launches_timed": len(cv),
+                     "launch_us_min_median_max": [min(cv) * 1e3, statistics.median(cv) * 1e3, max(cv) * 1e3],
+                     "note": "timed inside the training step on the features / prior / pose the networks produce at that step; "
+                             "long epipolar footprints (large predicted translation) take the kernel's global-gather route"},
         "clocks": sampler.summary(),
         "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},

@@ -180,6 +180,11 @@ int mvd_conv3d_c16c16(const float* in, const float* w, float* out, int B, int D,
  * A operand = the TMA-staged slice at a shifted start address.  flags: reserved, pass 0. */
 int mvd_conv3d_c16c16_tc(const float* in, const float* w, float* out, int B, int D, int H, int W,
                          int mode, int passes, int flags, void* stream);
+/* Weight gradient on tcgen05 (single-pass TF32; MN-major operands, the four M-groups of A are the x slice shifted by
+ * kw positions); same workspace / reduction scheme as mvd_conv3d_c16c16_wgrad. */
+long long mvd_conv3d_c16c16_wgrad_tc_workspace_bytes(int B, int D, int H, int W);
+int mvd_conv3d_c16c16_wgrad_tc(const float* gy, const float* x, float* gw, void* workspace,
+                               long long workspace_bytes, int B, int D, int H, int W, void* stream);
 /* Weight gradient of the same layer, exact fp32 (packed FFMA2 on the CUDA cores):
  *   gy, x : [B,D,H,W,16];  gw : [16,16,3,3,3] OVERWRITTEN;  workspace of
  *   mvd_conv3d_c16c16_wgrad_workspace_bytes(B,D,H,W) bytes (per-tile partials, reduced deterministically). */

@@ -82,7 +82,8 @@ int make_f32_tensor_map(CUtensorMap* map, const float* base, int rank, const uin
         estr[i] = 1u;
         if (i > 0) gstr[i - 1] = strides[i - 1];
     }
-    const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+    const CUtensorMapSwizzle sw = swizzle_bytes == 12832 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                  : swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                   : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                   : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<float*>(base), gdim, gstr, bx, estr,

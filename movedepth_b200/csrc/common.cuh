@@ -96,7 +96,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // `padding_mode='zeros'` of the reference's grid_sample.
 int make_nhwc32_tensor_map(CUtensorMap* map, const float* base, int B, int h, int w, int box_w, int box_h);
 // generic fp32 tiled descriptor, no swizzle; dims/box innermost first, strides (bytes) for dims 1..rank-1
-// swizzle_bytes: 0 (none), 32, 64 or 128
+// swizzle_bytes: 0 (none), 32, 64, 128, or 12832 (128B rows swizzled in 32 B atoms)
 int make_f32_tensor_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides,
                         const uint32_t* box, int swizzle_bytes = 0);
 

@@ -15,6 +15,8 @@
 #include "common.cuh"
 #include "../../include/movedepth_b200.h"
 
+#include <stdlib.h>
+
 namespace mvd {
 namespace c16 {
 
@@ -946,6 +948,179 @@ conv3d_c16c16_tc_kernel(const __grid_constant__ CUtensorMap map_in, const TArgs 
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(CF::TMEM_COLS) : "memory");
 }
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient of the 16 -> 16 layer on tcgen05:  gw[co,ci,kd,kh,kw] = sum_pos gy[pos,co] * x[pos + off(kd,kh,kw), ci]
+// with the reduction over positions as the MMA's K dimension, i.e. both operands MN-major (channels contiguous).
+// Measured on this part: kind::tf32 accepts MN-major operands ONLY in the SWIZZLE_128B_BASE32B layout (128 B rows, 4-row
+// atoms, 32 B chunks XOR-ed with the row index); with the 32/64/128 B swizzles or no swizzle the MMA is a silent no-op.
+// A 128 B row of a position-major buffer (64 B per position) is a PAIR of positions, so the tiles are TMA-loaded through
+// a paired view of the tensors ([.., W/2, 32] fp32, inner box = 128 B = the swizzle span, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)
+// with a flattened pitch of 36 positions (x tile origin at column w0-2, gy tile at w0; both even).  Then
+//   A row k, M-group m = [x(A0 + 2k + 2m), x(A0 + 2k + 2m + 1)]   (leading-dimension offset 128 B = the next row: groups overlap),
+//   B row k            = [gy(2k), gy(2k + 1)],
+//   D[(shift s, ci), (j, co)] = sum_k x[A0 + 2k + s, ci] * gy[2k + j, co]      (M = 128: s = 0..7, N = 32: j = 0,1),
+// with A0 = kh * 36, and the wanted tap is  gw[.., kw] = D[s = kw + 1][j = 0] + D[s = kw + 2][j = 1]  (even + odd positions).
+// One MMA covers 16 positions; nine accumulators (kd,kh) x 32 columns stay in TMEM for the whole work item.
+constexpr int WP = 36;                                         // flattened pitch (positions)
+constexpr int WX_POS = HH * WP, WG_POS = TH * WP;              // 324 / 252 positions per slice
+constexpr int GY_BYTES = 16384;                                // 256 positions = 16 k-steps of 16
+constexpr int WG_KSTEPS = 16;
+constexpr int WG_XBUF = 3, WG_GBUF = 4;
+constexpr uint32_t WG_TMEM_COLS = 512;                         // 9 x 32 columns in use
+
+struct WgCfg {
+    static constexpr int OFF_X = 0;
+    static constexpr int OFF_G = OFF_X + WG_XBUF * SLICE_BYTES;
+    static constexpr int OFF_BAR = OFF_G + WG_GBUF * GY_BYTES;  // xfull[3], gfull[4], done[2], tmem base
+    static constexpr int TOTAL = OFF_BAR + 96;
+    static constexpr int ALLOC = TOTAL + 1024;
+};
+static_assert(SLICE_BYTES % 1024 == 0 && GY_BYTES % 1024 == 0, "128 B-row swizzle needs 1024 B aligned tiles");
+static_assert((2 * (WP / 2) + (WG_KSTEPS - 1) * 8 + 8 + 3) * 128 <= SLICE_BYTES, "A operand stays inside the x slice buffer");
+
+// MN-major SWIZZLE_128B_BASE32B descriptor: LBO = byte stride between 32-element (128 B) groups along M/N,
+// SBO = stride between groups of 4 K rows (512 B)
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(128 >> 4) << 16;
+    d |= static_cast<uint64_t>(512 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(1) << 61;
+    return d;
+}
+// D = F32, A = B = TF32, both MN-major, M = 128, N = 32
+constexpr uint32_t WG_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+
+struct WTArgs {
+    float* part;         // [2 * items][6912]: even-position and odd-position halves of every item
+    int B, D, H, W;
+    int tiles_h, tiles_w, dsplit, dlen;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+conv3d_c16c16_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_gy, const WTArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* xfull = reinterpret_cast<uint64_t*>(smem + WgCfg::OFF_BAR);
+    uint64_t* gfull = xfull + WG_XBUF;
+    uint64_t* done = gfull + WG_GBUF;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 2);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    TArgs ta{};
+    ta.B = a.B; ta.D = a.D; ta.H = a.H; ta.W = a.W;
+    ta.tiles_h = a.tiles_h; ta.tiles_w = a.tiles_w; ta.dsplit = a.dsplit; ta.dlen = a.dlen;
+    const Item it = tc_item(ta, blockIdx.x);
+    const int count = it.d1 - it.d0 + 2;                           // x slices d0-1 .. d1
+
+    auto issue_x = [&](int i) {                                    // paired view: coordinate 1 counts pairs of columns
+        uint64_t* bar = xfull + (i % WG_XBUF);
+        mbar_expect_tx(bar, WX_POS * 64);
+        tma_load_5d(smem + WgCfg::OFF_X + (i % WG_XBUF) * SLICE_BYTES, &map_x, bar, 0, it.w0 / 2 - 1, it.h0 - 1, it.d0 - 1 + i, it.b);
+    };
+    auto issue_gy = [&](int d) {                                   // only this item's own gy slices are ever used
+        if (d >= it.d0 && d < it.d1) {
+            uint64_t* bar = gfull + (d & 3);
+            mbar_expect_tx(bar, WG_POS * 64);
+            tma_load_5d(smem + WgCfg::OFF_G + (d & 3) * GY_BYTES, &map_gy, bar, 0, it.w0 / 2, it.h0, d, it.b);
+        }
+    };
+    if (tid == 0) {
+        tma_prefetch_desc(&map_x);
+        tma_prefetch_desc(&map_gy);
+        for (int i = 0; i < WG_XBUF; ++i) mbar_init(xfull + i, 1);
+        for (int i = 0; i < WG_GBUF; ++i) mbar_init(gfull + i, 1);
+        mbar_init(done, THREADS / 32);
+        mbar_init(done + 1, THREADS / 32);
+        mbar_fence_init();
+        for (int i = 0; i < WG_XBUF && i < count; ++i) issue_x(i);
+        issue_gy(it.d0);
+        issue_gy(it.d0 + 1);
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(WG_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    for (uint32_t c = 0; c < 9 * 32; c += 16) tmem_zero16(lane_addr + c);     // every MMA accumulates
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+
+    for (int i = 0; i < count; ++i) {
+        const int s = it.d0 - 1 + i, xb = i % WG_XBUF;
+        mbar_wait(xfull + xb, (i / WG_XBUF) & 1);
+        // gy slice s+1 is new in this iteration: wait for it and zero what must not contribute -- the four pitch
+        // columns 32..35 (they hold the neighbouring tile's gradients) and the four pad positions at the end
+        const int dn = s + 1;
+        if (dn >= it.d0 && dn < it.d1) {
+            const int first = it.d0 + (((dn & 3) - (it.d0 & 3)) & 3);
+            mbar_wait(gfull + (dn & 3), ((dn - first) >> 2) & 1);
+            unsigned char* gb = smem + WgCfg::OFF_G + (dn & 3) * GY_BYTES;
+            {                                                          // 32 positions x 4 pieces of 16 B = 128 threads
+                const int j = tid >> 2, q = tid & 3;
+                const int p = j < 28 ? (j >> 2) * WP + TW + (j & 3) : WG_POS + (j - 28);
+                const int row = p >> 1, chunk = ((2 * (p & 1) + (q >> 1)) ^ (row & 3));      // 32 B chunks are XOR-ed with the row
+                *reinterpret_cast<float4*>(gb + row * 128 + chunk * 32 + (q & 1) * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (elect_one()) {
+            const uint32_t xaddr = smem_u32(smem + WgCfg::OFF_X + xb * SLICE_BYTES);
+#pragma unroll
+            for (int acc = 0; acc < 9; ++acc) {
+                if ((acc * 4) / 9 != warp) continue;                   // the nine (kd,kh) accumulators are dealt to the four warps
+                const int kd = acc / 3, kh = acc - kd * 3;
+                const int d = s + 1 - kd;
+                if (d < it.d0 || d >= it.d1) continue;
+                const uint64_t ad = smem_desc_mn(xaddr + static_cast<uint32_t>(kh * WP) * 64u);       // kh tile rows down = 18 smem rows
+                const uint64_t bd = smem_desc_mn(smem_u32(smem + WgCfg::OFF_G + (d & 3) * GY_BYTES));
+#pragma unroll 4
+                for (int ks = 0; ks < WG_KSTEPS; ++ks)                 // 8 rows = 16 positions = 1 KB per MMA
+                    umma_tf32(tmem_base + acc * 32, ad + static_cast<uint64_t>(ks * 64), bd + static_cast<uint64_t>(ks * 64), WG_IDESC);
+            }
+            umma_commit(done + (i & 1));
+        }
+        if (i >= 1) {
+            mbar_wait(done + ((i - 1) & 1), ((i - 1) >> 1) & 1);
+            tc_fence_after();
+            if (tid == 0) {                                            // slice i-1's MMAs are complete: its buffers are free
+                if (i - 1 + WG_XBUF < count) issue_x(i - 1 + WG_XBUF);
+                issue_gy(s + 2);                                       // slot of gy slice s-2, last used by x slice s-1
+            }
+        }
+    }
+    mbar_wait(done + ((count - 1) & 1), ((count - 1) >> 1) & 1);
+    tc_fence_after();
+    // ---- epilogue: accumulator (kd,kh): row (shift s, ci) = TMEM lane 16*s + ci, column j*16 + co
+    {
+        float* p0 = a.part + static_cast<size_t>(2 * blockIdx.x) * NW16;       // j = 0: kw = s - 1
+        float* p1 = p0 + NW16;                                                 // j = 1: kw = s - 2
+        const int sh = tid >> 4, ci = tid & 15;
+#pragma unroll 1
+        for (int acc = 0; acc < 9; ++acc) {
+            uint32_t r0[16], r1[16];
+            tmem_ld16(lane_addr + acc * 32, r0);
+            tmem_ld16(lane_addr + acc * 32 + 16, r1);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int co = 0; co < 16; ++co) {
+                if (sh >= 1 && sh <= 3) p0[(co * 16 + ci) * 27 + acc * 3 + sh - 1] = __uint_as_float(r0[co]);
+                if (sh >= 2 && sh <= 4) p1[(co * 16 + ci) * 27 + acc * 3 + sh - 2] = __uint_as_float(r1[co]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(WG_TMEM_COLS) : "memory");
+}
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------ host
@@ -1180,6 +1355,65 @@ int mvd_conv3d_c16c16_tc(const float* in, const float* w, float* out, int B, int
     if (passes == 3) tc::conv3d_c16c16_tc_kernel<3><<<items, tc::THREADS, tc::Cfg<3>::ALLOC, st>>>(map, a);
     else tc::conv3d_c16c16_tc_kernel<1><<<items, tc::THREADS, tc::Cfg<1>::ALLOC, st>>>(map, a);
     return mvd::check_launch("conv3d_c16c16_tc");
+}
+
+
+static int wgrad_tc_plan(mvd::c16::tc::WTArgs& a) {
+    using namespace mvd::c16;
+    a.tiles_h = (a.H + tc::TH - 1) / tc::TH;
+    a.tiles_w = (a.W + tc::TW - 1) / tc::TW;
+    const int base = a.B * a.tiles_h * a.tiles_w, slots = mvd::sm_count();
+    int best = 1;
+    double best_eff = 0.0;
+    for (int ds = 1; ds <= 16 && a.D / ds >= 8; ++ds) {
+        const int dlen = (a.D + ds - 1) / ds, items = base * ((a.D + dlen - 1) / dlen);
+        const double waves = static_cast<double>(items) / slots;
+        const double eff = waves / static_cast<double>((items + slots - 1) / slots) * dlen / (dlen + 2.0);
+        if (eff > best_eff + 1e-9) {
+            best_eff = eff;
+            best = ds;
+        }
+    }
+    a.dlen = (a.D + best - 1) / best;
+    a.dsplit = (a.D + a.dlen - 1) / a.dlen;
+    return base * a.dsplit;
+}
+
+long long mvd_conv3d_c16c16_wgrad_tc_workspace_bytes(int B, int D, int H, int W) {
+    if (B <= 0 || D <= 0 || H <= 0 || W <= 0) return 0;
+    mvd::c16::tc::WTArgs a{};
+    a.B = B; a.D = D; a.H = H; a.W = W;
+    return 2ll * wgrad_tc_plan(a) * mvd::c16::NW16 * sizeof(float);
+}
+
+int mvd_conv3d_c16c16_wgrad_tc(const float* gy, const float* x, float* gw, void* workspace, long long workspace_bytes, int B,
+                               int D, int H, int W, void* stream) {
+    using namespace mvd::c16;
+    MVD_REQUIRE(gy && x && gw && workspace, "null pointer argument");
+    if (int rc = check_shape(B, D, H, W)) return rc;
+    MVD_REQUIRE(mvd::aligned16(x) && mvd::aligned16(gy), "activation pointers must be 16-byte aligned");
+    cudaStream_t st = mvd::as_stream(stream);
+    tc::WTArgs a{};
+    a.part = static_cast<float*>(workspace); a.B = B; a.D = D; a.H = H; a.W = W;
+    const int items = wgrad_tc_plan(a);
+    MVD_REQUIRE(workspace_bytes >= 2ll * items * NW16 * 4, "workspace too small: %lld < %lld", workspace_bytes, 2ll * items * NW16 * 4);
+    MVD_REQUIRE(W % 2 == 0, "the tcgen05 weight gradient pairs columns: W must be even (got %d)", W);
+    CUtensorMap map_x, map_gy;
+    const uint64_t Wd = W, Hd = H, Dd = D;
+    const uint64_t dims[5] = {2 * C, Wd / 2, Hd, Dd, static_cast<uint64_t>(B)};             // paired view: 2 columns x 16 channels = 128 B
+    const uint64_t str[4] = {2 * C * 4, Wd * C * 4, Wd * Hd * C * 4, Wd * Hd * Dd * C * 4};
+    const uint32_t boxx[5] = {2 * C, tc::WP / 2, tc::HH, 1, 1}, boxg[5] = {2 * C, tc::WP / 2, tc::TH, 1, 1};
+    if (int rc = mvd::make_f32_tensor_map(&map_x, x, 5, dims, str, boxx, 12832)) return rc;
+    if (int rc = mvd::make_f32_tensor_map(&map_gy, gy, 5, dims, str, boxg, 12832)) return rc;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(tc::conv3d_c16c16_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::WgCfg::ALLOC);
+        attr_done = true;
+    }
+    tc::conv3d_c16c16_wgrad_tc_kernel<<<items, tc::THREADS, tc::WgCfg::ALLOC, st>>>(map_x, map_gy, a);
+    if (int rc = mvd::check_launch("conv3d_c16c16_wgrad_tc")) return rc;
+    conv3d_c16c16_wgrad_reduce_kernel<<<(NW16 + 3) / 4, 128, 0, st>>>(a.part, gw, 2 * items);
+    return mvd::check_launch("conv3d_c16c16_wgrad_reduce");
 }
 
 }

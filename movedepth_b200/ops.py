@@ -321,6 +321,22 @@ def c16c16_wgrad(gy, x):
     return gw
 
 
+def c16c16_wgrad_tc(gy, x):
+    """TF32 weight gradient [16,16,3,3,3] of the 16->16 layer on tcgen05 / TMEM (odd widths: exact-fp32 FFMA2 kernel)."""
+    B, C, D, H, W = x.shape
+    if W % 2:
+        return c16c16_wgrad(gy, x)
+    gy = _f32(gy).contiguous(memory_format=torch.channels_last_3d)
+    x = _f32(x).contiguous(memory_format=torch.channels_last_3d)
+    nbytes = _lib.lib().mvd_conv3d_c16c16_wgrad_tc_workspace_bytes(B, D, H, W)
+    ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32)
+    gw = torch.empty((16, 16, 3, 3, 3), device=x.device, dtype=torch.float32)
+    rc = _lib.lib().mvd_conv3d_c16c16_wgrad_tc(_p(gy), _p(x), _p(gw), _p(ws), nbytes, B, D, H, W, _stream())
+    _lib.check(rc, "mvd_conv3d_c16c16_wgrad_tc")
+    launch_counter["n"] += 2
+    return gw
+
+
 class _Conv3dC16C16(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, passes):
@@ -332,14 +348,14 @@ class _Conv3dC16C16(torch.autograd.Function):
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
         gx = c16c16_conv_tc(gy, w, 1, 1) if ctx.needs_input_grad[0] else None   # single-pass TF32 data gradient (tcgen05)
-        gw = c16c16_wgrad(gy, x) if ctx.needs_input_grad[1] else None           # exact fp32 weight gradient
+        gw = c16c16_wgrad_tc(gy, x) if ctx.needs_input_grad[1] else None        # single-pass TF32 weight gradient (tcgen05)
         return gx, gw, None
 
 
 def conv3d_c16_to_16(x, weight, passes=3):
     """Conv3d(16 -> 16, k=3, stride 1, padding 1, no bias) on a channels-last-3d volume, all three passes hand-written:
-    tcgen05/TMEM implicit GEMM forward (3xTF32 split with passes=3, plain TF32 with passes=1) and TF32 data gradient,
-    exact-fp32 FFMA2 weight gradient.  Reference: reg3d.conv0.conv, movedepth/networks/resnet_encoder.py:178, 231."""
+    tcgen05/TMEM implicit GEMM forward (3xTF32 split with passes=3, plain TF32 with passes=1), TF32 data gradient and
+    TF32 weight gradient (MN-major operands); `c16c16_wgrad` is the exact-fp32 FFMA2 weight gradient.  Reference: reg3d.conv0.conv, movedepth/networks/resnet_encoder.py:178, 231."""
     return _Conv3dC16C16.apply(x, weight, passes)
 
 

@@ -107,7 +107,7 @@ class _SplitConv(torch.autograd.Function):
                 # reg3d's full-resolution 16->16 layer: hand-written gradients (cuDNN needs 1.6 ms + 2.6 ms here)
                 from . import ops
                 gx = ops.c16c16_conv_tc(gy, w, 1, 1) if need_x else None      # tcgen05 / TMEM implicit GEMM, TF32
-                gw = ops.c16c16_wgrad(gy, x) if need_w else None
+                gw = ops.c16c16_wgrad_tc(gy, x) if need_w else None                   # tcgen05, MN-major operands, TF32
             elif not _policy["split_backward"]:
                 gx, gw, _ = torch.ops.aten.convolution_backward(gy, x, w.contiguous(memory_format=_fmt(w)), None, stride,
                                                                 padding, (1,) * nd, transposed, output_padding, 1,

@@ -349,8 +349,11 @@ def test_cuda_graph_step_tracks_the_eager_step():
             np.random.seed(100 + i)
             losses.append(float(tr.train_step(batch)[1]["loss"].detach()))
         assert abs(losses[1] - losses[0]) <= 1e-3 * abs(losses[0]), (i, losses)
-        for a, b in zip(eager.arenas, graphed.arenas):           # gradients (a few auto-mask pixels may flip: 5e-3 of the max)
-            torch.testing.assert_close(b.grad, a.grad, atol=5e-3 * float(a.grad.abs().max()), rtol=1e-2)
+        for a, b in zip(eager.arenas, graphed.arenas):           # gradients: a few auto-mask / argmax pixels may flip between the
+            tol = 5e-3 * float(a.grad.abs().max()) + 1e-2 * a.grad.abs()      # two runs (atomics order), so bound the outliers
+            bad = float(((b.grad - a.grad).abs() > tol).float().mean())
+            assert bad < 1e-5, (i, bad)
+            assert float((b.grad - a.grad).abs().max()) < 5e-2 * float(a.grad.abs().max())
     assert len(graphed._graphs) == 1, "the graph was never captured"
 
 
@@ -429,7 +432,7 @@ def test_conv3d_16_to_16_matches_torch_conv3d(ops, shape):
     wo = w.double().requires_grad_(True)
     (F.conv3d(x.double(), wo, padding=1) * gy.double()).sum().backward()
     gwo = wo.grad.float()
-    torch.testing.assert_close(wg.grad.cpu(), gwo, atol=2e-5 * float(gwo.abs().max()), rtol=0)     # exact-fp32 weight gradient
+    torch.testing.assert_close(wg.grad.cpu(), gwo, atol=3e-3 * float(gwo.abs().max()), rtol=0)     # TF32 weight gradient (tcgen05; odd W: fp32)
 
 
 # ---------------------------------------------------------------------------------------------- BatchNorm kernels
@@ -545,3 +548,23 @@ def test_conv3d_16_to_16_tcgen05_matches_torch_conv3d(ops, shape):
         torch.testing.assert_close(y.cpu(), yo, atol=tol * float(yo.abs().max()), rtol=0)
         gx = ops.c16c16_conv_tc(xg, wg, 1, passes)
         torch.testing.assert_close(gx.cpu(), go, atol=tol * float(go.abs().max()), rtol=0)
+
+
+@pytest.mark.parametrize("shape", [(1, 6, 7, 32), (1, 5, 11, 46), (2, 26, 24, 80)], ids=["aligned", "ragged", "multi-tile"])
+def test_conv3d_16_to_16_tcgen05_weight_gradient(ops, shape):
+    """tcgen05 weight gradient (MN-major SWIZZLE_128B_BASE32B operands through a paired TMA view, even + odd position
+    halves summed) vs torch's fp64 conv3d_weight: single-pass TF32 with truncated operands -> 3e-3 of the scale; the
+    exact-fp32 FFMA2 kernel of the same contract -> 2e-5.  Odd widths fall back to the FFMA2 kernel."""
+    B, D, H, W = shape
+    gen = torch.Generator().manual_seed(6)
+    x = torch.randn(B, 16, D, H, W, generator=gen)
+    gy = torch.randn(B, 16, D, H, W, generator=gen)
+    want = torch.nn.grad.conv3d_weight(x.double(), (16, 16, 3, 3, 3), gy.double(), padding=1).float()
+    xg = g(x).contiguous(memory_format=torch.channels_last_3d)
+    gg = g(gy).contiguous(memory_format=torch.channels_last_3d)
+    scale = float(want.abs().max())
+    torch.testing.assert_close(ops.c16c16_wgrad_tc(gg, xg).cpu(), want, atol=3e-3 * scale, rtol=0)
+    torch.testing.assert_close(ops.c16c16_wgrad(gg, xg).cpu(), want, atol=2e-5 * scale, rtol=0)
+    xo = g(torch.randn(1, 16, 4, 7, 33, generator=gen)).contiguous(memory_format=torch.channels_last_3d)
+    go = g(torch.randn(1, 16, 4, 7, 33, generator=gen)).contiguous(memory_format=torch.channels_last_3d)
+    torch.testing.assert_close(ops.c16c16_wgrad_tc(go, xo), ops.c16c16_wgrad(go, xo))

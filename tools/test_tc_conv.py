@@ -14,7 +14,7 @@ from movedepth_b200 import ops  # noqa: E402
 def main():
     dev = "cuda:0"
     gen = torch.Generator().manual_seed(4)
-    for shape in ((1, 6, 7, 32), (1, 5, 11, 45), (2, 26, 24, 80)):
+    for shape in (() if "--wgrad-only" in sys.argv else ((1, 6, 7, 32), (1, 5, 11, 45), (2, 26, 24, 80))):
         B, D, H, W = shape
         x = torch.randn(B, 16, D, H, W, generator=gen)
         w = torch.randn(16, 16, 3, 3, 3, generator=gen) * 0.1
@@ -31,13 +31,27 @@ def main():
                 torch.cuda.synchronize()
                 eg = float((g.cpu() - go).abs().max() / go.abs().max())
                 print("shape %s flags %d passes %d: fwd rel err %.2e, dgrad rel err %.2e" % (shape, flags, passes, e, eg), flush=True)
+    # weight gradient
+    for shape in ((1, 6, 7, 32), (1, 5, 11, 46), (2, 26, 24, 80), (1, 9, 20, 160)):
+        B, D, H, W = shape
+        x = torch.randn(B, 16, D, H, W, generator=gen)
+        gy = torch.randn(B, 16, D, H, W, generator=gen)
+        gwo = torch.nn.grad.conv3d_weight(x.double(), (16, 16, 3, 3, 3), gy.double(), padding=1).float()
+        xg = x.to(dev).contiguous(memory_format=torch.channels_last_3d)
+        gg = gy.to(dev).contiguous(memory_format=torch.channels_last_3d)
+        gw = ops.c16c16_wgrad_tc(gg, xg)
+        torch.cuda.synchronize()
+        gwf = ops.c16c16_wgrad(gg, xg)
+        print("wgrad shape %s: tc rel err %.2e, ffma2 rel err %.2e" % (shape, float((gw.cpu() - gwo).abs().max() / gwo.abs().max()),
+                                                                       float((gwf.cpu() - gwo).abs().max() / gwo.abs().max())), flush=True)
     # timing
     x = torch.randn(6, 16, 96, 48, 160, device=dev).contiguous(memory_format=torch.channels_last_3d)
     w = torch.randn(16, 16, 3, 3, 3, device=dev) * 0.1
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    cases = [("tc 3-pass", lambda: ops.c16c16_conv_tc(x, w, 0, 3)), ("tc 1-pass", lambda: ops.c16c16_conv_tc(x, w, 1, 1)),
+    cases = [("wgrad tc", lambda: ops.c16c16_wgrad_tc(x, x)), ("wgrad ffma2", lambda: ops.c16c16_wgrad(x, x)),
+             ("tc 3-pass", lambda: ops.c16c16_conv_tc(x, w, 0, 3)), ("tc 1-pass", lambda: ops.c16c16_conv_tc(x, w, 1, 1)),
              ("mma.sync 1-pass", lambda: ops.c16c16_conv(x, w, 1, 1))]
-    for dbg, nm in ((2, "no MMA"), (4, "no stores"), (8, "no split"), (14, "TMA + sync only")):
+    for dbg, nm in ():
         cases.append(("tc 3-pass dbg %s" % nm, lambda dbg=dbg: ops.c16c16_conv_tc(x, w, 0, 3, dbg)))
         cases.append(("tc 1-pass dbg %s" % nm, lambda dbg=dbg: ops.c16c16_conv_tc(x, w, 1, 1, dbg)))
     for name, fn in cases:
