@@ -160,7 +160,10 @@ def run_own(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(batches, steps, read_loss):
+    def timed(batches, steps, read_loss, graph_pairs=None, cv=None):
+        """K steps bracketed by barrier + synchronize, device-timed.  With `graph_pairs` (the cost-volume timing-event nodes
+        inside the replayed graph) every step ends with a stream synchronize so the pair can be read before the next replay
+        overwrites it -- the kernel is then timed on exactly the steps `value` is measured on (costs ~0.1 % of a step)."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -168,7 +171,10 @@ def run_own(args):
             flush.fill_(i & 1)                                            # L2 flush between iterations
             _, losses = tr.train_step(batches[i % len(batches)])
             if read_loss:
-                float(losses["loss"])                                     # device -> host read of the step result
+                float(losses["loss"].detach())                            # device -> host read of the step result
+            if graph_pairs is not None:
+                torch.cuda.current_stream().synchronize()
+                cv.extend(a.elapsed_time(b) for a, b in graph_pairs)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -177,7 +183,8 @@ def run_own(args):
         return float(ms)
 
     ops.costvol_events = []                      # the cost-volume forward records (start, stop) events around its launch
-    warm = max(3, args.warmup) + (0 if args.no_graph else tr.GRAPH_WARMUP + 1)   # graph mode: eager warm-up, capture, replays
+    # graph mode: train_step itself runs GRAPH_WARMUP eager steps and captures on the next call
+    warm = max(3, args.warmup) if args.no_graph else max(args.warmup, tr.GRAPH_WARMUP + 1)
     for i in range(warm):
         tr.train_step(dev_batches[i % 4])
     torch.cuda.synchronize()
@@ -188,20 +195,21 @@ def run_own(args):
     n0 = ops.launch_counter["n"]
     if args.ncu_range:                       # `ncu --profile-from-start off`: capture exactly the timed steps
         torch.cuda.profiler.start()
-    ms = timed(dev_batches, args.steps, read_loss=False)
+    cv = []
+    ms = timed(dev_batches, args.steps, read_loss=False, graph_pairs=graph_pairs, cv=cv)
     if args.ncu_range:
         torch.cuda.profiler.stop()
     launches = ops.launch_counter["n"] - n0
     if graph_pairs is None:
         cv = [a.elapsed_time(b) for a, b in ops.costvol_events]
-    else:                                    # same graph, same replays; a synchronize per step only to read the event nodes
-        cv = []
-        for i in range(args.steps):
-            flush.fill_(i & 1)
-            tr.train_step(dev_batches[i % len(dev_batches)])
-            torch.cuda.synchronize()
-            cv += [a.elapsed_time(b) for a, b in graph_pairs]
     ops.costvol_events = None
+    if args.verbose and rank == 0:               # what did K1 see?  (pose / prior statistics of the last step)
+        out, _ = tr.train_step(dev_batches[0])
+        T = out[("cam_T_cam", 0, -1)].detach()
+        pr = out["depth_prior"].detach()
+        print("K1 inputs: |t| per item %s, tz %s, prior min/median/max %.3f/%.3f/%.3f; K1 us per launch %s" % (
+            [round(float(v), 4) for v in T[:, :3, 3].norm(dim=1)], [round(float(v), 4) for v in T[:, 2, 3]],
+            float(pr.min()), float(pr.median()), float(pr.max()), [round(v * 1e3) for v in cv]), file=sys.stderr)
     ms_e2e = timed(host_batches, args.steps, read_loss=True)
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -215,7 +223,7 @@ def run_own(args):
     achieved = costvol_bytes(BATCH) / (cv_ms * 1e-3) / 1e9
     line = {
         "metric": METRIC, "value": frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "precision": {"3xtf32": "convs on tensor cores with a 3-way TF32 operand split in the forward (near-fp32 outputs, "
                    "movedepth_b200/precision.py); gradients single-pass TF32 (PyTorch's default conv policy)",
@@ -252,6 +260,7 @@ def main():
     ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "fp32", "tf32"])
     ap.add_argument("--velocity", action="store_true", help="use the velocity-guided hypothesis range (epoch > 8)")
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--verbose", action="store_true", help="print the pose / prior statistics the cost-volume kernel saw")
     ap.add_argument("--no_graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--ncu_range", action="store_true", help="cudaProfilerStart/Stop around the device-timed steps")
     ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from the committed ncu capture")

@@ -27,8 +27,12 @@ def main():
     ap.add_argument("--h", type=int, default=48)
     ap.add_argument("--w", type=int, default=160)
     ap.add_argument("--D", type=int, default=96)
+    ap.add_argument("--tscale", type=float, default=1.0, help="scale the pose translation (longer epipolar footprints)")
     a = ap.parse_args()
     c = C.case_costvol(a.pose, B=a.B, h=a.h, w=a.w, D=a.D)
+    if a.tscale != 1.0:
+        c["pose"] = c["pose"].clone()
+        c["pose"][:, 0, :3, 3] *= a.tscale
     dev = "cuda:0"
     ref = c["ref"].to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(a.bwd)
     src = c["src"].to(dev).contiguous(memory_format=torch.channels_last).requires_grad_(a.bwd)
