@@ -220,6 +220,18 @@ int mvd_bn_bwd_apply(const float* gy, const float* x, const float* y, const floa
                      float* gw, float* gb, long long M, int C, int relu, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * SyncBatchNorm statistics exchange over NVLink peer memory (replaces the all_gather / all_reduce
+ * of nn.SyncBatchNorm, movedepth/trainer.py:69-129, for the 2C-double vectors of mvd_bn_stats /
+ * mvd_bn_bwd_reduce).  `peers` is a DEVICE array of `world` addresses: the same symmetric
+ * buffer (mvd_peer_allreduce_buffer_bytes(world, nmax) bytes, zero-initialised once) as mapped
+ * on this GPU for every rank.  out[i] = sum over ranks of local[i], added in rank order (bitwise
+ * identical on all ranks).  Collective: every rank must launch it the same number of times.
+ * ------------------------------------------------------------------------------------- */
+long long mvd_peer_allreduce_buffer_bytes(int world, int nmax);
+int mvd_peer_allreduce_f64(const double* local, double* out, int n, const unsigned long long* peers,
+                           int rank, int world, int nmax, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Measurement helpers (bench.py's live cost-volume roofline): CUDA timing events that also
  * work INSIDE a captured CUDA graph.  mvd_event_record with external != 0 uses
  * cudaEventRecordExternal, i.e. the record becomes an event-record NODE when the stream is

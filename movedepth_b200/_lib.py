@@ -49,6 +49,8 @@ SIGNATURES = {
     "mvd_bn_apply": ([_P, _P, _P, _P, _LL, _I, _I, _P], _I),
     "mvd_bn_bwd_reduce": ([_P, _P, _P, _P, _P, _LL, _I, _I, _P], _I),
     "mvd_bn_bwd_apply": ([_P] * 6 + [_D] + [_P] * 4 + [_LL, _I, _I, _P], _I),
+    "mvd_peer_allreduce_buffer_bytes": ([_I, _I], _LL),
+    "mvd_peer_allreduce_f64": ([_P, _P, _I, _P, _I, _I, _I, _P], _I),
     "mvd_event_create": ([], _P),
     "mvd_event_record": ([_P, _P, _I], _I),
     "mvd_event_elapsed_ms": ([_P, _P, ctypes.POINTER(ctypes.c_float)], _I),

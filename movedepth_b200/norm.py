@@ -32,6 +32,52 @@ def _fmt(t):
     return torch.channels_last_3d if t.dim() == 5 else torch.channels_last
 
 
+class PeerExchange:
+    """All-reduce of the small fp64 statistic vectors by our own kernel over NVLink peer memory
+    (csrc/peer.cu) instead of NCCL.  One symmetric buffer per process (torch symmetric memory: CUDA VMM
+    allocations mapped into every rank of the node)."""
+    NMAX = 2048
+    _inst = None
+    _failed = False
+
+    def __init__(self, device):
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        nbytes = _lib.lib().mvd_peer_allreduce_buffer_bytes(self.world, self.NMAX)
+        self.buf = symm.empty((nbytes + 7) // 8, dtype=torch.float64, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, dist.group.WORLD)
+        self.ptrs = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
+        torch.cuda.synchronize()
+        dist.barrier()
+
+    @classmethod
+    def get(cls, device):
+        if cls._inst is None and not cls._failed:
+            try:
+                cls._inst = cls(device)
+            except Exception as e:                      # no peer access / symmetric memory: NCCL does the exchange
+                cls._failed = True
+                print("movedepth_b200: peer-memory SyncBN exchange unavailable (%s: %s); using NCCL" % (type(e).__name__, e))
+        return cls._inst
+
+    def allreduce_(self, v):
+        rc = _lib.lib().mvd_peer_allreduce_f64(_p(v), _p(v), v.numel(), _p(self.ptrs), self.rank, self.world, self.NMAX, _stream())
+        _lib.check(rc, "mvd_peer_allreduce_f64")
+        _count_launch(1)
+
+
+peer_exchange = True      # SyncBN statistics over NVLink peer memory when available (else NCCL all_reduce)
+
+
+def _sync_sum_(v):
+    px = PeerExchange.get(v.device) if (peer_exchange and v.numel() <= PeerExchange.NMAX) else None
+    if px is not None:
+        px.allreduce_(v)
+    else:
+        dist.all_reduce(v)
+
+
 def _count_launch(n):
     from . import ops
     ops.launch_counter["n"] += n
@@ -49,7 +95,7 @@ class _BNAct(torch.autograd.Function):
         _lib.check(L.mvd_bn_stats(_p(xc), M, C, _p(sums), _stream()), "mvd_bn_stats")
         count = float(M)
         if sync:
-            dist.all_reduce(sums)
+            _sync_sum_(sums)
             count *= dist.get_world_size()
         stats = torch.empty(4 * C, device=x.device, dtype=torch.float32)
         _lib.check(L.mvd_bn_finalize(_p(sums), count, _p(weight), _p(bias), _p(running_mean), _p(running_var), float(momentum),
@@ -72,7 +118,7 @@ class _BNAct(torch.autograd.Function):
         gw = gb = None
         if sync:                                  # parameter gradients are this rank's own sums (DDP averages them later)
             gb, gw = sums2[:C].float(), sums2[C:].float()
-            dist.all_reduce(sums2)
+            _sync_sum_(sums2)
         else:
             gw = torch.empty(C, device=xc.device, dtype=torch.float32)
             gb = torch.empty(C, device=xc.device, dtype=torch.float32)

@@ -1,0 +1,83 @@
+"""2+ GPU check of the peer-memory all-reduce (csrc/peer.cu) against NCCL, eager and inside a CUDA graph.
+   torchrun --nproc-per-node 2 tools/test_peer_allreduce.py"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from movedepth_b200 import norm as NM  # noqa: E402
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", local)
+    px = NM.PeerExchange.get(dev)
+    assert px is not None, "peer exchange unavailable"
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    worst = 0.0
+    for it in range(300):
+        n = [16, 64, 256, 1024, 2048][it % 5]
+        v = torch.randn(n, device=dev, dtype=torch.float64, generator=g)
+        want = v.clone()
+        dist.all_reduce(want)
+        px.allreduce_(v)
+        worst = max(worst, float((v - want).abs().max()))
+    torch.cuda.synchronize()
+    # inside a CUDA graph
+    bufs = [torch.randn(128, device=dev, dtype=torch.float64, generator=g) for _ in range(50)]
+    want = []
+    for b in bufs:
+        w = b.clone()
+        dist.all_reduce(w)
+        want.append(w)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    work = [b.clone() for b in bufs]
+    with torch.cuda.stream(s):
+        for w in work:
+            px.allreduce_(w)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    gerr = max(float((a - b).abs().max()) for a, b in zip(work, want))
+    graph = torch.cuda.CUDAGraph()
+    static = [b.clone() for b in bufs]
+    outs = [torch.empty_like(b) for b in bufs]
+    with torch.cuda.graph(graph, stream=s):
+        for a, o in zip(static, outs):
+            o.copy_(a)
+            px.allreduce_(o)
+    for _ in range(5):
+        graph.replay()
+    torch.cuda.synchronize()
+    gerr = max(gerr, max(float((a - b).abs().max()) for a, b in zip(outs, want)))
+    # latency
+    v = torch.randn(128, device=dev, dtype=torch.float64)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dist.barrier()
+    e0.record()
+    for _ in range(200):
+        px.allreduce_(v)
+    e1.record()
+    torch.cuda.synchronize()
+    t_peer = e0.elapsed_time(e1) / 200 * 1e3
+    e0.record()
+    for _ in range(200):
+        dist.all_reduce(v)
+    e1.record()
+    torch.cuda.synchronize()
+    t_nccl = e0.elapsed_time(e1) / 200 * 1e3
+    print("rank %d/%d: eager max err %.2e, graph max err %.2e, peer %.1f us/call, nccl %.1f us/call (eager launches)" % (
+        rank, world, worst, gerr, t_peer, t_nccl), flush=True)
+    dist.barrier()
+    torch.cuda.synchronize()
+    os._exit(0)
+
+
+if __name__ == "__main__":
+    main()
