@@ -263,7 +263,10 @@ def main():
     ap.add_argument("--verbose", action="store_true", help="print the pose / prior statistics the cost-volume kernel saw")
     ap.add_argument("--no_graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--ncu_range", action="store_true", help="cudaProfilerStart/Stop around the device-timed steps")
-    ap.add_argument("--traffic", type=float, default=None, help="dram bytes per launch from the committed ncu capture")
+    ap.add_argument("--traffic", type=float, default=243.05e6,
+                    help="dram__bytes_read.sum + dram__bytes_write.sum per launch of the cost-volume forward from the committed "
+                         "ncu --set full capture (profiles/r01_costvol_ncu_full.txt: 12.06 MB + 230.99 MB; the rest of the 283 MB "
+                         "volume is still in L2 when the kernel ends)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -177,7 +177,8 @@ int mvd_conv3d_c16o1_wgrad(const float* gy, const float* x, float* gw, void* wor
 int mvd_conv3d_c16c16(const float* in, const float* w, float* out, int B, int D, int H, int W,
                       int mode, int passes, void* stream);
 /* The same contract on the 5th-generation tensor cores: tcgen05.mma kind::tf32, accumulators in TMEM, every tap's
- * A operand = the TMA-staged slice at a shifted start address.  flags: reserved, pass 0. */
+ * A operand = the TMA-staged slice at a shifted start address.  flags: 0; profiling only (results become meaningless):
+ * 2 = skip the MMAs, 4 = skip the global stores, 8 = skip the hi/lo operand split. */
 int mvd_conv3d_c16c16_tc(const float* in, const float* w, float* out, int B, int D, int H, int W,
                          int mode, int passes, int flags, void* stream);
 /* Weight gradient on tcgen05 (single-pass TF32; MN-major operands, the four M-groups of A are the x slice shifted by

@@ -216,3 +216,46 @@ def test_3xtf32_split_conv_matches_plain_conv_and_its_gradients():
         torch.testing.assert_close(mine.weight.grad, plain.weight.grad, rtol=1e-5, atol=2e-5)
     hi = PR.tf32_round(torch.tensor([1.0 + 2 ** -11, 3.14159274]))
     assert (hi.view(torch.int32) & 0x1FFF).abs().sum() == 0
+
+
+def test_bn_act_routes_cpu_tensors_through_torch_batchnorm():
+    """norm.bn_act is what every conv block calls; without CUDA tensors (oracle comparisons, evaluation mode) it must be
+    exactly relu(bn(x) + residual) of the stock module, running statistics included."""
+    import torch.nn as nn
+    from movedepth_b200 import norm as NM
+    torch.manual_seed(0)
+    x, r = torch.randn(3, 8, 5, 7), torch.randn(3, 8, 5, 7)
+    a, b = nn.BatchNorm2d(8), nn.BatchNorm2d(8)
+    want = torch.relu(a(x) + r)
+    got = NM.bn_act(b, x, relu=True, residual=r)
+    torch.testing.assert_close(got, want)
+    torch.testing.assert_close(b.running_var, a.running_var)
+    b.eval()
+    a.eval()
+    torch.testing.assert_close(NM.bn_act(b, x), a(x))
+
+
+def test_workspace_and_buffer_size_queries_need_no_gpu():
+    """Pure host entry points of the C ABI: wgrad workspaces (per-tile partials) and the peer-exchange buffer."""
+    from movedepth_b200 import _lib
+    L = _lib.lib()
+    assert L.mvd_peer_allreduce_buffer_bytes(8, 2048) == 4096 + 2 * 8 * 2048 * 8
+    assert L.mvd_peer_allreduce_buffer_bytes(0, 2048) == 0
+    for fn, per_item in ((L.mvd_conv3d_c16o1_wgrad_workspace_bytes, 432 * 4), (L.mvd_conv3d_c16c16_wgrad_workspace_bytes, 6912 * 4),
+                         (L.mvd_conv3d_c16c16_wgrad_tc_workspace_bytes, 2 * 6912 * 4)):
+        n = fn(6, 96, 48, 160)
+        assert n > 0 and n % per_item == 0 and n // per_item >= 6 * 6 * 5       # at least one item per (batch, tile)
+        assert fn(0, 96, 48, 160) == 0
+
+
+def test_custom_conv_modules_keep_reference_state_dict_and_cpu_path():
+    """ProbConv3d / ConvBnReLUSeq are drop-ins: nn.Conv3d / nn.Sequential state-dict keys, stock arithmetic on CPU."""
+    import torch.nn as nn
+    from movedepth_b200 import networks as PN, precision as PR
+    PR.set_policy("fp32")
+    reg = PN.reg3d(16, 16, 3)
+    keys = set(reg.state_dict().keys())
+    assert "prob.weight" in keys and "conv7.0.weight" in keys and "conv7.1.running_mean" in keys and "conv0.bn.weight" in keys
+    x = torch.randn(1, 16, 8, 8, 16)
+    want = nn.functional.conv3d(x, reg.prob.weight, padding=1)
+    torch.testing.assert_close(reg.prob(x), want)
