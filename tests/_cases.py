@@ -135,6 +135,7 @@ STEP_CASES = {
     "r18_3f": dict(H=64, W=96, D=16, B=2, frame_ids=[0, -1, 1], epoch=0, arch=18),
     "r50_3f": dict(H=64, W=96, D=8, B=1, frame_ids=[0, -1, 1], epoch=9, arch=50),
 }
+EVAL_CASE = dict(H=64, W=96, D=8, B=2, frame_ids=[0, -1], epoch=9, arch=18)      # inference path (evaluate_depth.py:181-253)
 GRAD_PROBES = [("pose", "net.3.bias"), ("reg3d", "prob.weight"), ("mask_cnn", "head_convs.weight"),
                ("mono_depth", "decoder.10.conv.bias"), ("up", "upsample_mask.2.weight"),
                ("mvs_encoder", "out.weight")]

@@ -177,8 +177,62 @@ def step_vectors(rl, rn, rt, Options):
               {k: float(v) for k, v in g.items() if k.startswith("loss/")})
 
 
+def eval_vectors(rl, rn):
+    """The inference loop body of movedepth/evaluate_depth.py:181-253 re-assembled from the REFERENCE's own functions
+    and networks (the loop itself is inline in evaluate(), which needs the KITTI dataset), eval mode, deterministic
+    weights, one smooth synthetic batch."""
+    import _cases as C
+    from _weights import fill_deterministic
+    import torch.nn.functional as F
+    cfg = C.EVAL_CASE
+    opt = C.step_options(cfg)
+    m = {}
+    m["mono_encoder"] = rn.ResnetEncoder(num_layers=18, pretrained=False)
+    m["mono_depth"] = rn.DepthDecoder(m["mono_encoder"].num_ch_enc, match_conv=False, ddv=False, discret=None, mono_conf=False, mono_bins=None)
+    m["pose_encoder"] = rn.ResnetEncoder(18, False, num_input_images=2)
+    m["pose"] = rn.PoseDecoder(m["pose_encoder"].num_ch_enc, num_input_features=1, num_frames_to_predict_for=2)
+    m["mvs_encoder"] = rn.FPN4(base_channels=8, scale=opt.prior_scale, dcn=False)
+    m["reg3d"] = rn.reg3d(in_channels=opt.reg3d_c, base_channels=opt.reg3d_c, down_size=3)
+    m["up"] = rl.convex_upsample_layer(feature_dim=8 * 2 ** opt.prior_scale, scale=opt.prior_scale)
+    for k, mod in m.items():
+        fill_deterministic(mod, salt=k + "/")
+        mod.eval()
+    data, _, _ = C.step_inputs(cfg)
+    h, w = cfg["H"] // 4, cfg["W"] // 4
+    bp, pj = rl.BackprojectDepth(cfg["D"], h, w), rl.Project3D(cfg["D"], h, w)
+    with torch.no_grad():
+        color = data["color", 0, 0]
+        out = m["mono_depth"](m["mono_encoder"](color))
+        poses = []
+        for f in cfg["frame_ids"][1:]:
+            pair = [data["color", f, 0], color] if f < 0 else [color, data["color", f, 0]]
+            aa, tr = m["pose"]([m["pose_encoder"](torch.cat(pair, 1))])
+            poses.append(rl.transformation_from_parameters(aa[:, 0], tr[:, 0], invert=f < 0))
+        rel = torch.stack(poses, 1)
+        ref_feat, ref_ctx = m["mvs_encoder"](color)
+        src_feat, _ = m["mvs_encoder"](data["color_aug", -1, 0])
+        disp_prior = out[("disp", opt.prior_scale)]
+        depth_prior = 1 / (1 / opt.max_depth + disp_prior * (1 / opt.min_depth - 1 / opt.max_depth))
+        z_scale = opt.z_scale * rel[0, 0, 2, -1]
+        hyps = rl.schedule_depth_range_zv2(depth_prior, ndepth=cfg["D"], scale_fac=opt.depth_bin_fac, z_trans=z_scale)
+        cv = rl.generate_costvol(ref_feat, src_feat, data["K", 2], data["inv_K", 2], hyps, rel[:, 0:1], cfg["D"], bp, pj)
+        B, D, Cc, H, W = cv.shape
+        cv = cv.reshape(B, D, -1, opt.reg3d_c, H, W).mean(2)
+        wgt = torch.softmax(cv.mean(2), dim=1).max(1)[0]
+        feats = (wgt.unsqueeze(1).unsqueeze(1) * cv) / (1e-8 + wgt).unsqueeze(1).unsqueeze(1)
+        prob = F.softmax(m["reg3d"](feats), 1)
+        depth = rl.localmax(prob, opt.norm_radius, cfg["D"], 1 / hyps[:, -1], 1 / hyps[:, 0])
+        depth_up = m["up"](depth, ref_ctx)
+        disp_mono, _ = rl.disp_to_depth(out[("disp", 0)], opt.min_depth, opt.max_depth)
+    g = dict(pred_disp_z=np32(1 / depth_up), pred_disp_mono=np32(disp_mono[:, 0]), depth_lowres=np32(depth), tz0=np32(rel[0, 0, 2, -1]))
+    np.savez_compressed(os.path.join(HERE, "eval_r18.npz"), **g)
+    print("eval_r18.npz:", {k: v.shape for k, v in g.items()}, "tz0", float(g["tz0"]))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     rl, rn, rt, Options = import_reference()
-    op_vectors(rl)
-    step_vectors(rl, rn, rt, Options)
+    if "--eval-only" not in sys.argv:
+        op_vectors(rl)
+        step_vectors(rl, rn, rt, Options)
+    eval_vectors(rl, rn)

@@ -568,3 +568,32 @@ def test_conv3d_16_to_16_tcgen05_weight_gradient(ops, shape):
     xo = g(torch.randn(1, 16, 4, 7, 33, generator=gen)).contiguous(memory_format=torch.channels_last_3d)
     go = g(torch.randn(1, 16, 4, 7, 33, generator=gen)).contiguous(memory_format=torch.channels_last_3d)
     torch.testing.assert_close(ops.c16c16_wgrad_tc(go, xo), ops.c16c16_wgrad(go, xo))
+
+
+# ---------------------------------------------------------------------------------------------- inference path
+def test_depth_predictor_matches_reference_golden():
+    """movedepth_b200.evaluate_depth.DepthPredictor (fused kernels, eval mode, fp32 convolutions) vs the golden output of
+    the reference's inference loop body (tests/golden/eval_r18.npz): mono disparity to 1e-3, >= 99 % of the multi-frame
+    disparities within 1e-3 relative; and the CPU oracle's metric code on the same numbers."""
+    from movedepth_b200 import evaluate_depth as ED
+    from movedepth_b200.options import MonodepthOptions
+    from oracle import evaluate as OE
+    gold = dict(np.load(os.path.join(GOLD, "eval_r18.npz")))
+    cfg = C.EVAL_CASE
+    argv = ["--height", str(cfg["H"]), "--width", str(cfg["W"]), "--num_depth_bins", str(cfg["D"]), "--batch_size", str(cfg["B"]),
+            "--weights_init", "scratch", "--convex_up", "--b200_conv_precision", "fp32", "--frame_ids", "0", "-1"]
+    opt = MonodepthOptions().parse(argv)
+    models = ED.build_models(opt)
+    for k, m in models.items():
+        fill_deterministic(m, salt=k + "/")
+    pred = ED.DepthPredictor(opt, models=models)
+    data, _, _ = C.step_inputs(cfg)
+    out = pred.predict(data)
+    mono = out["pred_disp_mono"].cpu().numpy()
+    np.testing.assert_allclose(mono, gold["pred_disp_mono"], rtol=1e-3, atol=1e-5)
+    dz = out["pred_disp_z"].cpu().numpy()
+    rel = np.abs(dz - gold["pred_disp_z"]) / np.abs(gold["pred_disp_z"])
+    assert (rel < 1e-3).mean() > 0.99, float((rel < 1e-3).mean())
+    gt = 1.0 / gold["pred_disp_z"][0]
+    np.testing.assert_allclose(ED.compute_errors(gt, 1.0 / dz[0]), OE.compute_errors(gt, 1.0 / dz[0]), rtol=1e-12)
+    assert ED.compute_fuse_errors(gt, 1.0 / dz[0], gt)[0] == 0.0          # oracle fusion picks the exact prediction
