@@ -204,7 +204,8 @@ int mvd_conv3d_c16c16_wgrad(const float* gy, const float* x, float* gw, void* wo
  *   mvd_bn_finalize   stats = [mean, invstd, scale = w*invstd, shift = b - mean*scale] (4C floats),
  *                     running_mean/var updated in place (unbiased variance), count = rows over all ranks
  *   mvd_bn_apply      y = relu?(x*scale + shift (+ residual))
- *   mvd_bn_bwd_reduce sums2 = [sum g (C), sum g*xhat (C)],  g = gy * (y > 0) when relu
+ *   mvd_bn_bwd_reduce sums2 = [sum g (C), sum g*xhat (C)],  g = gy * (y > 0) when relu; y may be NULL when the forward had
+ *                     no residual: the mask is then recomputed from x*scale + shift (bit-identical), saving one read
  *   mvd_bn_bwd_apply  gx = w*invstd*(g - sum g/count - xhat * sum g*xhat/count); gres = g (nullable);
  *                     gw = sum g*xhat, gb = sum g (nullable; pass NULL when sums2 was all-reduced)
  * ------------------------------------------------------------------------------------- */

@@ -123,6 +123,12 @@ __device__ __forceinline__ float4 masked(const float4& g, const float4& y, int r
     return make_float4(y.x > 0.f ? g.x : 0.f, y.y > 0.f ? g.y : 0.f, y.z > 0.f ? g.z : 0.f, y.w > 0.f ? g.w : 0.f);
 }
 
+// the forward's pre-activation x*scale + shift, bit-identical to what bn_apply_kernel clamped (no residual): its sign is
+// the ReLU mask, so the backward does not have to read y
+__device__ __forceinline__ float4 affine(const float4& v, const float4& sc, const float4& sh) {
+    return make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
+}
+
 // sums2: [sum g (C)][sum g*xhat (C)]
 __global__ void __launch_bounds__(THREADS) bn_bwd_reduce_kernel(const float* __restrict__ gy, const float* __restrict__ x,
                                                                 const float* __restrict__ y, const float* __restrict__ stats,
@@ -130,6 +136,8 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_reduce_kernel(const float* __r
     const Map m = make_map(C);
     const float4 mean = *reinterpret_cast<const float4*>(stats + 4 * m.quad);
     const float4 istd = *reinterpret_cast<const float4*>(stats + C + 4 * m.quad);
+    const float4 sc = *reinterpret_cast<const float4*>(stats + 2 * C + 4 * m.quad);
+    const float4 sh = *reinterpret_cast<const float4*>(stats + 3 * C + 4 * m.quad);
     float s[4] = {0.f, 0.f, 0.f, 0.f}, sx[4] = {0.f, 0.f, 0.f, 0.f};
     const float4* gp = reinterpret_cast<const float4*>(gy);
     const float4* xp = reinterpret_cast<const float4*>(x);
@@ -138,8 +146,8 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_reduce_kernel(const float* __r
          r += static_cast<long long>(gridDim.x) * m.rows_per_iter) {
         const long long i = r * m.q + m.quad;
         float4 g = __ldg(gp + i);
-        if (relu) g = masked(g, __ldg(yp + i), 1);
         const float4 v = __ldg(xp + i);
+        if (relu) g = masked(g, yp ? __ldg(yp + i) : affine(v, sc, sh), 1);
         add4(s, g);
         sx[0] = fmaf(g.x, (v.x - mean.x) * istd.x, sx[0]);
         sx[1] = fmaf(g.y, (v.y - mean.y) * istd.y, sx[1]);
@@ -158,6 +166,8 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const float* __re
     const Map m = make_map(C);
     const float4 mean = *reinterpret_cast<const float4*>(stats + 4 * m.quad);
     const float4 istd = *reinterpret_cast<const float4*>(stats + C + 4 * m.quad);
+    const float4 sc = *reinterpret_cast<const float4*>(stats + 2 * C + 4 * m.quad);
+    const float4 sh = *reinterpret_cast<const float4*>(stats + 3 * C + 4 * m.quad);
     float k[4], mg[4], mgx[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -182,8 +192,8 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const float* __re
          r += static_cast<long long>(gridDim.x) * m.rows_per_iter) {
         const long long i = r * m.q + m.quad;
         float4 g = __ldg(gp + i);
-        if (relu) g = masked(g, __ldg(yp + i), 1);
         const float4 v = __ldg(xp + i);
+        if (relu) g = masked(g, yp ? __ldg(yp + i) : affine(v, sc, sh), 1);
         float4 o;
         o.x = k[0] * (g.x - mg[0] - (v.x - mean.x) * istd.x * mgx[0]);
         o.y = k[1] * (g.y - mg[1] - (v.y - mean.y) * istd.y * mgx[1]);
@@ -242,7 +252,7 @@ int mvd_bn_apply(const float* x, const float* residual, const float* stats, floa
 int mvd_bn_bwd_reduce(const float* gy, const float* x, const float* y, const float* stats, double* sums2, long long M, int C,
                       int relu, void* stream) {
     using namespace mvd::bn;
-    MVD_REQUIRE(gy && x && stats && sums2 && (!relu || y), "null pointer argument");
+    MVD_REQUIRE(gy && x && stats && sums2, "null pointer argument");
     if (int rc = check(M, C)) return rc;
     cudaStream_t st = mvd::as_stream(stream);
     cudaError_t e = cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * C, st);
@@ -255,7 +265,7 @@ int mvd_bn_bwd_apply(const float* gy, const float* x, const float* y, const floa
                      const double* sums2, double count, float* gx, float* gres, float* gw, float* gb, long long M, int C,
                      int relu, void* stream) {
     using namespace mvd::bn;
-    MVD_REQUIRE(gy && x && stats && sums2 && gx && (!relu || y) && count > 0, "bad argument");
+    MVD_REQUIRE(gy && x && stats && sums2 && gx && count > 0, "bad argument");
     if (int rc = check(M, C)) return rc;
     bn_bwd_apply_kernel<<<grid_for(M, C), THREADS, 0, mvd::as_stream(stream)>>>(gy, x, y, stats, weight, sums2, count, gx, gres, gw,
                                                                                  gb, M, C, relu);

@@ -103,7 +103,7 @@ class _BNAct(torch.autograd.Function):
         y = torch.empty_like(xc)
         _lib.check(L.mvd_bn_apply(_p(xc), _p(rc_), _p(stats), _p(y), M, C, int(relu), _stream()), "mvd_bn_apply")
         _count_launch(4)
-        ctx.save_for_backward(xc, y if relu else None, stats, weight)
+        ctx.save_for_backward(xc, y if (relu and residual is not None) else None, stats, weight)   # no residual: mask from x
         ctx.cfg = (M, C, count, bool(relu), bool(sync), residual is not None)
         return y
 
