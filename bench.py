@@ -150,7 +150,12 @@ def run_own(args):
     torch.manual_seed(0)
     tr = Trainer(opt)
     tr.epoch = 9 if args.velocity else 0        # epoch > ztrans_start_epc switches to the velocity-guided range
-    host_batches = list(SyntheticKITTI(opt, BATCH, 4, seed=1 + rank))
+    # Synthetic KITTI-shape batches.  Default: band-limited noise images whose source frames are the reference frame shifted by
+    # 2 px per frame index (image-like statistics and a consistent inter-frame motion, so the self-supervised losses have a
+    # signal and the predicted pose / depth stay in the regime the cost-volume kernel is designed for).  `--noise` selects the
+    # U[0,1) white-noise images of SURVEY section 8(d): the dense kernels are data independent (same step time), but the
+    # networks then drift to arbitrary poses / saturated depths within ~10 steps and the cost volume's gather locality with them.
+    host_batches = list(SyntheticKITTI(opt, BATCH, 4, seed=1 + rank, smooth=not args.noise))
     dev_batches = [{k: v.cuda(non_blocking=True) for k, v in b.items()} for b in host_batches]
     h2d = sum(v.numel() * v.element_size() for v in host_batches[0].values())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
@@ -211,6 +216,10 @@ def run_own(args):
             [round(float(v), 4) for v in T[:, :3, 3].norm(dim=1)], [round(float(v), 4) for v in T[:, 2, 3]],
             float(pr.min()), float(pr.median()), float(pr.max()), [round(v * 1e3) for v in cv]), file=sys.stderr)
     ms_e2e = timed(host_batches, args.steps, read_loss=True)
+    cv_noise = []
+    if graph_pairs is not None and not args.noise:       # the same kernel inside steps fed with white-noise images, for the record
+        noise_batches = [{k: v.cuda() for k, v in b.items()} for b in SyntheticKITTI(opt, BATCH, 2, seed=101 + rank, smooth=False, pin=False)]
+        timed(noise_batches, min(args.steps, 6), read_loss=False, graph_pairs=graph_pairs, cv=cv_noise)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -224,7 +233,8 @@ def run_own(args):
     line = {
         "metric": METRIC, "value": frames / (ms * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (U[0,1) white noise, SURVEY 8d)" if args.noise else "synthetic (band-limited noise images, source frames shifted 2 px)",
         "config": {"workload": WORKLOAD, "precision": {"3xtf32": "convs on tensor cores with a 3-way TF32 operand split in the forward (near-fp32 outputs, "
                    "movedepth_b200/precision.py); gradients single-pass TF32 (PyTorch's default conv policy)",
                    "fp32": "fp32 everywhere (cuDNN SIMT convs)", "tf32": "cuDNN TF32 everywhere"}[args.precision],
@@ -237,7 +247,11 @@ def run_own(args):
                      "algorithmic_bytes": costvol_bytes(BATCH), "avg_launch_us": cv_ms * 1e3, "launches_timed": len(cv),
                      "launch_us_min_median_max": [min(cv) * 1e3, statistics.median(cv) * 1e3, max(cv) * 1e3],
                      "note": "timed inside the training step on the features / prior / pose the networks produce at that step; "
-                             "long epipolar footprints (large predicted translation) take the kernel's global-gather route"},
+                             "long epipolar footprints (large predicted translation) take the kernel's global-gather route",
+                     "white_noise_inputs": ({"avg_launch_us": sum(cv_noise) / len(cv_noise) * 1e3,
+                                             "frac": costvol_bytes(BATCH) / (sum(cv_noise) / len(cv_noise) * 1e-3) / 1e9 / pk["hbm_gbs"],
+                                             "launch_us_min_median_max": [min(cv_noise) * 1e3, statistics.median(cv_noise) * 1e3, max(cv_noise) * 1e3]}
+                                            if cv_noise else None)},
         "clocks": sampler.summary(),
         "e2e": {"value": frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
@@ -260,6 +274,7 @@ def main():
     ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "fp32", "tf32"])
     ap.add_argument("--velocity", action="store_true", help="use the velocity-guided hypothesis range (epoch > 8)")
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--noise", action="store_true", help="U[0,1) white-noise images (SURVEY 8d) instead of band-limited ones")
     ap.add_argument("--verbose", action="store_true", help="print the pose / prior statistics the cost-volume kernel saw")
     ap.add_argument("--no_graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--ncu_range", action="store_true", help="cudaProfilerStart/Stop around the device-timed steps")

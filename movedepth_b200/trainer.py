@@ -52,8 +52,11 @@ class SyntheticKITTI:
     """Iterable of synthetic KITTI-shape item dicts in pinned host memory (U[0,1) images, KITTI
     intrinsics at 4 scales), schema of movedepth/datasets/mono_dataset.py:134-154."""
 
-    def __init__(self, opt, batch_size, steps, seed=1, pin=True):
+    def __init__(self, opt, batch_size, steps, seed=1, pin=True, smooth=False, shift_px=2):
+        """smooth=True: band-limited noise (bicubic-upsampled low-resolution noise) with the source frames shifted by
+        `shift_px` pixels per frame index, i.e. images with image-like statistics and a consistent inter-frame motion."""
         self.opt, self.batch_size, self.steps, self.seed, self.pin = opt, batch_size, steps, seed, pin
+        self.smooth, self.shift_px = smooth, shift_px
 
     def __len__(self):
         return self.steps
@@ -61,8 +64,16 @@ class SyntheticKITTI:
     def make(self, g):
         o, B = self.opt, self.batch_size
         item = {}
+        base = None
         for f in o.frame_ids:
-            img = torch.rand(B, 3, o.height, o.width, generator=g)
+            if self.smooth:
+                if base is None:
+                    lo = torch.rand(B, 3, o.height // 8, (o.width + 64) // 8, generator=g)
+                    base = F.interpolate(lo, size=(o.height, o.width + 64), mode="bicubic", align_corners=False).clamp(0, 1)
+                off = 32 + self.shift_px * f
+                img = base[:, :, :, off:off + o.width].contiguous()
+            else:
+                img = torch.rand(B, 3, o.height, o.width, generator=g)
             for s in range(4):
                 im = img if s == 0 else F.interpolate(img, size=(o.height // 2 ** s, o.width // 2 ** s), mode="area")
                 item[("color", f, s)] = im
