@@ -1,3 +1,6 @@
+"""Tap-by-tap check of the tcgen05 weight gradient against torch's fp64 conv3d_weight (which reference tap, transposed or
+not, does each computed [co x ci] block match best?) -- the bring-up tool for the MN-major descriptor layout.
+   python tools/debug_wgrad_tc.py"""
 import os, sys, ctypes, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
