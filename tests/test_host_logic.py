@@ -238,6 +238,8 @@ def test_bn_act_routes_cpu_tensors_through_torch_batchnorm():
 def test_workspace_and_buffer_size_queries_need_no_gpu():
     """Pure host entry points of the C ABI: wgrad workspaces (per-tile partials) and the peer-exchange buffer."""
     from movedepth_b200 import _lib
+    from movedepth_b200.build import build
+    build()                                   # no-op when the in-tree library is current
     L = _lib.lib()
     assert L.mvd_peer_allreduce_buffer_bytes(8, 2048) == 4096 + 2 * 8 * 2048 * 8
     assert L.mvd_peer_allreduce_buffer_bytes(0, 2048) == 0
