@@ -129,6 +129,24 @@ int mvd_photometric_bwd(const float* gloss, const float* depth, const float* src
                         float* gdepth, float* gP, int B, int H, int W, float ssim_w, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Loss assembly on the per-pixel reprojection losses of mvd_photometric_fwd.
+ * Replaces: min over sources, identity auto-mask and masked mean -- movedepth/trainer.py:687-709
+ * (mono), 621-662 (multi-frame: no identity term, mask = ones), 589-609 (fused).
+ *   l0, l1 (nullable) : [n] losses of the source frames;  ident (nullable) : [n] identity loss,
+ *   already the minimum over the source frames;  noise (nullable) : [n] N(0,1) tie-break noise
+ *   reproj : [n] = min(l0, l1);  sel : [n] bytes (bit 0 = selected source, bit 1 = mask);
+ *   sums : 2 doubles = [sum(reproj*mask), sum(mask)] (zeroed inside);
+ *   loss : 1 float = sums[0] / (sums[1] + 1e-7)
+ * Backward: g0, g1 (nullable) [n] OVERWRITTEN = gloss[0] / (sums[1] + 1e-7) where the pixel is
+ * unmasked and the source was selected, else 0.
+ * ------------------------------------------------------------------------------------- */
+int mvd_reproj_select_fwd(const float* l0, const float* l1, const float* ident, const float* noise,
+                          float* reproj, unsigned char* sel, double* sums, float* loss, long long n,
+                          void* stream);
+int mvd_reproj_select_bwd(const float* gloss, const double* sums, const unsigned char* sel, float* g0,
+                          float* g1, long long n, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Fused multi-tensor Adam on a flat fp32 arena (torch.optim.Adam semantics, no amsgrad, no
  * weight decay; replaces optimizer.step() movedepth/trainer.py:137-141, 272).
  *   step_size = lr / (1 - beta1^t);  bias2 = sqrt(1 - beta2^t)

@@ -33,6 +33,8 @@ SIGNATURES = {
     "mvd_convex_up_bwd": ([_P] * 5 + [_I] * 4 + [_P], _I),
     "mvd_photometric_fwd": ([_P] * 8 + [_I] * 3 + [_F, _I, _P], _I),
     "mvd_photometric_bwd": ([_P] * 10 + [_I] * 3 + [_F, _P], _I),
+    "mvd_reproj_select_fwd": ([_P] * 8 + [_LL, _P], _I),
+    "mvd_reproj_select_bwd": ([_P] * 5 + [_LL, _P], _I),
     "mvd_split_tf32": ([_P, _P, _LL, _I, _I, _P], _I),
     "mvd_conv3d_c16o1_fwd": ([_P] * 3 + [_I] * 4 + [_P], _I),
     "mvd_conv3d_c16o1_dgrad": ([_P] * 3 + [_I] * 4 + [_P], _I),

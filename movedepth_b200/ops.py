@@ -237,6 +237,49 @@ def convex_upsample(depth, mask, scale=2):
     return _ConvexUp.apply(depth, mask, 2 ** scale)
 
 
+# ------------------------------------------------------------------------------------- loss assembly
+class _ReprojSelect(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, l0, l1, ident, noise):
+        l0 = _f32(l0).contiguous()
+        n = l0.numel()
+        l1c = _f32(l1).contiguous() if l1 is not None else None
+        identc = _f32(ident.detach()).contiguous() if ident is not None else None
+        noisec = _f32(noise.detach()).contiguous() if noise is not None else None
+        reproj = torch.empty_like(l0)
+        sel = torch.empty(n, device=l0.device, dtype=torch.uint8)
+        sums = torch.empty(2, device=l0.device, dtype=torch.float64)
+        loss = torch.empty((), device=l0.device, dtype=torch.float32)
+        rc = _lib.lib().mvd_reproj_select_fwd(_p(l0), _p(l1c), _p(identc), _p(noisec), _p(reproj), _p(sel), _p(sums), _p(loss), n,
+                                              _stream())
+        _lib.check(rc, "mvd_reproj_select_fwd")
+        launch_counter["n"] += 3
+        ctx.save_for_backward(sel, sums)
+        ctx.shape, ctx.two = l0.shape, l1 is not None
+        ctx.mark_non_differentiable(reproj)
+        return loss, reproj
+
+    @staticmethod
+    def backward(ctx, gloss, _greproj):
+        sel, sums = ctx.saved_tensors
+        gloss = _f32(gloss).contiguous()
+        g0 = torch.empty(ctx.shape, device=sel.device, dtype=torch.float32)
+        g1 = torch.empty(ctx.shape, device=sel.device, dtype=torch.float32) if ctx.two else None
+        rc = _lib.lib().mvd_reproj_select_bwd(_p(gloss), _p(sums), _p(sel), _p(g0), _p(g1), sel.numel(), _stream())
+        _lib.check(rc, "mvd_reproj_select_bwd")
+        launch_counter["n"] += 1
+        return g0, g1, None, None
+
+
+def reproj_select(per_src, ident=None, noise=None):
+    """min over the source frames' reprojection losses, identity auto-mask, masked mean -- one kernel.
+    per_src: list of 1 or 2 [B,1,H,W] loss maps; ident: [B,1,H,W] identity loss (already min over sources) or None
+    (mask = ones); noise: N(0,1) tie-break noise or None.  Returns (loss scalar, reproj [B,1,H,W]).
+    Reference: movedepth/trainer.py:687-709, 621-662, 589-609."""
+    assert 1 <= len(per_src) <= 2
+    return _ReprojSelect.apply(per_src[0], per_src[1] if len(per_src) == 2 else None, ident, noise)
+
+
 # ------------------------------------------------------------------------------------- reg3d output head
 class _Conv3dC16O1(torch.autograd.Function):
     @staticmethod

@@ -468,11 +468,14 @@ class Trainer:
                 l, warped = photo.reprojection_loss(depth, inputs[("color", f, 0)], tgt, K, invK, T, ssim_w)
                 outputs[("mvs_color", f)] = warped
                 per_src.append(l)
-            reproj = torch.cat(per_src, 1).min(1, keepdim=True)[0]
             if o.mask_mvs_auto and noise is not None and len(noise):
                 noise.pop(0)                         # drawn by the reference, the mask is then overwritten by ones
+            if len(per_src) <= 2:                    # min over sources + mean in one kernel (mask = ones)
+                loss, reproj = ops.reproj_select(per_src)
+            else:
+                reproj = torch.cat(per_src, 1).min(1, keepdim=True)[0]
+                loss = reproj.sum() / (reproj.numel() + 1e-7)
             outputs["mvs_reprojection_loss"] = reproj
-            loss = reproj.sum() / (reproj.numel() + 1e-7)
             if o.mvs_smooth_loss:
                 d = depth.unsqueeze(1)
                 sm = get_smooth_loss(d / (d.mean(2, True).mean(3, True) + 1e-7), tgt)
@@ -495,15 +498,18 @@ class Trainer:
                                                     outputs[("cam_T_cam", 0, f)], ssim_w)
                 outputs[("color", f, s)] = warped
                 per_src.append(l)
-            reproj = torch.cat(per_src, 1).min(1, keepdim=True)[0]
+            nz = None
             if ident is not None:
                 nz = noise.pop(0).to(self.device) if noise is not None else torch.randn_like(ident)
-                mask = (reproj <= ident + nz * 1e-5).float()            # argmin over [reproj, identity] == 0
+            if len(per_src) <= 2:                    # min over sources, auto-mask and masked mean in one kernel
+                loss, reproj = ops.reproj_select(per_src, ident, nz)
             else:
-                mask = torch.ones_like(reproj)
+                reproj = torch.cat(per_src, 1).min(1, keepdim=True)[0]
+                # argmin over [reproj, identity] == 0
+                mask = (reproj <= ident + nz * 1e-5).float() if ident is not None else torch.ones_like(reproj)
+                loss = (reproj * mask).sum() / (mask.sum() + 1e-7)
             if s == 0:
                 outputs["mono_reproj_loss"] = reproj
-            loss = (reproj * mask).sum() / (mask.sum() + 1e-7)
             norm_disp = disp / (disp.mean(2, True).mean(3, True) + 1e-7)
             sm = get_smooth_loss(norm_disp, inputs[("color", 0, s)])
             losses["mono_smooth_loss/{}".format(s)] = sm
@@ -524,13 +530,14 @@ class Trainer:
                                                 outputs[("cam_T_cam", 0, f)].detach(), 0)
             outputs[("mvs_color_fuse", f)] = warped
             per_src.append(l)
-        reproj = torch.cat(per_src, 1).min(1, keepdim=True)[0]
+        ident = nz = None
         if o.mask_mvs_auto:
             ident = self._identity_min(inputs, 0)
             nz = noise.pop(0).to(self.device) if noise is not None else torch.randn_like(ident)
-            mask = (reproj <= ident + nz * 1e-5).float()
-        else:
-            mask = torch.ones_like(reproj)
+        if len(per_src) <= 2:
+            return ops.reproj_select(per_src, ident, nz)[0]
+        reproj = torch.cat(per_src, 1).min(1, keepdim=True)[0]
+        mask = (reproj <= ident + nz * 1e-5).float() if ident is not None else torch.ones_like(reproj)
         return (reproj * mask).sum() / (mask.sum() + 1e-7)
 
     # ------------------------------------------------------------------ validation / logging / checkpoints

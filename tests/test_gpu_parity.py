@@ -597,3 +597,27 @@ def test_depth_predictor_matches_reference_golden():
     gt = 1.0 / gold["pred_disp_z"][0]
     np.testing.assert_allclose(ED.compute_errors(gt, 1.0 / dz[0]), OE.compute_errors(gt, 1.0 / dz[0]), rtol=1e-12)
     assert ED.compute_fuse_errors(gt, 1.0 / dz[0], gt)[0] == 0.0          # oracle fusion picks the exact prediction
+
+
+# ---------------------------------------------------------------------------------------------- loss assembly
+@pytest.mark.parametrize("nsrc,automask", [(1, True), (2, True), (2, False), (1, False)])
+def test_reproj_select_matches_the_tensor_formula(ops, nsrc, automask):
+    """min over sources + identity auto-mask + masked mean (trainer.py:687-709) in one kernel vs the tensor code it
+    replaces, values and the gradients routed to the selected source."""
+    gen = torch.Generator().manual_seed(12)
+    B, H, W = 2, 24, 40
+    ls = [torch.rand(B, 1, H, W, generator=gen) for _ in range(nsrc)]
+    ident = torch.rand(B, 1, H, W, generator=gen) * 0.8
+    nz = torch.randn(B, 1, H, W, generator=gen)
+    want_in = [l.clone().requires_grad_(True) for l in ls]
+    reproj = torch.cat(want_in, 1).min(1, keepdim=True)[0]
+    mask = (reproj <= ident + nz * 1e-5).float() if automask else torch.ones_like(reproj)
+    want = (reproj * mask).sum() / (mask.sum() + 1e-7)
+    (want * 3.0).backward()
+    got_in = [g(l).requires_grad_(True) for l in ls]
+    loss, rp = ops.reproj_select(got_in, g(ident) if automask else None, g(nz) if automask else None)
+    (loss * 3.0).backward()
+    torch.testing.assert_close(rp.cpu(), reproj.detach())
+    torch.testing.assert_close(loss.detach().cpu(), want.detach(), rtol=1e-5, atol=1e-7)
+    for a, b in zip(got_in, want_in):
+        torch.testing.assert_close(a.grad.cpu(), b.grad, rtol=1e-5, atol=1e-9)
