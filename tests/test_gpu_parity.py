@@ -621,3 +621,27 @@ def test_reproj_select_matches_the_tensor_formula(ops, nsrc, automask):
     torch.testing.assert_close(loss.detach().cpu(), want.detach(), rtol=1e-5, atol=1e-7)
     for a, b in zip(got_in, want_in):
         torch.testing.assert_close(a.grad.cpu(), b.grad, rtol=1e-5, atol=1e-9)
+
+
+def test_reg3d_first_layer_kernels_are_linear_at_full_size(ops):
+    """Size-independent property at BASELINE config 2 (volume [6,16,96,48,160]): the tcgen05 3xTF32 forward is linear in
+    its input to fp32 accuracy, conv(2*x1 + x2) == 2*conv(x1) + conv(x2); the TF32 weight gradient is bilinear to TF32
+    accuracy; the 16->1 head (exact fp32) likewise."""
+    gen = torch.Generator(device=DEV).manual_seed(8)
+    shape = (6, 16, 96, 48, 160)
+    cl = torch.channels_last_3d
+    x1 = torch.randn(shape, device=DEV, generator=gen).contiguous(memory_format=cl)
+    x2 = torch.randn(shape, device=DEV, generator=gen).contiguous(memory_format=cl)
+    w = 0.1 * torch.randn(16, 16, 3, 3, 3, device=DEV, generator=gen)
+    lhs = ops.c16c16_conv_tc(2.0 * x1 + x2, w, 0, 3)
+    rhs = 2.0 * ops.c16c16_conv_tc(x1, w, 0, 3) + ops.c16c16_conv_tc(x2, w, 0, 3)
+    scale = float(rhs.abs().max())
+    assert float((lhs - rhs).abs().max()) < 1e-4 * scale
+    gw_l = ops.c16c16_wgrad_tc(x2, 2.0 * x1 + x2)
+    gw_r = 2.0 * ops.c16c16_wgrad_tc(x2, x1) + ops.c16c16_wgrad_tc(x2, x2)
+    assert float((gw_l - gw_r).abs().max()) < 5e-3 * float(gw_r.abs().max())
+    w1 = 0.1 * torch.randn(1, 16, 3, 3, 3, device=DEV, generator=gen)
+    yl = ops.conv3d_c16_to_1(2.0 * x1 + x2, w1)
+    yr = 2.0 * ops.conv3d_c16_to_1(x1, w1) + ops.conv3d_c16_to_1(x2, w1)
+    assert yl.shape == (6, 1, 96, 48, 160)
+    assert float((yl - yr).abs().max()) < 1e-4 * float(yr.abs().max())
