@@ -147,6 +147,39 @@ int mvd_reproj_select_bwd(const float* gloss, const double* sums, const unsigned
                           float* g1, long long n, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Loss glue (csrc/lossglue.cu): the remaining per-scale tensor code of the loss section.
+ *
+ * mvd_disp_to_depth_{fwd,bwd}: F.interpolate(disp, [H,W], bilinear, align_corners=False) followed by
+ * disp_to_depth (movedepth/trainer.py:512-515, layers.py:400-409):
+ *   depth[b,y,x] = 1 / (inv_far + range * up(disp)[b,y,x]),  inv_far = 1/max_depth, range = 1/min_depth - 1/max_depth
+ *   disp [B,hs,ws], depth/gdepth [B,H,W] (H, W integer multiples of hs, ws), gdisp [B,hs,ws] OVERWRITTEN.
+ *
+ * mvd_smooth_loss_{fwd,bwd}: get_smooth_loss (layers.py:630-643), with normalize != 0 preceded by the mean
+ * normalisation disp / (disp.mean(2).mean(3) + 1e-7) of trainer.py:712-713 (mono) / 663-666 (mvs_smooth_loss):
+ *   disp [B,h,w], img [B,3,h,w] (NCHW), loss: 1 float, work: mvd_smooth_loss_workspace_bytes(B) bytes written by fwd
+ *   and read by bwd; dot: B doubles of scratch; gdisp [B,h,w] OVERWRITTEN = gloss[0] * d loss / d disp.
+ *
+ * mvd_masked_smooth_l1_{fwd,bwd}: the masked-augmentation consistency term (trainer.py:398-400):
+ *   sel = bilinear(box mask [H,W] -> [h,w], align_corners=True) != 0, box = fh x fw zeros at box_xy = (x, y) (device int64[2],
+ *   layers.py:52-69); loss = weight * mean over sel of smooth_l1(a - b); sel [B*h*w] bytes and sums (2 doubles) are
+ *   written by fwd and read by bwd; ga, gb [B,h,w] OVERWRITTEN (gb may be NULL).
+ * ------------------------------------------------------------------------------------- */
+int mvd_disp_to_depth_fwd(const float* disp, float* depth, int B, int hs, int ws, int H, int W, float inv_far,
+                          float range, void* stream);
+int mvd_disp_to_depth_bwd(const float* gdepth, const float* depth, float* gdisp, int B, int hs, int ws, int H,
+                          int W, float range, void* stream);
+long long mvd_smooth_loss_workspace_bytes(int B);
+int mvd_smooth_loss_fwd(const float* disp, const float* img, double* work, float* loss, int B, int h, int w,
+                        int normalize, void* stream);
+int mvd_smooth_loss_bwd(const float* gloss, const float* disp, const float* img, const double* work, double* dot,
+                        float* gdisp, int B, int h, int w, int normalize, void* stream);
+int mvd_masked_smooth_l1_fwd(const float* a, const float* b, const long long* box_xy, unsigned char* sel,
+                             double* sums, float* loss, int B, int h, int w, int H, int W, int fh, int fw,
+                             float weight, void* stream);
+int mvd_masked_smooth_l1_bwd(const float* gloss, const float* a, const float* b, const unsigned char* sel,
+                             const double* sums, float* ga, float* gb, long long n, float weight, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Fused multi-tensor Adam on a flat fp32 arena (torch.optim.Adam semantics, no amsgrad, no
  * weight decay; replaces optimizer.step() movedepth/trainer.py:137-141, 272).
  *   step_size = lr / (1 - beta1^t);  bias2 = sqrt(1 - beta2^t)

@@ -35,6 +35,13 @@ SIGNATURES = {
     "mvd_photometric_bwd": ([_P] * 10 + [_I] * 3 + [_F, _P], _I),
     "mvd_reproj_select_fwd": ([_P] * 8 + [_LL, _P], _I),
     "mvd_reproj_select_bwd": ([_P] * 5 + [_LL, _P], _I),
+    "mvd_disp_to_depth_fwd": ([_P, _P] + [_I] * 5 + [_F, _F, _P], _I),
+    "mvd_disp_to_depth_bwd": ([_P, _P, _P] + [_I] * 5 + [_F, _P], _I),
+    "mvd_smooth_loss_workspace_bytes": ([_I], _LL),
+    "mvd_smooth_loss_fwd": ([_P] * 4 + [_I] * 4 + [_P], _I),
+    "mvd_smooth_loss_bwd": ([_P] * 6 + [_I] * 4 + [_P], _I),
+    "mvd_masked_smooth_l1_fwd": ([_P] * 6 + [_I] * 7 + [_F, _P], _I),
+    "mvd_masked_smooth_l1_bwd": ([_P] * 7 + [_LL, _F, _P], _I),
     "mvd_split_tf32": ([_P, _P, _LL, _I, _I, _P], _I),
     "mvd_conv3d_c16o1_fwd": ([_P] * 3 + [_I] * 4 + [_P], _I),
     "mvd_conv3d_c16o1_dgrad": ([_P] * 3 + [_I] * 4 + [_P], _I),

@@ -1177,7 +1177,7 @@ int mvd_conv3d_c16o1_fwd(const float* x, const float* w, float* y, int B, int D,
     CUtensorMap map;
     if (int rc = make_x_map(&map, x, a)) return rc;
     if (int rc = upload_weights(w, st)) return rc;
-    static bool attr_done = false;
+    bool attr_done = false;       // set on every call (a few hundred ns): the attribute is per device, a process-wide latch is not
     if (!attr_done) {
         cudaFuncSetAttribute(conv3d_c16o1_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
         attr_done = true;
@@ -1222,7 +1222,7 @@ int mvd_conv3d_c16o1_wgrad(const float* gy, const float* x, float* gw, void* wor
                 static_cast<long long>(items) * NW * 4);
     CUtensorMap map;
     if (int rc = make_x_map(&map, x, a)) return rc;
-    static bool attr_done = false;
+    bool attr_done = false;       // set on every call (a few hundred ns): the attribute is per device, a process-wide latch is not
     if (!attr_done) {
         cudaFuncSetAttribute(conv3d_c16o1_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WGRAD_SMEM);
         attr_done = true;
@@ -1252,7 +1252,7 @@ int mvd_conv3d_c16c16(const float* in, const float* w, float* out, int B, int D,
     pa.x = in;
     CUtensorMap map;
     if (int rc = make_x_map(&map, in, pa)) return rc;
-    static bool attr_done = false;
+    bool attr_done = false;       // set on every call (a few hundred ns): the attribute is per device, a process-wide latch is not
     if (!attr_done) {
         cudaFuncSetAttribute(conv3d_c16c16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
         cudaFuncSetAttribute(conv3d_c16c16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
@@ -1296,7 +1296,7 @@ int mvd_conv3d_c16c16_wgrad(const float* gy, const float* x, float* gw, void* wo
         const uint32_t box[5] = {C, TW, TH, 1, 1};
         if (int rc = mvd::make_f32_tensor_map(&map_gy, gy, 5, dims, str, box, 64)) return rc;
     }
-    static bool attr_done = false;
+    bool attr_done = false;       // set on every call (a few hundred ns): the attribute is per device, a process-wide latch is not
     if (!attr_done) {
         cudaFuncSetAttribute(conv3d_c16c16_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
         attr_done = true;
@@ -1346,7 +1346,7 @@ int mvd_conv3d_c16c16_tc(const float* in, const float* w, float* out, int B, int
         const uint32_t box[5] = {C, tc::HW, tc::HH, 1, 1};
         if (int rc = mvd::make_f32_tensor_map(&map, in, 5, dims, str, box, 64)) return rc;
     }
-    static bool attr_done = false;
+    bool attr_done = false;       // set on every call (a few hundred ns): the attribute is per device, a process-wide latch is not
     if (!attr_done) {
         cudaFuncSetAttribute(tc::conv3d_c16c16_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<1>::ALLOC);
         cudaFuncSetAttribute(tc::conv3d_c16c16_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<3>::ALLOC);
@@ -1405,7 +1405,7 @@ int mvd_conv3d_c16c16_wgrad_tc(const float* gy, const float* x, float* gw, void*
     const uint32_t boxx[5] = {2 * C, tc::WP / 2, tc::HH, 1, 1}, boxg[5] = {2 * C, tc::WP / 2, tc::TH, 1, 1};
     if (int rc = mvd::make_f32_tensor_map(&map_x, x, 5, dims, str, boxx, 12832)) return rc;
     if (int rc = mvd::make_f32_tensor_map(&map_gy, gy, 5, dims, str, boxg, 12832)) return rc;
-    static bool attr_done = false;
+    bool attr_done = false;       // set on every call (a few hundred ns): the attribute is per device, a process-wide latch is not
     if (!attr_done) {
         cudaFuncSetAttribute(tc::conv3d_c16c16_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::WgCfg::ALLOC);
         attr_done = true;

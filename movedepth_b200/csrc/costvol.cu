@@ -939,7 +939,7 @@ static int costvol_grouped_launch(bool bwd, CvArgs a, int C, int G, int flags, c
         cudaError_t e = cudaMemsetAsync(a.gref, 0, sizeof(float) * a.B * a.h * a.w * CV_C, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(a.gsrc, 0, sizeof(float) * a.B * a.h * a.w * CV_C, st);
         if (e != cudaSuccess) return fail(static_cast<int>(e), "costvol bwd memset: %s", cudaGetErrorString(e));
-        static bool attr_done = false;
+        bool attr_done = false;       // per call: the attribute is per device, a process-wide latch is not
         if (!attr_done) {
             cudaFuncSetAttribute(costvol_grouped_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             attr_done = true;
@@ -997,7 +997,7 @@ static int costvol_grouped_launch(bool bwd, CvArgs a, int C, int G, int flags, c
     if (!a.tma_store) map_out = map_ref;        // unused by the kernel, but must be a valid descriptor
     const int smem = f3::Smem::ALLOC;
     const int grid = min(a.num_tiles, sm_count() * 2);
-    static bool attr_done = false;
+    bool attr_done = false;       // per call: the attribute is per device, a process-wide latch is not
     if (!attr_done) {
         cudaFuncSetAttribute(costvol_grouped_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         attr_done = true;

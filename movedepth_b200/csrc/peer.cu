@@ -7,6 +7,8 @@
 //
 // Symmetric buffer layout (same on every rank; allocated by the caller, zero-initialised):
 //   [0, 8)                       epoch counter of this rank (local)
+//   [8, 16)                      time-out marker: set to the epoch at which a peer's flag did not arrive within ~4 s
+//                                (the wait is bounded so that a dead or never-launched peer cannot hang the GPU)
 //   [64, 64 + 8*world)           flags: flag[p] = last epoch rank p has published into this buffer
 //   [4096, ...)                  data [2 slots][world][nmax] doubles      (slot = epoch & 1)
 #include "common.cuh"
@@ -15,6 +17,7 @@
 namespace mvd {
 
 constexpr int PEER_HEADER = 4096;
+constexpr long long PEER_SPIN_LIMIT = 8000000000ll;       // SM clocks (~4 s at 1.97 GHz)
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -55,7 +58,12 @@ __global__ void __launch_bounds__(256) peer_allreduce_f64_kernel(const double* _
     if (tid < world) {
         st_release_sys(reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(peers[tid]) + 64) + rank, epoch);
         const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine + 64) + tid;
+        const long long t0 = clock64();
         while (ld_acquire_sys(f) < epoch) {
+            if (clock64() - t0 > PEER_SPIN_LIMIT) {
+                reinterpret_cast<unsigned long long*>(mine)[1] = epoch;
+                break;
+            }
         }
     }
     __syncthreads();

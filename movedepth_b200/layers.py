@@ -77,10 +77,16 @@ def hypothesis_ratios(ndepth, scale, device, type="inverse"):
         return 1.0 / (1.0 / (1 + s) + ((1 + s) - 1.0 / (1 + s)) * k)
     if type == "linear":
         return 1.0 / (1 + s) + ((1 + s) - 1.0 / (1 + s)) * k
-    if type == "log":
-        lo, hi = torch.log(1.0 / (1 + s)), torch.log(1 + s)
-        return torch.exp(lo + (hi - lo) * k)
+    if type == "log":       # affine map of a fixed 0.1 -> 1 geometric ramp (layers.py:276-282)
+        return 1.0 / (1 + s) + ((1 + s) - 1.0 / (1 + s)) * _log_ramp(ndepth, device).reshape(1, -1)
     raise NotImplementedError(type)
+
+
+def _log_ramp(ndepth, device):
+    """itv_k = exp(log(0.1) + log(10) * k / (D-1)), evaluated in fp32 like the reference's FloatTensor loop."""
+    k = torch.arange(ndepth, dtype=torch.float32)
+    lo, span = torch.log(torch.tensor([0.1])), torch.log(torch.tensor([1 / 0.1]))
+    return torch.exp(lo + span * k / (ndepth - 1)).to(device)
 
 
 def _schedule(prior_depth, ndepth, s, type):
@@ -93,7 +99,7 @@ def _schedule(prior_depth, ndepth, s, type):
         if type == "linear":
             return lo + (hi - lo) * k
         if type == "log":
-            return torch.exp(torch.log(lo) + (torch.log(hi) - torch.log(lo)) * k)
+            return lo + (hi - lo) * _log_ramp(ndepth, prior_depth.device).reshape(1, -1, 1, 1)
         raise NotImplementedError(type)
 
 
@@ -233,7 +239,10 @@ def upsample(x):
 
 # ------------------------------------------------------------------ photometric pieces
 def get_smooth_loss(disp, img):
-    """Edge-aware first-order smoothness.  Reference: movedepth/layers.py:630-643."""
+    """Edge-aware first-order smoothness.  Reference: movedepth/layers.py:630-643.  Device tensors go through the
+    `mvd_smooth_loss` kernels; the tensor formula below serves host-side callers."""
+    if disp.is_cuda and disp.dim() == 4 and disp.shape[1] == 1 and img.shape[1] == 3 and not img.requires_grad:
+        return ops.smooth_loss(disp, img, normalize=False)
     dx = (disp[:, :, :, :-1] - disp[:, :, :, 1:]).abs()
     dy = (disp[:, :, :-1, :] - disp[:, :, 1:, :]).abs()
     ix = (img[:, :, :, :-1] - img[:, :, :, 1:]).abs().mean(1, keepdim=True)

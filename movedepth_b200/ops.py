@@ -473,3 +473,108 @@ def photometric_identity(src, tgt, ssim_w=0.85):
     _lib.check(rc, "mvd_photometric_fwd(identity)")
     launch_counter["n"] += 1
     return loss
+
+
+# ------------------------------------------------------------------------------------- loss glue
+class _DispToDepth(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, H, W, min_depth, max_depth):
+        B, _, hs, ws = disp.shape
+        disp = _f32(disp).contiguous()
+        inv_far, rng = 1.0 / max_depth, 1.0 / min_depth - 1.0 / max_depth
+        depth = torch.empty((B, 1, H, W), device=disp.device, dtype=torch.float32)
+        rc = _lib.lib().mvd_disp_to_depth_fwd(_p(disp), _p(depth), B, hs, ws, H, W, inv_far, rng, _stream())
+        _lib.check(rc, "mvd_disp_to_depth_fwd")
+        launch_counter["n"] += 1
+        ctx.save_for_backward(depth)
+        ctx.meta = (B, hs, ws, H, W, rng)
+        return depth
+
+    @staticmethod
+    def backward(ctx, gdepth):
+        depth, = ctx.saved_tensors
+        B, hs, ws, H, W, rng = ctx.meta
+        gdepth = _f32(gdepth).contiguous()
+        gdisp = torch.empty((B, 1, hs, ws), device=depth.device, dtype=torch.float32)
+        rc = _lib.lib().mvd_disp_to_depth_bwd(_p(gdepth), _p(depth), _p(gdisp), B, hs, ws, H, W, rng, _stream())
+        _lib.check(rc, "mvd_disp_to_depth_bwd")
+        launch_counter["n"] += 1
+        return gdisp, None, None, None, None
+
+
+def disp_to_depth_full(disp, height, width, min_depth, max_depth):
+    """Sigmoid disparity [B,1,hs,ws] -> depth [B,1,height,width]: bilinear upsampling (align_corners=False) and
+    disp_to_depth in one kernel.  Reference: movedepth/trainer.py:512-515, layers.py:400-409."""
+    return _DispToDepth.apply(disp, int(height), int(width), float(min_depth), float(max_depth))
+
+
+class _SmoothLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, disp, img, normalize):
+        B, _, h, w = disp.shape
+        disp, img = _f32(disp).contiguous(), _f32(img.detach()).contiguous()
+        assert img.shape == (B, 3, h, w), (disp.shape, img.shape)
+        work = torch.empty(B + 2, device=disp.device, dtype=torch.float64)
+        loss = torch.empty((), device=disp.device, dtype=torch.float32)
+        rc = _lib.lib().mvd_smooth_loss_fwd(_p(disp), _p(img), _p(work), _p(loss), B, h, w, int(normalize), _stream())
+        _lib.check(rc, "mvd_smooth_loss_fwd")
+        launch_counter["n"] += 3 if normalize else 2
+        ctx.save_for_backward(disp, img, work)
+        ctx.normalize = int(normalize)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        disp, img, work = ctx.saved_tensors
+        B, _, h, w = disp.shape
+        gloss = _f32(gloss).contiguous()
+        dot = torch.empty(B, device=disp.device, dtype=torch.float64)
+        gdisp = torch.empty_like(disp)
+        rc = _lib.lib().mvd_smooth_loss_bwd(_p(gloss), _p(disp), _p(img), _p(work), _p(dot), _p(gdisp), B, h, w, ctx.normalize,
+                                            _stream())
+        _lib.check(rc, "mvd_smooth_loss_bwd")
+        launch_counter["n"] += 2
+        return gdisp, None, None
+
+
+def smooth_loss(disp, img, normalize=False):
+    """Edge-aware first-order smoothness of `disp` [B,1,h,w] against `img` [B,3,h,w] (movedepth/layers.py:630-643); with
+    normalize=True the disparity is first divided by its per-item mean + 1e-7 (movedepth/trainer.py:712-713)."""
+    return _SmoothLoss.apply(disp, img, bool(normalize))
+
+
+class _MaskedSmoothL1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, box_xy, H, W, fh, fw, weight):
+        B, h, w = a.shape
+        a, b = _f32(a).contiguous(), _f32(b).contiguous()
+        assert box_xy.dtype == torch.int64 and box_xy.numel() == 2
+        sel = torch.empty(B * h * w, device=a.device, dtype=torch.uint8)
+        sums = torch.empty(2, device=a.device, dtype=torch.float64)
+        loss = torch.empty((), device=a.device, dtype=torch.float32)
+        rc = _lib.lib().mvd_masked_smooth_l1_fwd(_p(a), _p(b), _p(box_xy), _p(sel), _p(sums), _p(loss), B, h, w, H, W, fh, fw,
+                                                 float(weight), _stream())
+        _lib.check(rc, "mvd_masked_smooth_l1_fwd")
+        launch_counter["n"] += 2
+        ctx.save_for_backward(a, b, sel, sums)
+        ctx.weight = float(weight)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        a, b, sel, sums = ctx.saved_tensors
+        gloss = _f32(gloss).contiguous()
+        ga = torch.empty_like(a)
+        gb = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        rc = _lib.lib().mvd_masked_smooth_l1_bwd(_p(gloss), _p(a), _p(b), _p(sel), _p(sums), _p(ga), _p(gb), a.numel(), ctx.weight,
+                                                 _stream())
+        _lib.check(rc, "mvd_masked_smooth_l1_bwd")
+        launch_counter["n"] += 1
+        return ga, gb, None, None, None, None, None, None
+
+
+def masked_smooth_l1(a, b, box_xy, height, width, box_h, box_w, weight=1.0):
+    """weight * mean over the selected pixels of smooth_l1(a - b); a, b: [B,h,w] depth maps; a low-resolution pixel is
+    selected when the bilinear (align_corners=True) resize of the [height,width] box mask (zeros in the box_h x box_w box
+    at box_xy = device int64 (x, y)) is non-zero there.  Reference: movedepth/trainer.py:398-400."""
+    return _MaskedSmoothL1.apply(a, b, box_xy, int(height), int(width), int(box_h), int(box_w), float(weight))

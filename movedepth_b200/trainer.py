@@ -163,25 +163,22 @@ class Trainer:
         if o.num_depth_bins >= 8:
             m["reg3d"] = networks.reg3d(o.reg3d_c, o.reg3d_c, 3)
         else:
-            m["reg3d"] = networks.reg2d(o.reg3d_c, 8)
-        m["up"] = convex_upsample_layer(8 * 2 ** o.prior_scale, o.prior_scale)
+            m["reg3d"] = networks.reg2d(o.reg3d_c, o.reg3d_c)      # same constructor arguments as evaluate_depth.build_models
+        if o.convex_up:
+            m["up"] = convex_upsample_layer(8 * 2 ** o.prior_scale, o.prior_scale)
         for k in m:
             if o.ddp and self.world_size > 1:
                 m[k] = nn.SyncBatchNorm.convert_sync_batchnorm(m[k])
             PR.adopt(m[k])                                # torchvision convs follow the precision policy too
             m[k].to(self.device)
         self.models = m
-        self.parameters_to_train = [p for k in GROUP0 for p in m[k].parameters()]
-        self.mvs_parameters_to_train = [p for k in GROUP1 for p in m[k].parameters()]
+        self.parameters_to_train = [p for k in GROUP0 if k in m for p in m[k].parameters()]
+        self.mvs_parameters_to_train = [p for k in GROUP1 if k in m for p in m[k].parameters()]
 
-        if o.load_weights_folder is not None:
-            self.load_model()
-        if o.mono_weights_folder is not None:
-            self.load_mono_model()
-        if o.ddp and self.world_size > 1:                 # what the DDP constructor's broadcast does
-            for k in m:
-                for t in list(m[k].parameters()) + list(m[k].buffers()):
-                    dist.broadcast(t.data, 0)
+        if o.mask_mvs_geo:
+            # the reference reads outputs[("geo_mask", f)] (trainer.py:654-656) but nothing ever writes it: KeyError there
+            raise NotImplementedError("--mask_mvs_geo: the reference never produces the geo_mask it multiplies in "
+                                      "(movedepth/trainer.py:654-656 raises KeyError); not supported")
 
         # ---- flat arenas + fused Adam (replaces optim.Adam + StepLR, trainer.py:137-141)
         self.arenas = [FlatArena(self.parameters_to_train, self.device),
@@ -190,6 +187,18 @@ class Trainer:
         self.opt_step = 0
         self.epoch = 0
         self.step = 0
+
+        # checkpoints are loaded into the arenas (parameters are views of them), Adam moments included
+        if o.load_weights_folder is not None:
+            self.load_model()
+        if o.mono_weights_folder is not None:
+            self.load_mono_model()
+        if o.ddp and self.world_size > 1:                 # what the DDP constructor's broadcast does
+            for a in self.arenas:
+                dist.broadcast(a.data, 0)
+            for k in m:
+                for t in m[k].buffers():
+                    dist.broadcast(t.data, 0)
 
         # ---- data: any iterable of item dicts; synthetic KITTI-shape tensors by default
         steps = 100
@@ -201,6 +210,14 @@ class Trainer:
             o.log_frequency = max(1, o.log_frequency // self.world_size)
         self._aug_box = torch.zeros(2, dtype=torch.int64, device=self.device)
         self._static_inputs, self._graphs, self._graph_warm, self._graph_pool, self._graph_stream = None, {}, {}, None, None
+        # auto-mask tie-break noise (trainer.py:600,641,698 draw it on the CPU and copy it over): a device generator of this
+        # trainer fills static buffers OUTSIDE the captured graph, so eager and graph steps with the same seed see the same
+        # noise and a replay never re-uses the noise of the capture
+        self.noise_generator = torch.Generator(device=self.device)
+        self.noise_generator.manual_seed(torch.initial_seed() + self.rank)
+        self._noise_buf = None
+        if self.rank == 0:
+            self.save_opts()
         self.set_train()
 
     # ------------------------------------------------------------------ mode switches
@@ -241,17 +258,22 @@ class Trainer:
             if early or late:
                 if self.rank == 0:
                     self.log_time(batch_idx, time.time() - t0, float(losses["loss"]))
+                if "depth_gt" in inputs:
+                    self.compute_depth_losses(inputs, outputs, losses)
+                if self.rank == 0:
                     self.log("train", inputs, outputs, losses)
+                self.val()
             if self.opt.save_intermediate_models and late:
                 self.save_model(save_step=True)
             self.step += 1
 
     def train_step(self, inputs, noise=None, mask_xy=None):
         """process_batch + zero_grad + backward + optimizer.step (movedepth/trainer.py:269-272).
-        With `--b200_cuda_graph` (and no test overrides) the whole forward + backward + gradient exchange is one
-        CUDA graph replayed per step: `inputs` are copied into static device buffers first."""
-        if getattr(self.opt, "b200_cuda_graph", False) and noise is None and mask_xy is None:
-            return self._graph_step(inputs)
+        With `--b200_cuda_graph` the whole forward + backward + gradient exchange is one CUDA graph replayed per step:
+        `inputs` (and the `noise` / `mask_xy` overrides of the parity tests, if given) are copied into static device
+        buffers first."""
+        if getattr(self.opt, "b200_cuda_graph", False):
+            return self._graph_step(inputs, noise, mask_xy)
         outputs, losses = self._forward_backward(inputs, noise, mask_xy)
         self._optimizer_step()
         return outputs, losses
@@ -278,26 +300,51 @@ class Trainer:
         for a, lr in zip(self.arenas, self.current_lrs()):
             ops.adam_step(a.data, a.grad, a.exp_avg, a.exp_avg_sq, self.opt_step, lr, grad_scale=1.0 / self.world_size)
 
+    # ------------------------------------------------------------------ random draws of a step
+    def _num_noise_maps(self):
+        o = self.opt
+        return (0 if o.disable_automasking else len(o.scales)) + (2 if o.mask_mvs_auto else 0)
+
+    def _draw_noise(self, B, given=None):
+        """The step's N(0,1) tie-break maps as a list of [B,1,H,W] views of one static buffer: drawn from this trainer's
+        device generator, or copied from `given` (parity tests)."""
+        o, n = self.opt, self._num_noise_maps()
+        if self._noise_buf is None or self._noise_buf.shape[1] != B:
+            self._noise_buf = torch.zeros(max(n, 1), B, 1, o.height, o.width, device=self.device)
+        if given is not None:
+            for i, t in enumerate(list(given)[:n]):
+                self._noise_buf[i].copy_(t, non_blocking=True)
+        elif n:
+            self._noise_buf.normal_(generator=self.noise_generator)
+        return [self._noise_buf[i] for i in range(n)]
+
+    def _set_aug_box(self, mask_xy=None):
+        """Corner of the masked-augmentation box (layers.py:64-65: np.random.randint, x before y) -> device."""
+        o = self.opt
+        fh, fw = o.height // 3, o.width // 3
+        if mask_xy is None:
+            mask_xy = (np.random.randint(0, o.width - fw), np.random.randint(0, o.height - fh))
+        # pageable source: the copy is staged before the call returns, so the host may run ahead safely
+        self._aug_box.copy_(torch.tensor([int(mask_xy[0]), int(mask_xy[1])], dtype=torch.int64))
+
     # ------------------------------------------------------------------ CUDA-graph step
     GRAPH_WARMUP = 3          # eager steps before capture (cuDNN autotuning, lazy initialisation, NCCL warm-up)
 
-    def _stage_inputs(self, inputs):
-        """host (pinned) or device item dict -> the static device buffers the graph reads."""
+    def _stage_inputs(self, inputs, noise=None, mask_xy=None):
+        """host (pinned) or device item dict -> the static device buffers the graph reads; the step's random draws
+        (tie-break noise, augmentation box) are made here, outside the graph."""
         if self._static_inputs is None:
             self._static_inputs = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device)
                                    for k, v in inputs.items() if torch.is_tensor(v)}
-            self._aug_box_host = torch.zeros(2, dtype=torch.int64).pin_memory()
         for k, buf in self._static_inputs.items():
             buf.copy_(inputs[k], non_blocking=True)
-        o = self.opt
-        fh, fw = o.height // 3, o.width // 3
-        self._aug_box_host[0] = np.random.randint(0, o.width - fw)        # x first, as the reference (layers.py:64-65)
-        self._aug_box_host[1] = np.random.randint(0, o.height - fh)
-        self._aug_box.copy_(self._aug_box_host, non_blocking=True)
+        B = self._static_inputs[("color_aug", 0, 0)].shape[0]
+        self._draw_noise(B, noise)
+        self._set_aug_box(mask_xy)
         return dict(self._static_inputs)
 
-    def _graph_step(self, inputs):
-        static = self._stage_inputs(inputs)
+    def _graph_step(self, inputs, noise=None, mask_xy=None):
+        static = self._stage_inputs(inputs, noise, mask_xy)
         key = self.epoch > self.opt.ztrans_start_epc      # the only data-independent branch of the step (trainer.py:336)
         g = self._graphs.get(key)
         if g is None:
@@ -310,7 +357,7 @@ class Trainer:
             if self._graph_warm.get(key, 0) < self.GRAPH_WARMUP:
                 self._graph_warm[key] = self._graph_warm.get(key, 0) + 1
                 with torch.cuda.stream(side):
-                    outputs, losses = self._forward_backward(static, mask_xy="preset")
+                    outputs, losses = self._forward_backward(static, noise="preset", mask_xy="preset")
                     self._optimizer_step()
                 cur.wait_stream(side)
                 return outputs, losses
@@ -318,7 +365,7 @@ class Trainer:
             graph = torch.cuda.CUDAGraph()
             n0 = ops.launch_counter["n"]
             with torch.cuda.graph(graph, pool=self._graph_pool, stream=side):
-                outputs, losses = self._forward_backward(static, mask_xy="preset")
+                outputs, losses = self._forward_backward(static, noise="preset", mask_xy="preset")
             g = self._graphs[key] = (graph, outputs, losses, ops.launch_counter["n"] - n0)
             if self._graph_pool is None:
                 self._graph_pool = graph.pool()
@@ -369,7 +416,10 @@ class Trainer:
         o = self.opt
         inputs = {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in inputs.items()}
         B = inputs[("color_aug", 0, 0)].shape[0]
-        noise = list(noise) if noise is not None else None
+        if isinstance(noise, str):                       # "preset": the graph step already filled the static noise buffers
+            noise = [self._noise_buf[i] for i in range(self._num_noise_maps())]
+        elif is_train or noise is not None:
+            noise = self._draw_noise(B, noise)
 
         # ---------------- mono / pose graph
         self._tf32("mono")
@@ -399,16 +449,14 @@ class Trainer:
         ref_feat, ref_ctx = enc(ref_img)
         src_feats = [enc(inputs[("color_aug", f, 0)].contiguous(memory_format=cl))[0] for f in self.matching_ids[1:]]
         logits, vol = self._volume_logits(ref_feat, src_feats, inputs, prior, ratio, poses)
-        _, ent, depth_mvs = ops.regress_depth(logits, inv_a, inv_b, o.norm_radius)
+        cost_prob, ent, depth_mvs = ops.regress_depth(logits, inv_a, inv_b, o.norm_radius, want_prob=bool(o.mask_mvs_conf))
         trust = self.models["mask_cnn"](ent)
         outputs["cost_volume"], outputs["cost_logits"], outputs["depth_mvs_lowres"] = vol, logits, depth_mvs
 
         # masked-augmentation consistency (trainer.py:374-403): zero a random box of the reference image
         fh, fw = o.height // 3, o.width // 3
-        if mask_xy is None:
-            mask_xy = (np.random.randint(0, o.width - fw), np.random.randint(0, o.height - fh))   # x first, as the reference
-        if mask_xy != "preset":              # "preset": the caller already wrote the box corner into self._aug_box (graph step)
-            self._aug_box.copy_(torch.tensor(mask_xy, dtype=torch.int64), non_blocking=True)
+        if not isinstance(mask_xy, str):     # "preset": the caller already wrote the box corner into self._aug_box (graph step)
+            self._set_aug_box(mask_xy)
         ys = torch.arange(o.height, device=self.device).view(1, 1, -1, 1)
         xs = torch.arange(o.width, device=self.device).view(1, 1, 1, -1)
         inside = (xs >= self._aug_box[0]) & (xs < self._aug_box[0] + fw) & (ys >= self._aug_box[1]) & (ys < self._aug_box[1] + fh)
@@ -416,9 +464,9 @@ class Trainer:
         aug_feat, _ = enc((ref_img * aug_mask).contiguous(memory_format=cl))
         logits_aug, _ = self._volume_logits(aug_feat, src_feats, inputs, prior, ratio, poses)
         _, _, depth_aug = ops.regress_depth(logits_aug, inv_a, inv_b, o.norm_radius)
-        sel = (F.interpolate(aug_mask, list(depth_aug.shape[1:]), mode="bilinear", align_corners=True).sum(1) != 0).float()
-        masked = (F.smooth_l1_loss(depth_aug, depth_mvs, reduction="none") * sel).sum() / sel.sum()
-        masked = masked * o.mask_lw * o.mask_lw            # weight applied twice in the reference (trainer.py:399-400)
+        # mean smooth-L1 over the pixels the resized box mask selects, one kernel; the weight is applied twice in the
+        # reference (trainer.py:399-400)
+        masked = ops.masked_smooth_l1(depth_aug, depth_mvs, self._aug_box, o.height, o.width, fh, fw, o.mask_lw * o.mask_lw)
         outputs["masked_depth"], outputs["masked_aug"] = depth_aug, aug_mask
 
         # upsample + fuse (trainer.py:405-416)
@@ -432,6 +480,11 @@ class Trainer:
         outputs["trust_mono_mask"] = trust
         outputs["fused_depth"] = (1 - trust) * depth_up.unsqueeze(1).detach() + trust * mono_depth.detach()
         fuse_loss = self.compute_fuse_losses(inputs, outputs, noise=noise)
+        if o.mask_mvs_conf:                  # trainer.py:419-422: trilinear-upsampled probability peak above photo_conf
+            up = F.interpolate(cost_prob.unsqueeze(1), [o.num_depth_bins, o.height, o.width], mode="trilinear", align_corners=True)
+            outputs["photo_conf_map"] = up.max(2)[0] > o.photo_conf
+        if o.mask_mvs_dist:                  # trainer.py:423-425
+            outputs["dist_mask"] = outputs[("disp", 0)] > o.dist_thres
         mvs_losses = self.compute_losses(inputs, outputs, is_mvs=True, noise=noise)
 
         # ---------------- totals (trainer.py:429-440): loss = mvs + (mono + masked) + fuse
@@ -442,6 +495,34 @@ class Trainer:
         losses["_mvs_total"] = mvs_losses["loss"] + masked + fuse_loss
         losses["loss"] = losses["_mono_total"] + losses["_mvs_total"]
         return outputs, losses
+
+    def generate_images_pred(self, inputs, outputs, is_mvs=False):
+        """Warped source images into `outputs` (movedepth/trainer.py:491-532).  `compute_losses` produces the same images
+        as a by-product of the fused warp + SSIM kernel; this entry point is for callers that only want the images:
+        `("depth", 0, s)`, `("color", f, s)`, `("color_identity", f, s)`, or `("mvs_color", f)` with is_mvs."""
+        o = self.opt
+        tgt = inputs[("color", 0, 0)]
+        K, invK = inputs[("K", 0)], inputs[("inv_K", 0)]
+        with torch.no_grad():
+            if is_mvs:
+                for f in o.frame_ids[1:]:
+                    outputs[("mvs_color", f)] = photo.reprojection_loss(outputs["depth_mvs"], inputs[("color", f, 0)], tgt, K, invK,
+                                                                        outputs[("cam_T_cam", 0, f)].detach(), 0)[1]
+                return
+            for s in o.scales:
+                depth = ops.disp_to_depth_full(outputs[("disp", s)].detach(), o.height, o.width, o.min_depth, o.max_depth)
+                outputs[("depth", 0, s)] = depth
+                for f in o.frame_ids[1:]:
+                    outputs[("color", f, s)] = photo.reprojection_loss(depth, inputs[("color", f, 0)], tgt, K, invK,
+                                                                       outputs[("cam_T_cam", 0, f)].detach(), 0)[1]
+                    outputs[("color_identity", f, s)] = inputs[("color", f, 0)]
+
+    @staticmethod
+    def compute_loss_masks(reprojection_loss, identity_reprojection_loss):
+        """argmin over [reprojection, identity] == 0 (movedepth/trainer.py:552-567)."""
+        if identity_reprojection_loss is None:
+            return torch.ones_like(reprojection_loss)
+        return (reprojection_loss <= identity_reprojection_loss).float()
 
     def compute_reprojection_loss(self, pred, target, ssim_lw=None):
         """movedepth/trainer.py:535-550."""
@@ -470,15 +551,20 @@ class Trainer:
                 per_src.append(l)
             if o.mask_mvs_auto and noise is not None and len(noise):
                 noise.pop(0)                         # drawn by the reference, the mask is then overwritten by ones
-            if len(per_src) <= 2:                    # min over sources + mean in one kernel (mask = ones)
+            extra = [outputs[k].float() for k, on in (("photo_conf_map", o.mask_mvs_conf), ("dist_mask", o.mask_mvs_dist)) if on]
+            if len(per_src) <= 2 and not extra:      # min over sources + mean in one kernel (mask = ones)
                 loss, reproj = ops.reproj_select(per_src)
-            else:
+                outputs["reprojection_loss_mask"] = torch.ones_like(reproj)
+            else:                                    # optional confidence / distance masks (trainer.py:648-660)
                 reproj = torch.cat(per_src, 1).min(1, keepdim=True)[0]
-                loss = reproj.sum() / (reproj.numel() + 1e-7)
+                mask = torch.ones_like(reproj)
+                for e in extra:
+                    mask = mask * e
+                outputs["reprojection_loss_mask"] = mask
+                loss = (reproj * mask).sum() / (mask.sum() + 1e-7)
             outputs["mvs_reprojection_loss"] = reproj
             if o.mvs_smooth_loss:
-                d = depth.unsqueeze(1)
-                sm = get_smooth_loss(d / (d.mean(2, True).mean(3, True) + 1e-7), tgt)
+                sm = ops.smooth_loss(depth.unsqueeze(1), tgt, normalize=True)
                 losses["mvs_smooth_loss/0"] = sm
                 loss = loss + o.disparity_smoothness * sm
             losses["mvs_reproj_loss"] = loss
@@ -489,8 +575,7 @@ class Trainer:
         total = 0
         for s in o.scales:
             disp = outputs[("disp", s)]
-            disp_full = F.interpolate(disp, [o.height, o.width], mode="bilinear", align_corners=False)
-            _, depth = disp_to_depth(disp_full, o.min_depth, o.max_depth)
+            depth = ops.disp_to_depth_full(disp, o.height, o.width, o.min_depth, o.max_depth)   # upsample + disp_to_depth
             outputs[("depth", 0, s)] = depth
             per_src = []
             for f in o.frame_ids[1:]:
@@ -510,8 +595,7 @@ class Trainer:
                 loss = (reproj * mask).sum() / (mask.sum() + 1e-7)
             if s == 0:
                 outputs["mono_reproj_loss"] = reproj
-            norm_disp = disp / (disp.mean(2, True).mean(3, True) + 1e-7)
-            sm = get_smooth_loss(norm_disp, inputs[("color", 0, s)])
+            sm = ops.smooth_loss(disp, inputs[("color", 0, s)], normalize=True)     # mean normalisation + smoothness
             losses["mono_smooth_loss/{}".format(s)] = sm
             loss = loss + o.disparity_smoothness * sm / (2 ** s)
             total = total + loss
@@ -599,49 +683,91 @@ class Trainer:
             json.dump(dict(self.opt.__dict__), f, indent=2)
 
     def save_model(self, save_step=False):
-        """One <name>.pth state_dict per sub-model + adam.pth (movedepth/trainer.py:807-831); rank 0 only."""
+        """One <name>.pth state_dict per sub-model + adam.pth (movedepth/trainer.py:807-831); rank 0 only.  The files have
+        the reference's formats: plain state_dicts (loadable with strict=True by evaluate_depth.py:115-174) and
+        `torch.optim.Adam.state_dict()` for adam.pth (parameter indices in the reference's registration order)."""
         if self.rank != 0:
             return
         tag = "weights_{}".format(self.epoch) if not save_step else "weights_{}_{}".format(self.epoch, self.step)
-        if self.epoch == self.opt.num_epochs - 1 and not save_step:
+        if self.epoch == self.opt.num_epochs - 1:
             tag = "last"
         folder = os.path.join(self.log_path, "models", tag)
         os.makedirs(folder, exist_ok=True)
         for name, model in self.models.items():
             sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
-            if name == "mono_encoder":
-                sd["height"], sd["width"] = self.opt.height, self.opt.width
             torch.save(sd, os.path.join(folder, "{}.pth".format(name)))
-        torch.save({"step": self.opt_step, "epoch": self.epoch,
-                    "exp_avg": [a.exp_avg.clone() for a in self.arenas],
-                    "exp_avg_sq": [a.exp_avg_sq.clone() for a in self.arenas]}, os.path.join(folder, "adam.pth"))
+        torch.save(self.adam_state_dict(), os.path.join(folder, "adam.pth"))
+
+    def adam_state_dict(self):
+        """The arenas' Adam moments in `torch.optim.Adam.state_dict()` layout (what trainer.py:830-831 saves)."""
+        state, groups, idx = {}, [], 0
+        step = torch.tensor(float(self.opt_step))
+        for a, lr, base in zip(self.arenas, self.current_lrs(), self.base_lrs):
+            ids = []
+            for p, o in zip(a.params, a.offsets):
+                n = p.numel()
+                state[idx] = {"step": step.clone(), "exp_avg": a.exp_avg[o:o + n].view_as(p).clone(),
+                              "exp_avg_sq": a.exp_avg_sq[o:o + n].view_as(p).clone()}
+                ids.append(idx)
+                idx += 1
+            groups.append({"lr": lr, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False, "maximize": False,
+                           "foreach": None, "capturable": False, "differentiable": False, "fused": None,
+                           "decoupled_weight_decay": False, "initial_lr": base, "params": ids})
+        return {"state": state, "param_groups": groups}
+
+    def load_adam_state_dict(self, st):
+        """Restore the moments and the step count from an Adam state_dict (ours or the reference's)."""
+        flat = [(a, p, o) for a in self.arenas for p, o in zip(a.params, a.offsets)]
+        n_given = sum(len(g["params"]) for g in st["param_groups"])
+        if n_given != len(flat):
+            raise ValueError("adam.pth holds %d parameter states, this model has %d" % (n_given, len(flat)))
+        step = 0
+        for i, (a, p, o) in enumerate(flat):
+            e = st["state"].get(i)
+            if e is None:
+                continue
+            if tuple(e["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError("adam.pth state %d has shape %s, parameter has %s" % (i, tuple(e["exp_avg"].shape), tuple(p.shape)))
+            a.exp_avg[o:o + p.numel()].view_as(p).copy_(e["exp_avg"])
+            a.exp_avg_sq[o:o + p.numel()].view_as(p).copy_(e["exp_avg_sq"])
+            step = max(step, int(float(e["step"])))
+        self.opt_step = step
 
     def _load_into(self, name, path):
         model = self.models[name]
         have = model.state_dict()
         sd = torch.load(path, map_location="cpu")
         have.update({k: v for k, v in sd.items() if k in have})
-        model.load_state_dict(have)
+        model.load_state_dict(have)              # parameters are views of the arenas: copies land there
 
     def load_mono_model(self):
         """movedepth/trainer.py:833-844."""
         folder = os.path.expanduser(self.opt.mono_weights_folder)
         for name in ("pose_encoder", "pose", "mono_encoder", "mono_depth"):
+            if self.rank == 0:
+                print("loading {}".format(name))
             self._load_into(name, os.path.join(folder, "{}.pth".format(name)))
 
     def load_model(self):
-        """movedepth/trainer.py:846-880 (names not in `models`, e.g. the stale defaults, are skipped)."""
+        """movedepth/trainer.py:846-880 (names not in `models`, e.g. the stale defaults, are skipped); the Adam
+        moments and step count are restored into the arenas."""
         folder = os.path.expanduser(self.opt.load_weights_folder)
         assert os.path.isdir(folder), "Cannot find folder {}".format(folder)
+        if self.rank == 0:
+            print("loading model from folder {}".format(folder))
         for name in self.opt.models_to_load:
             path = os.path.join(folder, "{}.pth".format(name))
             if name in self.models and os.path.isfile(path):
+                if self.rank == 0:
+                    print("Loading {} weights...".format(name))
                 self._load_into(name, path)
         adam = os.path.join(folder, "adam.pth")
-        if hasattr(self, "arenas") and os.path.isfile(adam):
-            st = torch.load(adam, map_location=self.device)
-            if "exp_avg" in st:
-                for a, m1, m2 in zip(self.arenas, st["exp_avg"], st["exp_avg_sq"]):
-                    a.exp_avg.copy_(m1)
-                    a.exp_avg_sq.copy_(m2)
-                self.opt_step = int(st.get("step", 0))
+        if os.path.isfile(adam):
+            try:
+                if self.rank == 0:
+                    print("Loading Adam weights")
+                self.load_adam_state_dict(torch.load(adam, map_location=self.device))
+            except (ValueError, KeyError, TypeError) as e:
+                print("Can't load Adam ({}) - using random".format(e))
+        else:
+            print("Cannot find Adam weights so Adam is randomly initialized")

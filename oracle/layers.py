@@ -116,6 +116,10 @@ def depth_hypotheses(prior_depth, ndepth, scale_fac, z_trans=None, kind="inverse
             return 1 / (1 / d_hi + (1 / d_lo - 1 / d_hi) * itv)
         if kind == "linear":
             return d_lo + (d_hi - d_lo) * itv
+        if kind == "log":       # layers.py:276-282 / 389-395: affine map of a fixed 0.1 -> 1 geometric ramp (fp32 loop)
+            ramp = torch.stack([torch.exp(torch.log(torch.tensor([0.1])) + torch.log(torch.tensor([1 / 0.1])) *
+                                          torch.tensor([float(k)]) / (ndepth - 1)) for k in range(ndepth)]).reshape(1, -1, 1, 1)
+            return d_lo + (d_hi - d_lo) * ramp.to(prior_depth.dtype)
         raise NotImplementedError(kind)
 
 
@@ -274,3 +278,23 @@ def box_mask(img, box_hw, xy=None):
     m = torch.ones_like(img)
     m[:, :, y:y + fh, x:x + fw] = 0.0
     return img * m, m
+
+
+def upsampled_depth(disp, height, width, min_depth, max_depth):
+    """movedepth/trainer.py:512-515: bilinear (align_corners=False) upsampling of a sigmoid disparity to full
+    resolution, then disp_to_depth.  [B,1,hs,ws] -> [B,1,H,W]."""
+    up = F.interpolate(disp, [height, width], mode="bilinear", align_corners=False)
+    return disp_to_depth(up, min_depth, max_depth)[1]
+
+
+def normalized_smooth_loss(disp, img):
+    """movedepth/trainer.py:712-714: mean-normalised disparity, then the edge-aware smoothness."""
+    mean = disp.mean(2, True).mean(3, True)
+    return smooth_loss(disp / (mean + 1e-7), img)
+
+
+def masked_consistency(depth_aug, depth, aug_mask, weight):
+    """movedepth/trainer.py:398-400: smooth-L1 (mean) between the two low-resolution depth maps over the pixels where the
+    bilinearly resized (align_corners=True) box mask is non-zero; `weight` = mask_lw * mask_lw (applied twice there)."""
+    sel = F.interpolate(aug_mask, list(depth_aug.shape[1:]), mode="bilinear", align_corners=True).sum(1).to(torch.bool)
+    return F.smooth_l1_loss(depth_aug[sel], depth[sel], reduction="mean") * weight

@@ -128,12 +128,29 @@ def case_warp(B=2, H=16, W=24):
                 depth=1.0 + 5 * torch.rand(B, 1, H, W, generator=g))
 
 
+def case_disp_pyramid(B=2, H=32, W=64):
+    """Sigmoid-like disparities at the 4 decoder scales + gradient seeds (disp -> full-res depth kernel)."""
+    g = _gen(91)
+    return dict(B=B, H=H, W=W, disp=[torch.rand(B, 1, H // 2 ** s, W // 2 ** s, generator=g) for s in range(4)],
+                gdepth=torch.randn(B, 1, H, W, generator=g), img=torch.rand(B, 3, H, W, generator=g))
+
+
+def case_masked(B=2, h=12, w=20, H=48, W=80):
+    """Two low-resolution depth maps and the augmentation boxes (x, y) of the masked-consistency term."""
+    g = _gen(101)
+    a = 1.0 + 8 * torch.rand(B, h, w, generator=g)
+    return dict(B=B, h=h, w=w, H=H, W=W, a=a, b=a + 1.5 * torch.randn(B, h, w, generator=g),
+                boxes=[(0, 0), (17, 9), (W - W // 3 - 1, H - H // 3 - 1), (31, 2)])
+
+
 # ---------------------------------------------------------------- whole-step cases
 STEP_CASES = {
     "r18_2f": dict(H=64, W=96, D=8, B=2, frame_ids=[0, -1], epoch=0, arch=18),
     "r18_2f_z": dict(H=64, W=96, D=8, B=2, frame_ids=[0, -1], epoch=9, arch=18),
     "r18_3f": dict(H=64, W=96, D=16, B=2, frame_ids=[0, -1, 1], epoch=0, arch=18),
     "r50_3f": dict(H=64, W=96, D=8, B=1, frame_ids=[0, -1, 1], epoch=9, arch=50),
+    # BASELINE.json configs[0] (the reference's own CPU-runnable case): R18 2-frame 192x640 D=16 batch 2, velocity-guided range
+    "c1": dict(H=192, W=640, D=16, B=2, frame_ids=[0, -1], epoch=9, arch=18, slim=True),
 }
 EVAL_CASE = dict(H=64, W=96, D=8, B=2, frame_ids=[0, -1], epoch=9, arch=18)      # inference path (evaluate_depth.py:181-253)
 GRAD_PROBES = [("pose", "net.3.bias"), ("reg3d", "prob.weight"), ("mask_cnn", "head_convs.weight"),

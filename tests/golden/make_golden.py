@@ -76,6 +76,8 @@ def op_vectors(rl):
     g["hyp_v2"] = np32(rl.schedule_depth_rangev2(c["prior"], c["D"], c["fac"]))
     g["hyp_zv2"] = np32(rl.schedule_depth_range_zv2(c["prior"], c["D"], c["fac"], c["z_trans"]))
     g["hyp_v2_linear"] = np32(rl.schedule_depth_rangev2(c["prior"], c["D"], c["fac"], type="linear"))
+    g["hyp_v2_log"] = np32(rl.schedule_depth_rangev2(c["prior"], c["D"], c["fac"], type="log"))
+    g["hyp_zv2_log"] = np32(rl.schedule_depth_range_zv2(c["prior"], c["D"], c["fac"], c["z_trans"], type="log"))
     # A2: cost volume (reference layout [B,D,C,h,w]) for each pose case
     for name in C.COSTVOL_CASES:
         c = C.case_costvol(name)
@@ -111,6 +113,29 @@ def op_vectors(rl):
     grid = pj(bp(c["depth"], c["invK"]), c["K"], c["T"])
     g["warp_grid"] = np32(grid)
     g["warp_img"] = np32(torch.nn.functional.grid_sample(c["img"], grid, padding_mode="border", align_corners=True))
+    g["reproj_loss"] = np32(0.85 * rl.SSIM()(torch.from_numpy(g["warp_img"]), c["img"].flip(0)).mean(1, True) +
+                            0.15 * (c["img"].flip(0) - torch.from_numpy(g["warp_img"])).abs().mean(1, True))
+    # A8: loss glue -- upsample + disp_to_depth (trainer.py:512-515), normalised smoothness (712-714), masked consistency (374, 398-400)
+    import torch.nn.functional as F
+    c = C.case_disp_pyramid()
+    for s_ in range(4):
+        up = F.interpolate(c["disp"][s_], [c["H"], c["W"]], mode="bilinear", align_corners=False)
+        g["up_depth_s%d" % s_] = np32(rl.disp_to_depth(up, 0.1, 100.0)[1])
+        d = c["disp"][s_]
+        img = F.interpolate(c["img"], [c["H"] // 2 ** s_, c["W"] // 2 ** s_], mode="area") if s_ else c["img"]
+        g["smooth_norm_s%d" % s_] = np32(rl.get_smooth_loss(d / (d.mean(2, True).mean(3, True) + 1e-7), img))
+    c = C.case_masked()
+    orig_ri = np.random.randint
+    for i, xy in enumerate(c["boxes"]):
+        q = list(xy)
+        np.random.randint = lambda *a, **k: q.pop(0)
+        try:
+            _, m = rl.random_image_mask(torch.ones(c["B"], 3, c["H"], c["W"]), [c["H"] // 3, c["W"] // 3])
+        finally:
+            np.random.randint = orig_ri
+        sel = F.interpolate(m, [c["h"], c["w"]], mode="bilinear", align_corners=True).sum(1).to(torch.bool)
+        g["masked_sel_%d" % i] = sel.numpy()
+        g["masked_loss_%d" % i] = np32(F.smooth_l1_loss(c["a"][sel], c["b"][sel], size_average=True) * 10 * 10)
     np.savez_compressed(os.path.join(HERE, "ops.npz"), **g)
     print("ops.npz:", {k: v.shape for k, v in g.items()})
 
@@ -118,7 +143,10 @@ def op_vectors(rl):
 def step_vectors(rl, rn, rt, Options):
     import _cases as C
     from _weights import fill_deterministic
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--step=")]
     for name, cfg in C.STEP_CASES.items():
+        if only and name not in only:
+            continue
         argv = ["--no_cuda", "--weights_init", "scratch", "--num_workers", "0", "--data_path", "/nonexistent",
                 "--png", "--log_dir", "/tmp/mvd_golden", "--prior_scale", "2", "--convex_up",
                 "--height", str(cfg["H"]), "--width", str(cfg["W"]), "--num_depth_bins", str(cfg["D"]),
@@ -158,10 +186,15 @@ def step_vectors(rl, rn, rt, Options):
         g["trust_mono_mask"] = np32(outputs["trust_mono_mask"])
         g["mono_reproj_loss"] = np32(outputs["mono_reproj_loss"])
         g["mvs_reprojection_loss"] = np32(outputs["mvs_reprojection_loss"])
-        g["cost_volume"] = np32(captured["vol"])
+        if not cfg.get("slim"):                 # full-size cases keep the maps the depth bar is stated on, not the volume
+            g["cost_volume"] = np32(captured["vol"])
+        else:
+            for k in ("mono_reproj_loss", "mvs_reprojection_loss", "masked_depth"):
+                g.pop(k)
         for f in cfg["frame_ids"][1:]:
             g["cam_T_cam_%d" % f] = np32(outputs[("cam_T_cam", 0, f)])
-            g["warped_%d_s0" % f] = np32(outputs[("color", f, 0)])
+            if not cfg.get("slim"):
+                g["warped_%d_s0" % f] = np32(outputs[("color", f, 0)])
         for k, m in tr.models.items():
             sq = sum(float((p.grad.double() ** 2).sum()) for p in m.parameters() if p.grad is not None)
             g["gradnorm/" + k] = np.float64(sq ** 0.5)
@@ -233,6 +266,9 @@ if __name__ == "__main__":
     torch.set_num_threads(8)
     rl, rn, rt, Options = import_reference()
     if "--eval-only" not in sys.argv:
-        op_vectors(rl)
-        step_vectors(rl, rn, rt, Options)
-    eval_vectors(rl, rn)
+        if "--steps-only" not in sys.argv:
+            op_vectors(rl)
+        if "--ops-only" not in sys.argv:
+            step_vectors(rl, rn, rt, Options)
+    if "--ops-only" not in sys.argv and "--steps-only" not in sys.argv:
+        eval_vectors(rl, rn)

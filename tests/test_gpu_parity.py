@@ -1,6 +1,7 @@
-"""GPU parity: every hand-written kernel, called through the C ABI (ctypes), against the CPU oracle
-on the same seeded inputs and against the reference-generated golden vectors.  Tolerances are
-stated per test; the end-to-end bar is 1e-3 relative on fp32 depth (BASELINE.json north_star)."""
+"""GPU parity, kernel level: every hand-written kernel, called through the C ABI (ctypes), against the CPU oracle
+on the same seeded inputs and against the reference-generated golden vectors.  Tolerances are stated per test.
+The whole-step / whole-model tests live in test_gpu_step.py, which is collected AFTER this file, so a step-level
+failure cannot hide a kernel test."""
 import os
 
 import numpy as np
@@ -232,131 +233,6 @@ def test_fused_adam_matches_torch_adam(ops):
         torch.testing.assert_close(p.cpu(), want.detach(), atol=1e-7, rtol=1e-6)
 
 
-# ---------------------------------------------------------------------------------------------- whole step
-def _trainer(cfg, precision="fp32"):
-    from movedepth_b200.options import MonodepthOptions
-    from movedepth_b200.trainer import Trainer
-    argv = ["--height", str(cfg["H"]), "--width", str(cfg["W"]), "--num_depth_bins", str(cfg["D"]), "--batch_size",
-            str(cfg["B"]), "--res_arch", str(cfg.get("arch", 18)), "--weights_init", "scratch", "--convex_up",
-            "--learning_rate", "2e-4", "--b200_conv_precision", precision, "--log_dir", "/tmp/mvd_test",
-            "--frame_ids"] + [str(f) for f in cfg["frame_ids"]]
-    tr = Trainer(MonodepthOptions().parse(argv))
-    for k, m in tr.models.items():
-        fill_deterministic(m, salt=k + "/")
-    tr.epoch = cfg["epoch"]
-    return tr
-
-
-@pytest.mark.parametrize("name", list(C.STEP_CASES))
-def test_whole_step_matches_reference_golden(name):
-    """Trainer.process_batch + backward + fused Adam on the GPU vs the REFERENCE's outputs for the same
-    weights and inputs (tests/golden/step_*.npz).  fp32 convolutions.  Depth maps: fraction of pixels
-    within 1e-3 relative (argmax ties flip under 1-ulp noise)."""
-    cfg = C.STEP_CASES[name]
-    gold = dict(np.load(os.path.join(GOLD, "step_%s.npz" % name)))
-    tr = _trainer(cfg)
-    inputs, noise, xy = C.step_inputs(cfg)
-    out, losses = tr.train_step(dict(inputs), noise=noise, mask_xy=xy)
-    torch.cuda.synchronize()
-
-    def close(a, b, atol, rtol):
-        np.testing.assert_allclose(a.detach().float().cpu().numpy().reshape(b.shape), b, atol=atol, rtol=rtol)
-
-    for s in range(4):
-        close(out[("disp", s)], gold["disp%d" % s], 2e-4, 1e-3)     # sigmoid outputs; R50 accumulates ~1e-4 abs vs the CPU convs
-    for f in cfg["frame_ids"][1:]:
-        close(out[("cam_T_cam", 0, f)], gold["cam_T_cam_%d" % f], 1e-5, 1e-4)
-        close(out[("color", f, 0)], gold["warped_%d_s0" % f], 1e-3, 1e-3)      # colours in [0,1]; R50 depth noise moves them ~5e-4
-    # The volume inherits the mono prior's conv noise: a 3e-5 drift of disp_2 (GPU vs CPU fp32 convs) moves the
-    # sampling positions by ~1e-4 px, and deterministic-weight FPN features reach |x|~8 with steep gradients, so the
-    # bound scales with the volume's magnitude (tools/diag_parity.py: K1 itself is within 4e-6 relative on identical
-    # inputs; the oracle on a different CPU already differs from the golden volume by 1e-4 relative).
-    close(out["cost_volume"].permute(0, 2, 1, 3, 4), gold["cost_volume"],
-          5e-4 * max(1.0, float(np.abs(gold["cost_volume"]).max())), 1e-3)
-    for key in ("depth_mvs", "masked_depth", "fused_depth"):
-        got = out[key].detach().cpu().numpy().reshape(gold[key].shape)
-        rel = np.abs(got - gold[key]) / np.abs(gold[key])
-        # r50_3f runs ResNet50 at batch 1: its deepest BatchNorms take statistics over 2x3 = 6 samples and amplify the
-        # GPU-vs-CPU fp32 summation-order noise to 3e-5 on disp_2, i.e. 4e-4 relative on the volume (tools/diag_parity.py),
-        # which flips the D=8 argmax at ~2 % of the pixels; the other cases stay above 99 %.
-        bar = 0.96 if name == "r50_3f" else 0.99
-        assert (rel < 1e-3).mean() > bar, (key, float((rel < 1e-3).mean()))
-    close(out["trust_mono_mask"], gold["trust_mono_mask"], 1e-4, 1e-3)
-    for key in gold:
-        if key.startswith("loss/"):
-            k = key[5:]
-            # the masked-consistency term (and hence the total) sums |depth_aug - depth_mvs| over pixels whose
-            # argmax can flip under 1-ulp conv noise: looser bound there
-            loose = k in ("masked_loss", "loss")
-            close(losses[k], gold[key], 1e-4, 5e-2 if loose else 2e-3)
-    named = {k: dict(m.named_parameters()) for k, m in tr.models.items()}
-    for k in tr.models:
-        sq = sum(float((p.grad.double() ** 2).sum()) for p in tr.models[k].parameters())
-        tol = 1e-2 if k in ("mono_encoder", "mono_depth", "pose_encoder", "pose") else 0.15
-        assert abs(sq ** 0.5 - gold["gradnorm/" + k]) <= tol * gold["gradnorm/" + k] + 1e-9, (k, sq ** 0.5, gold["gradnorm/" + k])
-    for mk, pk in C.GRAD_PROBES:
-        if mk in ("pose", "mono_depth"):
-            gr = gold["grad/%s/%s" % (mk, pk)]
-            close(named[mk][pk].grad, gr, 1e-2 * np.abs(gr).max() + 1e-9, 1e-2)
-            close(named[mk][pk], gold["adam/%s/%s" % (mk, pk)], 1e-5, 1e-4)
-
-
-def test_step_under_default_3xtf32_policy_stays_within_the_depth_bar():
-    """default precision policy (3xTF32 forward): >= 97 % of depth_mvs pixels and all mono disparities within
-    1e-3 relative of the REFERENCE (argmax flips under ~4e-6 conv noise), losses within 1 %."""
-    cfg = C.STEP_CASES["r18_2f"]
-    gold = dict(np.load(os.path.join(GOLD, "step_r18_2f.npz")))
-    tr = _trainer(cfg, "3xtf32")
-    inputs, noise, xy = C.step_inputs(cfg)
-    out, losses = tr.train_step(dict(inputs), noise=noise, mask_xy=xy)
-    d0 = out[("disp", 0)].detach().cpu().numpy()
-    assert float((np.abs(d0 - gold["disp0"]) / gold["disp0"]).max()) < 1e-3
-    got = out["depth_mvs"].detach().cpu().numpy().reshape(gold["depth_mvs"].shape)
-    frac = float((np.abs(got - gold["depth_mvs"]) / gold["depth_mvs"] < 1e-3).mean())
-    assert frac > 0.97, frac
-    for k in ("loss/0", "fuse_reproj_loss"):
-        assert abs(float(losses[k]) - float(gold["loss/" + k])) < 1e-2 * abs(float(gold["loss/" + k])), k
-
-
-def test_cuda_graph_step_tracks_the_eager_step():
-    """`--b200_cuda_graph`: forward + backward replayed as one CUDA graph.  Before every step the graphed trainer is
-    given the eager trainer's parameters and Adam moments (training from random init is chaotic: argmax flips amplify
-    the 1e-5 * N(0,1) auto-mask tie-break noise, which comes from a different generator offset), then both take the
-    step on the same batch and augmentation box: loss within 1e-3 relative, gradient arenas within 5e-3 of their max."""
-    from movedepth_b200.options import MonodepthOptions
-    from movedepth_b200.trainer import Trainer, SyntheticKITTI
-    cfg = C.STEP_CASES["r18_2f"]
-    base = ["--height", str(cfg["H"]), "--width", str(cfg["W"]), "--num_depth_bins", str(cfg["D"]), "--batch_size", "2",
-            "--weights_init", "scratch", "--convex_up", "--learning_rate", "2e-4", "--b200_conv_precision", "fp32",
-            "--log_dir", "/tmp/mvd_test", "--frame_ids", "0", "-1"]
-    trainers = []
-    for extra in ([], ["--b200_cuda_graph"]):
-        tr = Trainer(MonodepthOptions().parse(base + extra))
-        for k, m in tr.models.items():
-            fill_deterministic(m, salt=k + "/")
-        trainers.append(tr)
-    eager, graphed = trainers
-    for i, batch in enumerate(SyntheticKITTI(eager.opt, 2, 6, seed=3)):
-        for a, b in zip(eager.arenas, graphed.arenas):
-            b.data.copy_(a.data)
-            b.exp_avg.copy_(a.exp_avg)
-            b.exp_avg_sq.copy_(a.exp_avg_sq)
-        for m_e, m_g in zip(eager.models.values(), graphed.models.values()):
-            for be, bg in zip(m_e.buffers(), m_g.buffers()):
-                bg.copy_(be)                                          # BatchNorm running statistics
-        losses = []
-        for tr in (eager, graphed):
-            np.random.seed(100 + i)
-            losses.append(float(tr.train_step(batch)[1]["loss"].detach()))
-        assert abs(losses[1] - losses[0]) <= 1e-3 * abs(losses[0]), (i, losses)
-        for a, b in zip(eager.arenas, graphed.arenas):           # gradients: a few auto-mask / argmax pixels may flip between the
-            tol = 5e-3 * float(a.grad.abs().max()) + 1e-2 * a.grad.abs()      # two runs (atomics order), so bound the outliers
-            bad = float(((b.grad - a.grad).abs() > tol).float().mean())
-            assert bad < 1e-5, (i, bad)
-            assert float((b.grad - a.grad).abs().max()) < 5e-2 * float(a.grad.abs().max())
-    assert len(graphed._graphs) == 1, "the graph was never captured"
-
-
 # ---------------------------------------------------------------------------------------------- reg3d output head
 @pytest.mark.parametrize("shape", [(2, 8, 8, 32), (1, 5, 11, 45), (2, 24, 24, 80)], ids=["aligned", "ragged", "multi-tile"])
 def test_prob_conv3d_matches_torch_conv3d(ops, shape):
@@ -570,35 +446,6 @@ def test_conv3d_16_to_16_tcgen05_weight_gradient(ops, shape):
     torch.testing.assert_close(ops.c16c16_wgrad_tc(go, xo), ops.c16c16_wgrad(go, xo))
 
 
-# ---------------------------------------------------------------------------------------------- inference path
-def test_depth_predictor_matches_reference_golden():
-    """movedepth_b200.evaluate_depth.DepthPredictor (fused kernels, eval mode, fp32 convolutions) vs the golden output of
-    the reference's inference loop body (tests/golden/eval_r18.npz): mono disparity to 1e-3, >= 99 % of the multi-frame
-    disparities within 1e-3 relative; and the CPU oracle's metric code on the same numbers."""
-    from movedepth_b200 import evaluate_depth as ED
-    from movedepth_b200.options import MonodepthOptions
-    from oracle import evaluate as OE
-    gold = dict(np.load(os.path.join(GOLD, "eval_r18.npz")))
-    cfg = C.EVAL_CASE
-    argv = ["--height", str(cfg["H"]), "--width", str(cfg["W"]), "--num_depth_bins", str(cfg["D"]), "--batch_size", str(cfg["B"]),
-            "--weights_init", "scratch", "--convex_up", "--b200_conv_precision", "fp32", "--frame_ids", "0", "-1"]
-    opt = MonodepthOptions().parse(argv)
-    models = ED.build_models(opt)
-    for k, m in models.items():
-        fill_deterministic(m, salt=k + "/")
-    pred = ED.DepthPredictor(opt, models=models)
-    data, _, _ = C.step_inputs(cfg)
-    out = pred.predict(data)
-    mono = out["pred_disp_mono"].cpu().numpy()
-    np.testing.assert_allclose(mono, gold["pred_disp_mono"], rtol=1e-3, atol=1e-5)
-    dz = out["pred_disp_z"].cpu().numpy()
-    rel = np.abs(dz - gold["pred_disp_z"]) / np.abs(gold["pred_disp_z"])
-    assert (rel < 1e-3).mean() > 0.99, float((rel < 1e-3).mean())
-    gt = 1.0 / gold["pred_disp_z"][0]
-    np.testing.assert_allclose(ED.compute_errors(gt, 1.0 / dz[0]), OE.compute_errors(gt, 1.0 / dz[0]), rtol=1e-12)
-    assert ED.compute_fuse_errors(gt, 1.0 / dz[0], gt)[0] == 0.0          # oracle fusion picks the exact prediction
-
-
 # ---------------------------------------------------------------------------------------------- loss assembly
 @pytest.mark.parametrize("nsrc,automask", [(1, True), (2, True), (2, False), (1, False)])
 def test_reproj_select_matches_the_tensor_formula(ops, nsrc, automask):
@@ -645,3 +492,143 @@ def test_reg3d_first_layer_kernels_are_linear_at_full_size(ops):
     yr = 2.0 * ops.conv3d_c16_to_1(x1, w1) + ops.conv3d_c16_to_1(x2, w1)
     assert yl.shape == (6, 1, 96, 48, 160)
     assert float((yl - yr).abs().max()) < 1e-4 * float(yr.abs().max())
+
+
+# ---------------------------------------------------------------------------------------------- K5 + K6 (op level)
+def _photo_case(H, W, smooth):
+    c = C.case_warp(B=2, H=H, W=W)
+    if smooth:                       # image-like statistics at the benchmark resolution
+        c["img"] = C.smooth_noise((2, 3, H, W), 73, factor=8, normal=False).clamp(0, 1)
+        c["depth"] = 1.0 + 5 * C.smooth_noise((2, 1, H, W), 74, factor=16, normal=False).clamp(0, 1)
+    c["tgt"] = c["img"].flip(0).contiguous()
+    return c
+
+
+@pytest.mark.parametrize("ssim_w", [0.85, 0.0], ids=["ssim", "l1only"])
+@pytest.mark.parametrize("size,smooth", [((16, 24), False), ((192, 640), True)], ids=["16x24", "192x640"])
+def test_photometric_matches_oracle_and_golden(ops, gold, size, smooth, ssim_w):
+    """mvd_photometric_fwd/bwd (backproject -> project -> border bilinear warp -> 3x3 SSIM + L1) against the oracle's
+    warp_image + reprojection_loss (movedepth/trainer.py:519-550, layers.py:646-677) on identical inputs: loss map, warped
+    image, d loss / d depth and d loss / d T.  The second pose of the case throws a band of pixels outside the source
+    image (border clamp, zero derivative there).  Bars: 2e-4 abs on colours / losses in [0,1] (sampling coordinates differ
+    by <= 6e-5 px from the reference's normalise / unnormalise round trip); gradients within 2e-3 of their scale on
+    >= 99.5 % of the pixels (a pixel whose sample sits within 1e-4 px of a cell edge may take the neighbouring cell)."""
+    H, W = size
+    c = _photo_case(H, W, smooth)
+    d_o, T_o = c["depth"].clone().requires_grad_(True), c["T"].clone().requires_grad_(True)
+    img_o, _ = OL.warp_image(c["img"], d_o, c["K"], c["invK"], T_o)
+    loss_o = OL.reprojection_loss(img_o, c["tgt"], ssim_w, no_ssim=(ssim_w == 0))
+    gl = torch.rand(loss_o.shape, generator=torch.Generator().manual_seed(17))
+    (loss_o * gl).sum().backward()
+    d, T = g(c["depth"]).requires_grad_(True), g(c["T"]).requires_grad_(True)
+    loss, warped = ops.photometric_loss(d, g(c["img"]), g(c["tgt"]), g(c["K"]), g(c["invK"]), T, ssim_w)
+    (loss * g(gl)).sum().backward()
+    torch.testing.assert_close(warped.cpu(), img_o.detach(), atol=2e-4, rtol=0)
+    torch.testing.assert_close(loss.detach().cpu(), loss_o.detach(), atol=2e-4, rtol=0)
+    if size == (16, 24):             # the reference's own outputs for this case
+        np.testing.assert_allclose(warped.cpu().numpy(), gold["warp_img"], atol=2e-4, rtol=0)
+        if ssim_w:
+            np.testing.assert_allclose(loss.detach().cpu().numpy(), gold["reproj_loss"], atol=2e-4, rtol=0)
+    gd, gd_o = d.grad.cpu(), d_o.grad
+    err = (gd - gd_o).abs() / float(gd_o.abs().max())
+    assert float((err < 2e-3).float().mean()) > 0.995, float((err < 2e-3).float().mean())
+    assert float(err.max()) < 0.5                                        # and no wild outlier
+    assert 0.0 < float((gd_o == 0).float().mean()) < 0.9                 # some samples fall outside the image: clamped, zero gradient
+    torch.testing.assert_close(T.grad.cpu()[:, :3], T_o.grad[:, :3], atol=5e-3 * float(T_o.grad.abs().max()), rtol=5e-3)
+
+
+def test_photometric_identity_is_ssim_l1_of_the_unwarped_image(ops, gold):
+    c = C.case_images()
+    got = ops.photometric_identity(g(c["x"]), g(c["y"]), 0.85)
+    want = OL.reprojection_loss(c["x"], c["y"], 0.85)
+    torch.testing.assert_close(got.cpu(), want, atol=1e-6, rtol=1e-5)
+    want_g = 0.85 * torch.from_numpy(gold["ssim"]).mean(1, True) + 0.15 * (c["y"] - c["x"]).abs().mean(1, True)
+    torch.testing.assert_close(got.cpu(), want_g, atol=1e-6, rtol=1e-5)
+    assert float(ops.photometric_identity(g(c["x"]), g(c["x"]), 0.85).abs().max()) == 0.0        # SSIM(x, x) == 0 exactly
+
+
+# ---------------------------------------------------------------------------------------------- loss glue
+@pytest.mark.parametrize("s", [0, 1, 2, 3])
+def test_disp_to_depth_full_matches_golden_and_autograd(ops, gold, s):
+    """bilinear upsampling (align_corners=False) + disp_to_depth in one kernel vs the reference's own composition
+    (tests/golden/ops.npz: up_depth_s*) and the oracle's autograd."""
+    c = C.case_disp_pyramid()
+    disp = g(c["disp"][s]).requires_grad_(True)
+    depth = ops.disp_to_depth_full(disp, c["H"], c["W"], 0.1, 100.0)
+    np.testing.assert_allclose(depth.detach().cpu().numpy(), gold["up_depth_s%d" % s], rtol=2e-6, atol=0)
+    (depth * g(c["gdepth"])).sum().backward()
+    do = c["disp"][s].clone().requires_grad_(True)
+    (OL.upsampled_depth(do, c["H"], c["W"], 0.1, 100.0) * c["gdepth"]).sum().backward()
+    torch.testing.assert_close(disp.grad.cpu(), do.grad, atol=1e-6 * float(do.grad.abs().max()), rtol=1e-5)
+
+
+@pytest.mark.parametrize("s", [0, 1, 2, 3])
+def test_smooth_loss_matches_golden_and_autograd(ops, gold, s):
+    """mean normalisation + edge-aware smoothness (trainer.py:712-714, layers.py:630-643) vs the reference's value and the
+    oracle's autograd; normalize=False is the public get_smooth_loss."""
+    import torch.nn.functional as F
+    from movedepth_b200 import layers as PL
+    c = C.case_disp_pyramid()
+    img = F.interpolate(c["img"], [c["H"] // 2 ** s, c["W"] // 2 ** s], mode="area") if s else c["img"]
+    for normalize in (True, False):
+        disp = g(c["disp"][s]).requires_grad_(True)
+        loss = ops.smooth_loss(disp, g(img), normalize=normalize) if normalize else PL.get_smooth_loss(disp, g(img))
+        do = c["disp"][s].clone().requires_grad_(True)
+        want = OL.normalized_smooth_loss(do, img) if normalize else OL.smooth_loss(do, img)
+        if normalize:
+            np.testing.assert_allclose(loss.detach().cpu().numpy(), gold["smooth_norm_s%d" % s], rtol=1e-5)
+        torch.testing.assert_close(loss.detach().cpu(), want.detach(), rtol=1e-5, atol=1e-7)
+        (loss * 3.0).backward()
+        (want * 3.0).backward()
+        torch.testing.assert_close(disp.grad.cpu(), do.grad, atol=2e-6 * float(do.grad.abs().max()), rtol=1e-4)
+    c = C.case_images()
+    np.testing.assert_allclose(PL.get_smooth_loss(g(c["disp"]), g(c["x"])).cpu().numpy(), gold["smooth"], rtol=1e-5)
+
+
+def test_masked_smooth_l1_matches_golden_and_autograd(ops, gold):
+    """masked-augmentation consistency (trainer.py:398-400): selection by the resized box mask, mean smooth-L1, weight 100."""
+    c = C.case_masked()
+    for i, xy in enumerate(c["boxes"]):
+        a, b = g(c["a"]).requires_grad_(True), g(c["b"]).requires_grad_(True)
+        box = torch.tensor(xy, dtype=torch.int64, device=DEV)
+        loss = ops.masked_smooth_l1(a, b, box, c["H"], c["W"], c["H"] // 3, c["W"] // 3, 100.0)
+        np.testing.assert_allclose(loss.detach().cpu().numpy(), gold["masked_loss_%d" % i], rtol=1e-5)
+        ao, bo = c["a"].clone().requires_grad_(True), c["b"].clone().requires_grad_(True)
+        _, m = OL.box_mask(torch.ones(c["B"], 3, c["H"], c["W"]), (c["H"] // 3, c["W"] // 3), xy)
+        want = OL.masked_consistency(ao, bo, m, 100.0)
+        (loss * 0.5).backward()
+        (want * 0.5).backward()
+        torch.testing.assert_close(a.grad.cpu(), ao.grad, atol=1e-7, rtol=1e-5)
+        torch.testing.assert_close(b.grad.cpu(), bo.grad, atol=1e-7, rtol=1e-5)
+        sel = torch.from_numpy(gold["masked_sel_%d" % i])
+        assert torch.equal(a.grad.cpu() != 0, sel & ((c["a"] - c["b"]) != 0))
+
+
+# ---------------------------------------------------------------------------------------------- peer-memory all-reduce
+def test_peer_allreduce_two_ranks_on_one_gpu(ops):
+    """csrc/peer.cu (the SyncBatchNorm statistics exchange): two 'ranks' = two streams of this process, each with its own
+    symmetric buffer on the same GPU, publish into each other's buffers, raise the epoch flags and reduce in rank order.
+    Both ranks must hold the bitwise identical sum, over many epochs (double-buffered by epoch parity) and vector lengths."""
+    import ctypes
+    L = ops._lib.lib()
+    world, nmax = 2, 256
+    nbytes = L.mvd_peer_allreduce_buffer_bytes(world, nmax)
+    bufs = [torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=DEV) for _ in range(world)]
+    ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=DEV)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    gen = torch.Generator(device=DEV).manual_seed(33)
+    torch.cuda.synchronize()
+    for it in range(40):
+        n = (16, 64, 256, 1)[it % 4]
+        vs = [torch.randn(n, dtype=torch.float64, device=DEV, generator=gen) for _ in range(world)]
+        outs = [torch.empty(n, dtype=torch.float64, device=DEV) for _ in range(world)]
+        torch.cuda.synchronize()
+        for r in range(world):
+            rc = L.mvd_peer_allreduce_f64(ctypes.c_void_p(vs[r].data_ptr()), ctypes.c_void_p(outs[r].data_ptr()), n,
+                                          ctypes.c_void_p(ptrs.data_ptr()), r, world, nmax, ctypes.c_void_p(streams[r].cuda_stream))
+            assert rc == 0
+        torch.cuda.synchronize()
+        assert torch.equal(outs[0], outs[1])
+        assert torch.equal(outs[0], vs[0] + vs[1])
+    for b in bufs:                                   # [1] of the header = epoch of a timed-out wait (0: none)
+        assert int(b.view(torch.int64)[1]) == 0 and int(b.view(torch.int64)[0]) == 40

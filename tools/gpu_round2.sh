@@ -1,0 +1,11 @@
+#!/bin/bash
+# One GPU-box visit (round 2): parity tests (kernel file first, no -x, deviations printed), smoke, bench, step profile.
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv -lms 500 > gpurun_out/clocks.csv &
+SMI=$!
+timeout 1800 env MVD_REPORT=1 python -m pytest tests -m gpu -q -s -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+tail -5 gpurun_out/pytest_gpu.log
+timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -1 gpurun_out/bench.log
+timeout 300 python tools/profile_step.py --ops > gpurun_out/step_profile.log 2>&1; head -12 gpurun_out/step_profile.log
+kill $SMI

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--top", type=int, default=45)
     ap.add_argument("--D", type=int, default=96)
     ap.add_argument("--B", type=int, default=6)
+    ap.add_argument("--ops", action="store_true", help="also print the per-ATen-op table (self device time): which tensor ops launch the at:: kernels")
     a = ap.parse_args()
     argv = ["--height", "192", "--width", "640", "--num_depth_bins", str(a.D), "--batch_size", str(a.B), "--frame_ids", "0", "-1",
             "--weights_init", "scratch", "--convex_up", "--learning_rate", "2e-4", "--b200_conv_precision", a.precision,
@@ -47,6 +48,17 @@ def main():
     print("GPU busy %.2f ms over %d kernels/copies in one step (precision=%s)" % (total / 1e3, n, a.precision))
     for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:a.top]:
         print("%9.1f us %5d %5.1f%%  %s" % (t, c, 100 * t / total, k))
+    if a.ops:
+        rows = []
+        for e in prof.key_averages():
+            t = getattr(e, "self_device_time_total", None)
+            if t is None:
+                t = e.self_cuda_time_total
+            if t > 0:
+                rows.append((t, e.count, e.key))
+        print("\nper-op self device time (top %d)" % a.top)
+        for t, c, k in sorted(rows, reverse=True)[:a.top]:
+            print("%9.1f us %5d %5.1f%%  %s" % (t, c, 100 * t / total, k[:100]))
 
 
 if __name__ == "__main__":
