@@ -64,35 +64,32 @@ def _import_reference():
     return rt, MonodepthOptions
 
 
-def time_reference(cfg, batch, steps, warmup, make_inputs, threads=None):
-    """frames/s of the reference's own training step on the host cores.
+class ReferenceStep:
+    """The reference's own training step on the host cores: Trainer(opts) -> process_batch -> backward -> Adam.step.
     cfg: dict(height, width, num_depth_bins, res_arch, frame_ids, epoch); make_inputs(opt, batch) -> item dict."""
-    import torch
-    torch.set_num_threads(threads or os.cpu_count() or 1)
-    rt, Options = _import_reference()
-    argv = ["--no_cuda", "--weights_init", "scratch", "--num_workers", "0", "--data_path", "/nonexistent", "--png",
-            "--log_dir", "/tmp/mvd_reference", "--prior_scale", "2", "--convex_up", "--learning_rate", "2e-4",
-            "--height", str(cfg["height"]), "--width", str(cfg["width"]), "--num_depth_bins", str(cfg["num_depth_bins"]),
-            "--batch_size", str(batch), "--res_arch", str(cfg["res_arch"]),
-            "--frame_ids"] + [str(f) for f in cfg["frame_ids"]]
-    opt = Options().parser.parse_args(argv)
-    torch.manual_seed(0)
-    tr = rt.Trainer(opt)
-    tr.set_train()
-    tr.epoch, tr.step = cfg["epoch"], 0
-    inputs = make_inputs(opt, batch)
 
-    def one():
-        outputs, losses = tr.process_batch(dict(inputs), is_train=True)
+    def __init__(self, cfg, batch, make_inputs, threads=None):
+        import torch
+        torch.set_num_threads(threads or os.cpu_count() or 1)
+        rt, Options = _import_reference()
+        argv = ["--no_cuda", "--weights_init", "scratch", "--num_workers", "0", "--data_path", "/nonexistent", "--png",
+                "--log_dir", "/tmp/mvd_reference", "--prior_scale", "2", "--convex_up", "--learning_rate", "2e-4",
+                "--height", str(cfg["height"]), "--width", str(cfg["width"]), "--num_depth_bins", str(cfg["num_depth_bins"]),
+                "--batch_size", str(batch), "--res_arch", str(cfg["res_arch"]),
+                "--frame_ids"] + [str(f) for f in cfg["frame_ids"]]
+        opt = Options().parser.parse_args(argv)
+        torch.manual_seed(0)
+        self.trainer = rt.Trainer(opt)
+        self.trainer.set_train()
+        self.trainer.epoch, self.trainer.step = cfg["epoch"], 0
+        self.inputs = make_inputs(opt, batch)
+        self.batch = batch
+        self.threads = torch.get_num_threads()
+
+    def step(self):
+        tr = self.trainer
+        outputs, losses = tr.process_batch(dict(self.inputs), is_train=True)
         tr.model_optimizer.zero_grad()
         losses["loss"].backward()
         tr.model_optimizer.step()
-        return float(losses["loss"])
-
-    for _ in range(warmup):
-        one()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        one()
-    dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps, torch.get_num_threads()
+        return float(losses["loss"].detach())

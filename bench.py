@@ -110,31 +110,48 @@ def oracle_options(cfg, batch):
                            matching_ids=[0, -1], res_arch=cfg["arch"], learning_rate=2e-4)
 
 
-def time_cpu(cfg, args, steps, warmup, batch):
-    """frames/s of the reference's training step on the host cores: the unmodified reference from baseline/_ref when it is
-    installed (kind "reference"), else the oracle port (kind "port").  Returns (fps, sec/step, threads, kind)."""
-    import torch
-    from oracle.step import OracleStep, synthetic_inputs
-    epoch = 0 if args.fixed_range else 9
-    make = lambda opt, b: synthetic_inputs(opt, b, seed=1, smooth=not args.noise)
-    from baseline import reference_runner as RR
-    with contextlib.redirect_stdout(sys.stderr):              # the reference prints its banner on stdout
-        if RR.available() and not args.port:
-            fps, sec, cores = RR.time_reference(dict(height=cfg["H"], width=cfg["W"], num_depth_bins=cfg["D"], res_arch=cfg["arch"],
-                                                     frame_ids=cfg["frame_ids"], epoch=epoch), batch, steps, warmup, make)
-            return fps, sec, cores, "reference"
+class _PortStep:
+    def __init__(self, cfg, batch, make_inputs, epoch):
+        import torch
+        from oracle.step import OracleStep
         torch.set_num_threads(os.cpu_count() or 1)
         opt = oracle_options(cfg, batch)
         torch.manual_seed(0)
-        st = OracleStep(opt)
-        inputs = make(opt, batch)
-        for _ in range(warmup):
-            st.train_step(dict(inputs), epoch=epoch)
+        self.st, self.inputs, self.epoch, self.batch = OracleStep(opt), make_inputs(opt, batch), epoch, batch
+        self.threads = torch.get_num_threads()
+
+    def step(self):
+        self.st.train_step(dict(self.inputs), epoch=self.epoch)
+
+
+def time_cpu(cfg, args, steps, warmup, batch, budget_s):
+    """frames/s of the reference's training step on the host cores: the unmodified reference from baseline/_ref when it is
+    installed (kind "reference"), else the oracle port (kind "port").  The step runs the workload's full batch; only when
+    the first (warm-up) step shows that `steps + warmup` of them cannot finish within `budget_s` is the per-step sample
+    bounded to fewer frames (stated in the returned `sample`).  Returns (fps, sec/step, threads, kind, frames per step)."""
+    from oracle.step import synthetic_inputs
+    from baseline import reference_runner as RR
+    epoch = 0 if args.fixed_range else 9
+    make = lambda opt, b: synthetic_inputs(opt, b, seed=1, smooth=not args.noise)
+    use_ref = RR.available() and not args.port
+    rcfg = dict(height=cfg["H"], width=cfg["W"], num_depth_bins=cfg["D"], res_arch=cfg["arch"], frame_ids=cfg["frame_ids"], epoch=epoch)
+    build = (lambda b: RR.ReferenceStep(rcfg, b, make)) if use_ref else (lambda b: _PortStep(cfg, b, make, epoch))
+    with contextlib.redirect_stdout(sys.stderr):              # the reference prints its banner on stdout
+        runner = build(batch)
+        t0 = time.perf_counter()
+        runner.step()                                         # first warm-up step, timed to size the sample
+        t1 = time.perf_counter() - t0
+        if t1 * (steps + warmup) > budget_s and batch > 1:
+            batch = max(1, int(batch * budget_s / (t1 * (steps + warmup))))
+            runner = build(batch)
+            runner.step()
+        for _ in range(warmup - 1):
+            runner.step()
         t0 = time.perf_counter()
         for _ in range(steps):
-            st.train_step(dict(inputs), epoch=epoch)
+            runner.step()
         dt = time.perf_counter() - t0
-    return batch * steps / dt, dt / steps, torch.get_num_threads(), "port"
+    return batch * steps / dt, dt / steps, runner.threads, "reference" if use_ref else "port", batch
 
 
 def run_reference(args, cfg):
@@ -142,9 +159,10 @@ def run_reference(args, cfg):
     if rank != 0:
         return
     warm = max(1, args.warmup)
-    fps, sec, cores, kind = time_cpu(cfg, args, args.steps, warm, cfg["B"])
-    sample = "%d frames per step (the workload's batch), %d timed steps after %d warm-up, torch CPU with %d threads" % (
-        cfg["B"], args.steps, warm, cores)
+    fps, sec, cores, kind, frames = time_cpu(cfg, args, args.steps, warm, cfg["B"], budget_s=args.cpu_budget)
+    sample = "%d frames per step (%s), %d timed steps after %d warm-up, torch CPU with %d threads" % (
+        frames, "the workload's batch" if frames == cfg["B"] else "bounded: %d steps of the full batch of %d exceed %d s on this host"
+        % (args.steps + warm, cfg["B"], args.cpu_budget), args.steps, warm, cores)
     print(json.dumps({
         "impl": "reference", "metric": metric_name(cfg), "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -353,9 +371,9 @@ def run_own(args, cfg):
         "gpu_launches": launches,
     }
     if world == 1 and not args.no_cpu_baseline:
-        fps, sec, cores, kind = time_cpu(cfg, args, 2, 1, BATCH)
+        fps, sec, cores, kind, frames = time_cpu(cfg, args, 2, 1, BATCH, budget_s=45)
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind,
-                                "sample": "%d frames per step (the workload's batch), 2 timed steps after 1 warm-up" % BATCH}
+                                "sample": "%d frames per step (workload batch %d), 2 timed steps after 1 warm-up" % (frames, BATCH)}
     print(json.dumps(line), flush=True)
     shutdown(tr, world)
 
@@ -371,6 +389,7 @@ def main():
     ap.add_argument("--fixed_range", action="store_true", help="epoch-0 fixed hypothesis range instead of the velocity-guided one")
     ap.add_argument("--velocity", action="store_true", help="(default now) velocity-guided hypothesis range; kept for old command lines")
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--cpu_budget", type=int, default=600, help="reference arm: seconds the K+W host steps may take before the per-step sample is bounded")
     ap.add_argument("--port", action="store_true", help="reference arm / cpu_baseline: time the oracle port even when baseline/_ref exists")
     ap.add_argument("--noise", action="store_true", help="U[0,1) white-noise images (SURVEY 8d) instead of band-limited ones")
     ap.add_argument("--verbose", action="store_true", help="print the pose / prior statistics the cost-volume kernel saw")

@@ -180,6 +180,21 @@ int mvd_masked_smooth_l1_bwd(const float* gloss, const float* a, const float* b,
                              const double* sums, float* ga, float* gb, long long n, float weight, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * DepthDecoder glue (csrc/decoder.cu): everything between two 3x3 convolutions of the U-Net decoder
+ * (movedepth/networks/depth_decoder.py:72-101; ConvBlock / Conv3x3 / upsample of layers.py:521-553, 624-627) in one pass:
+ *   xp = ReflectionPad2d(1)( cat( nearest_up(act(z + bias), up), skip ) ),   x3 = [hi | lo | hi] TF32 split of xp (optional)
+ *   z    : [B,h,w,C1] channels-last raw output of the previous conv (bias NOT yet added), or a plain feature map
+ *   bias : [C1] or NULL;  act: 0 = identity, 1 = ELU(alpha=1);  up: 1 or 2 (nearest)
+ *   skip : [B,up*h,up*w,C2] channels-last or NULL (C2 == 0);  C1, C2 multiples of 4
+ *   xp   : [B,up*h+2,up*w+2,C1+C2];  x3: [B,up*h+2,up*w+2,3*(C1+C2)] or NULL
+ * bwd: gxp -> gz [B,h,w,C1], gskip [B,up*h,up*w,C2] (or NULL), gbias [C1] (or NULL), all OVERWRITTEN.
+ * ------------------------------------------------------------------------------------- */
+int mvd_decoder_prep_fwd(const float* z, const float* bias, const float* skip, float* xp, float* x3, int B, int h,
+                         int w, int C1, int C2, int up, int act, void* stream);
+int mvd_decoder_prep_bwd(const float* gxp, const float* z, const float* bias, float* gz, float* gskip, float* gbias,
+                         int B, int h, int w, int C1, int C2, int up, int act, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Fused multi-tensor Adam on a flat fp32 arena (torch.optim.Adam semantics, no amsgrad, no
  * weight decay; replaces optimizer.step() movedepth/trainer.py:137-141, 272).
  *   step_size = lr / (1 - beta1^t);  bias2 = sqrt(1 - beta2^t)

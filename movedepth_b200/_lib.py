@@ -42,6 +42,8 @@ SIGNATURES = {
     "mvd_smooth_loss_bwd": ([_P] * 6 + [_I] * 4 + [_P], _I),
     "mvd_masked_smooth_l1_fwd": ([_P] * 6 + [_I] * 7 + [_F, _P], _I),
     "mvd_masked_smooth_l1_bwd": ([_P] * 7 + [_LL, _F, _P], _I),
+    "mvd_decoder_prep_fwd": ([_P] * 5 + [_I] * 7 + [_P], _I),
+    "mvd_decoder_prep_bwd": ([_P] * 6 + [_I] * 7 + [_P], _I),
     "mvd_split_tf32": ([_P, _P, _LL, _I, _I, _P], _I),
     "mvd_conv3d_c16o1_fwd": ([_P] * 3 + [_I] * 4 + [_P], _I),
     "mvd_conv3d_c16o1_dgrad": ([_P] * 3 + [_I] * 4 + [_P], _I),

@@ -264,12 +264,14 @@ int mvd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
 // 10-bit mantissa.  pattern 0: [hi, lo, hi] (activations / gradients), pattern 1: [hi, hi, lo] (weights).
 // One pass instead of round/sub/cat; rows are channels-last pixels (C innermost).
 namespace mvd {
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
+
 __global__ void __launch_bounds__(256)
 split_tf32_kernel(const float* __restrict__ x, float* __restrict__ out, long long n, int C, int pattern) {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride) {
         const float v = __ldg(x + i);
-        const float hi = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u);
+        const float hi = tf32_hi(v);
         const float lo = v - hi;
         const long long r = i / C;
         const int c = static_cast<int>(i - r * C);
@@ -279,12 +281,36 @@ split_tf32_kernel(const float* __restrict__ x, float* __restrict__ out, long lon
         o[2 * C] = pattern == 0 ? hi : lo;
     }
 }
+
+// C % 4 == 0: one thread per 4 channels, 16-byte loads and stores (the scalar kernel ran at 3.7 TB/s on the 283 MB volume)
+__global__ void __launch_bounds__(256)
+split_tf32_v4_kernel(const float4* __restrict__ x, float4* __restrict__ out, long long n4, int C4, int pattern) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
+        const float4 v = __ldg(x + i);
+        const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+        const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+        const long long r = i / C4;
+        const int c = static_cast<int>(i - r * C4);
+        float4* o = out + r * (3LL * C4) + c;
+        o[0] = hi;
+        o[C4] = pattern == 0 ? lo : hi;
+        o[2 * C4] = pattern == 0 ? hi : lo;
+    }
+}
 }  // namespace mvd
 
 extern "C" int mvd_split_tf32(const float* x, float* out, long long n, int C, int pattern, void* stream) {
     MVD_REQUIRE(x && out, "null pointer argument");
     MVD_REQUIRE(n >= 0 && C > 0 && n % C == 0 && (pattern == 0 || pattern == 1), "bad split arguments n=%lld C=%d", n, C);
     if (n == 0) return 0;
+    if (C % 4 == 0 && mvd::aligned16(x) && mvd::aligned16(out)) {
+        const long long n4 = n / 4;
+        const int grid = static_cast<int>(min(static_cast<long long>(mvd::sm_count()) * 16, (n4 + 255) / 256));
+        mvd::split_tf32_v4_kernel<<<grid, 256, 0, mvd::as_stream(stream)>>>(reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(out),
+                                                                            n4, C / 4, pattern);
+        return mvd::check_launch("split_tf32_v4");
+    }
     const int grid = static_cast<int>(min(static_cast<long long>(mvd::sm_count()) * 16, (n + 255) / 256));
     mvd::split_tf32_kernel<<<grid, 256, 0, mvd::as_stream(stream)>>>(x, out, n, C, pattern);
     return mvd::check_launch("split_tf32");

@@ -13,6 +13,9 @@ from ..layers import ConvBlock, Conv3x3, upsample
 from .resnet_encoder import ConvBnReLUSeq
 
 
+fused = True             # set False to run the decoder as separate tensor ops (A/B measurements, parity isolation)
+
+
 class DepthDecoder(nn.Module):
     """U-Net decoder over the 5 encoder maps -> sigmoid disparity at `scales`.
     Reference: movedepth/networks/depth_decoder.py:10-101 in the configuration the trainer uses
@@ -42,7 +45,30 @@ class DepthDecoder(nn.Module):
     def _m(self, *key):
         return self.decoder[self._slot[key]]
 
+    def _forward_fused(self, input_features):
+        """CUDA path: between two convolutions everything (bias, ELU, nearest x2, skip concatenation, reflection padding and
+        the 3xTF32 operand split) is ONE `decoder_prep` kernel; the convolutions themselves see pre-padded inputs."""
+        from .. import ops
+        want = PR.get_policy() == "3xtf32"
+        self.outputs = {}
+        xp, x3 = ops.decoder_prep(input_features[-1], None, None, act=False, up=1, want_split=want)
+        for i in range(4, -1, -1):
+            c0 = self._m("upconv", i, 0).conv.conv
+            z = PR.prepared_conv(xp, x3, c0.weight)
+            skip = input_features[i - 1] if (self.use_skips and i > 0) else None
+            xp, x3 = ops.decoder_prep(z, c0.bias, skip, act=True, up=2, want_split=want)
+            c1 = self._m("upconv", i, 1).conv.conv
+            z = PR.prepared_conv(xp, x3, c1.weight)
+            if i in self.scales or i > 0:                # this padded activation feeds dispconv(i) and upconv(i-1, 0)
+                xp, x3 = ops.decoder_prep(z, c1.bias, None, act=True, up=1, want_split=want)
+            if i in self.scales:
+                dc = self._m("dispconv", i).conv
+                self.outputs[("disp", i)] = torch.sigmoid(PR.prepared_conv(xp, x3, dc.weight) + dc.bias.view(1, -1, 1, 1))
+        return self.outputs
+
     def forward(self, input_features, **unused):
+        if input_features[-1].is_cuda and input_features[-1].dtype == torch.float32 and fused:
+            return self._forward_fused(input_features)
         self.outputs = {}
         x = input_features[-1]
         for i in range(4, -1, -1):

@@ -578,3 +578,52 @@ def masked_smooth_l1(a, b, box_xy, height, width, box_h, box_w, weight=1.0):
     selected when the bilinear (align_corners=True) resize of the [height,width] box mask (zeros in the box_h x box_w box
     at box_xy = device int64 (x, y)) is non-zero there.  Reference: movedepth/trainer.py:398-400."""
     return _MaskedSmoothL1.apply(a, b, box_xy, int(height), int(width), int(box_h), int(box_w), float(weight))
+
+
+# ------------------------------------------------------------------------------------- DepthDecoder glue
+class _DecoderPrep(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z, bias, skip, act, up, want_split):
+        B, C1, h, w = z.shape
+        z = _nhwc(z)
+        skip_c = _nhwc(skip) if skip is not None else None
+        C2 = skip_c.shape[1] if skip_c is not None else 0
+        H, W, C = h * up, w * up, C1 + C2
+        if skip_c is not None:
+            assert skip_c.shape == (B, C2, H, W), (z.shape, skip.shape, up)
+        bias_c = _f32(bias).contiguous() if bias is not None else None
+        xp = torch.empty((B, C, H + 2, W + 2), device=z.device, dtype=torch.float32, memory_format=torch.channels_last)
+        x3 = torch.empty((B, 3 * C, H + 2, W + 2), device=z.device, dtype=torch.float32,
+                         memory_format=torch.channels_last) if want_split else None
+        rc = _lib.lib().mvd_decoder_prep_fwd(_p(z), _p(bias_c), _p(skip_c), _p(xp), _p(x3), B, h, w, C1, C2, up, int(act), _stream())
+        _lib.check(rc, "mvd_decoder_prep_fwd")
+        launch_counter["n"] += 1
+        ctx.save_for_backward(z, bias_c)
+        ctx.meta = (B, h, w, C1, C2, up, int(act), skip is not None, bias is not None)
+        if x3 is None:
+            x3 = z.new_empty(0)
+        ctx.mark_non_differentiable(x3)
+        return xp, x3
+
+    @staticmethod
+    def backward(ctx, gxp, _gx3):
+        z, bias_c = ctx.saved_tensors
+        B, h, w, C1, C2, up, act, has_skip, has_bias = ctx.meta
+        gxp = _nhwc(gxp)
+        gz = torch.empty_like(z)                                  # channels-last
+        gskip = torch.empty((B, C2, h * up, w * up), device=z.device, dtype=torch.float32,
+                            memory_format=torch.channels_last) if has_skip else None
+        gbias = torch.empty(C1, device=z.device, dtype=torch.float32) if has_bias else None
+        rc = _lib.lib().mvd_decoder_prep_bwd(_p(gxp), _p(z), _p(bias_c), _p(gz), _p(gskip), _p(gbias), B, h, w, C1, C2, up, act,
+                                             _stream())
+        _lib.check(rc, "mvd_decoder_prep_bwd")
+        launch_counter["n"] += 2 if has_skip else 1
+        return gz, gbias, gskip, None, None, None
+
+
+def decoder_prep(z, bias=None, skip=None, act=True, up=1, want_split=False):
+    """ReflectionPad2d(1)(cat(nearest_up(act(z + bias), up), skip)) in one kernel, plus (want_split) the 3xTF32 operand
+    split of the result.  z: [B,C1,h,w] raw conv output (channels-last storage), skip: [B,C2,up*h,up*w] or None.
+    Returns (xp [B,C1+C2,up*h+2,up*w+2], x3 [B,3(C1+C2),...] or an empty tensor).
+    Reference: movedepth/networks/depth_decoder.py:72-101, layers.py:521-553, 624-627."""
+    return _DecoderPrep.apply(z, bias, skip, bool(act), int(up), bool(want_split))

@@ -128,6 +128,44 @@ class _SplitConv(torch.autograd.Function):
         return gx, gw, None, None, None, None
 
 
+class _PreparedConv(torch.autograd.Function):
+    """y = conv2d(xp, w) with NO padding on an input that is already padded (and, under 3xTF32, already split: `x3`)."""
+
+    @staticmethod
+    def forward(ctx, xp, x3, w):
+        ctx.save_for_backward(xp, w)
+        prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = True
+        try:
+            return torch.ops.aten.convolution(x3, _split_dim1(w, True), None, (1, 1), (0, 0), (1, 1), False, (0, 0), 1)
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev
+
+    @staticmethod
+    def backward(ctx, gy):
+        xp, w = ctx.saved_tensors
+        gy = gy.contiguous(memory_format=torch.channels_last)
+        prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = True
+        try:
+            gx, gw, _ = torch.ops.aten.convolution_backward(gy, xp, w.contiguous(memory_format=torch.channels_last), None, (1, 1),
+                                                            (0, 0), (1, 1), False, (0, 0), 1,
+                                                            [ctx.needs_input_grad[0], ctx.needs_input_grad[2], False])
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev
+        return gx, None, gw
+
+
+def prepared_conv(xp, x3, weight):
+    """3x3 (or any) stride-1 convolution, no padding, no bias, of a pre-padded channels-last input following the
+    precision policy; `x3` is the pre-split operand the DepthDecoder glue kernel wrote (used under 3xtf32 only)."""
+    if _policy["mode"] == "3xtf32" and not _policy["split_backward"] and x3.numel():
+        return _PreparedConv.apply(xp, x3, weight)
+    if _policy["mode"] == "3xtf32":
+        return _SplitConv.apply(xp, weight, (1, 1), (0, 0), (0, 0), False)
+    return torch.nn.functional.conv2d(xp, weight)
+
+
 def _tup(v, n):
     return tuple(v) if isinstance(v, (tuple, list)) else (v,) * n
 

@@ -374,7 +374,8 @@ def _sync_bn_worker(rank, world, port, q):
     xs = x[rank * 2:rank * 2 + 2].to("cuda:0").contiguous(memory_format=torch.channels_last).requires_grad_(True)
     y = NM.bn_act(bn, xs, relu=True)
     (y * gy[rank * 2:rank * 2 + 2].to("cuda:0")).sum().backward()
-    q.put((rank, y.detach().cpu(), xs.grad.cpu(), bn.weight.grad.cpu(), bn.running_var.cpu()))
+    # numpy arrays travel by value: tensors would be shared through file descriptors that die with this process
+    q.put((rank, y.detach().cpu().numpy(), xs.grad.cpu().numpy(), bn.weight.grad.cpu().numpy(), bn.running_var.cpu().numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -389,7 +390,7 @@ def test_sync_batchnorm_statistics_are_exchanged_across_ranks():
     procs = [ctx.Process(target=_sync_bn_worker, args=(r, 2, 29533, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = dict((r, rest) for r, *rest in [q.get(timeout=120) for _ in range(2)])
+    got = dict((r, [torch.from_numpy(t) for t in rest]) for r, *rest in [q.get(timeout=120) for _ in range(2)])
     for p in procs:
         p.join(timeout=60)
     gen = torch.Generator().manual_seed(21)
@@ -632,3 +633,92 @@ def test_peer_allreduce_two_ranks_on_one_gpu(ops):
         assert torch.equal(outs[0], vs[0] + vs[1])
     for b in bufs:                                   # [1] of the header = epoch of a timed-out wait (0: none)
         assert int(b.view(torch.int64)[1]) == 0 and int(b.view(torch.int64)[0]) == 40
+
+
+# ---------------------------------------------------------------------------------------------- DepthDecoder glue
+@pytest.mark.parametrize("shape,C2,up,act,bias", [((2, 16, 6, 10), 0, 1, True, True), ((2, 32, 5, 7), 64, 2, True, True),
+                                                   ((1, 512, 2, 4), 0, 1, False, False), ((2, 2048, 2, 3), 0, 1, False, False), ((1, 8, 3, 3), 0, 1, True, True),
+                                                   ((1, 256, 3, 4), 256, 2, True, True)],
+                         ids=["elu-pad", "elu-up-cat-pad", "plain-pad", "plain-pad-r50", "3x3", "c256"])
+def test_decoder_prep_matches_the_tensor_composition(ops, shape, C2, up, act, bias):
+    """mvd_decoder_prep_{fwd,bwd}: ReflectionPad2d(1)(cat(nearest_up(ELU(z + bias)), skip)) and its 3xTF32 split in one kernel
+    vs the torch ops the reference's DepthDecoder strings together (depth_decoder.py:72-101), forward and all gradients."""
+    import torch.nn.functional as F
+    gen = torch.Generator().manual_seed(23)
+    B, C1, h, w = shape
+    z = torch.randn(shape, generator=gen)
+    b = 0.3 * torch.randn(C1, generator=gen) if bias else None
+    skip = torch.randn(B, C2, h * up, w * up, generator=gen) if C2 else None
+    gout = torch.randn(B, C1 + C2, h * up + 2, w * up + 2, generator=gen)
+
+    def compose(z, b, skip):
+        t = z + b.view(1, -1, 1, 1) if b is not None else z
+        t = F.elu(t) if act else t
+        if up == 2:
+            t = F.interpolate(t, scale_factor=2, mode="nearest")
+        if skip is not None:
+            t = torch.cat([t, skip], 1)
+        return F.pad(t, (1, 1, 1, 1), mode="reflect")
+
+    leaves = [t.double().requires_grad_(True) if t is not None else None for t in (z, b, skip)]
+    want = compose(*leaves)
+    (want * gout.double()).sum().backward()
+    cl = torch.channels_last
+    zg = g(z).contiguous(memory_format=cl).requires_grad_(True)
+    bg = g(b).requires_grad_(True) if bias else None
+    sg = g(skip).contiguous(memory_format=cl).requires_grad_(True) if C2 else None
+    xp, x3 = ops.decoder_prep(zg, bg, sg, act=act, up=up, want_split=True)
+    torch.testing.assert_close(xp.cpu(), want.detach().float(), atol=1e-6, rtol=1e-6)
+    C = C1 + C2
+    hi, lo, hi2 = x3[:, :C], x3[:, C:2 * C], x3[:, 2 * C:]
+    assert torch.equal(hi, hi2) and torch.equal(hi + lo, xp)                       # exact split
+    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0                   # hi has a 10-bit mantissa
+    (xp * g(gout)).sum().backward()
+    torch.testing.assert_close(zg.grad.cpu(), leaves[0].grad.float(), atol=1e-5, rtol=1e-5)
+    if bias:
+        torch.testing.assert_close(bg.grad.cpu(), leaves[1].grad.float(), atol=1e-4, rtol=1e-4)
+    if C2:
+        torch.testing.assert_close(sg.grad.cpu(), leaves[2].grad.float(), atol=1e-6, rtol=1e-6)
+
+
+@pytest.mark.parametrize("arch", [18, 50])
+def test_fused_depth_decoder_matches_the_oracle_decoder(ops, arch):
+    """DepthDecoder on the glue kernel + pre-padded convolutions (fp32 policy) vs the oracle's module-by-module decoder on the
+    CPU: the four disparities and the gradients of every parameter and of the encoder features."""
+    from movedepth_b200 import networks as PN, precision as PR
+    from oracle import networks as ON
+    PR.set_policy("fp32")
+    gen = torch.Generator().manual_seed(31)
+    ch = [64, 64, 128, 256, 512] if arch == 18 else [64, 256, 512, 1024, 2048]
+    feats = [torch.randn(2, c, 32 >> i, 64 >> i, generator=gen) for i, c in enumerate(ch)]
+    a, b = PN.DepthDecoder(np.array(ch)), ON.DepthDecoder(np.array(ch))
+    fill_deterministic(a)
+    fill_deterministic(b)
+    a.to(DEV)
+    fa = [g(f).contiguous(memory_format=torch.channels_last).requires_grad_(True) for f in feats]
+    fb = [f.clone().requires_grad_(True) for f in feats]
+    oa, ob = a(fa), b(fb)
+    loss_a = sum((oa[("disp", s)] * (s + 1)).sum() for s in range(4))
+    loss_b = sum((ob[("disp", s)] * (s + 1)).sum() for s in range(4))
+    loss_a.backward()
+    loss_b.backward()
+    for s in range(4):
+        torch.testing.assert_close(oa[("disp", s)].detach().cpu(), ob[("disp", s)].detach(), atol=2e-5, rtol=1e-4)
+    for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        torch.testing.assert_close(pa.grad.cpu(), pb.grad, atol=2e-4 * float(pb.grad.abs().max()) + 1e-7, rtol=1e-3, msg=n)
+    for x, y in zip(fa, fb):
+        torch.testing.assert_close(x.grad.cpu(), y.grad, atol=2e-4 * float(y.grad.abs().max()), rtol=1e-3)
+
+
+def test_split_tf32_vectorised_and_scalar_paths(ops):
+    """mvd_split_tf32: x = hi + lo exactly, hi rounded to TF32; C % 4 == 0 takes the 16-byte path, C = 3 the scalar one."""
+    from movedepth_b200 import precision as PR
+    for shape in ((2, 16, 5, 7), (1, 3, 6, 9), (2, 8, 3, 4, 5)):
+        fmt = torch.channels_last_3d if len(shape) == 5 else torch.channels_last
+        x = torch.randn(shape, device=DEV).contiguous(memory_format=fmt)
+        for weight in (False, True):
+            y = PR._split_dim1(x, weight)
+            C = shape[1]
+            hi = PR.tf32_round(x)
+            want = torch.cat([hi, hi, x - hi] if weight else [hi, x - hi, hi], 1)
+            assert torch.equal(y, want) and y.shape[1] == 3 * C

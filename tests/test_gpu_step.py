@@ -19,7 +19,7 @@ MONO = ("mono_encoder", "mono_depth", "pose_encoder", "pose")
 
 
 # ---------------------------------------------------------------------------------------------- whole step
-def _trainer(cfg, precision="fp32", extra=()):
+def _trainer(cfg, precision="fp32", extra=(), fill=True):
     from movedepth_b200.options import MonodepthOptions
     from movedepth_b200.trainer import Trainer
     argv = ["--height", str(cfg["H"]), "--width", str(cfg["W"]), "--num_depth_bins", str(cfg["D"]), "--batch_size",
@@ -27,8 +27,9 @@ def _trainer(cfg, precision="fp32", extra=()):
             "--learning_rate", "2e-4", "--b200_conv_precision", precision, "--log_dir", "/tmp/mvd_test",
             "--frame_ids"] + [str(f) for f in cfg["frame_ids"]] + list(extra)
     tr = Trainer(MonodepthOptions().parse(argv))
-    for k, m in tr.models.items():
-        fill_deterministic(m, salt=k + "/")
+    if fill:
+        for k, m in tr.models.items():
+            fill_deterministic(m, salt=k + "/")
     tr.epoch = cfg["epoch"]
     return tr
 
@@ -122,8 +123,10 @@ def test_whole_step_matches_reference_golden(name):
     # r50_3f runs ResNet50 at batch 1: its deepest BatchNorms take statistics over 2x3 = 6 samples and amplify the
     # GPU-vs-CPU fp32 summation-order noise to 3e-5 on disp_2, i.e. 4e-4 relative on the volume (tools/diag_parity.py),
     # which flips the D=8 argmax at ~2 % of the pixels; the other cases stay above 99 %.
-    _check_step(ck, tr, out, losses, gold, cfg, name, depth_bar=0.96 if name == "r50_3f" else 0.99,
-                mvs_grad_tol=0.05 if name == "r50_3f" else 0.02, mono_grad_tol=1e-2, probe_tol=1e-2, loss_rtol=2e-3)
+    # measured on B200 (profiles/r02_parity_report.txt): depth fractions 0.9994-1.0, gradient norms within 1e-3 (mono / pose)
+    # and 4.3e-3 (cost-volume branch), probed gradients within 1.2e-3 / 1.9e-2 of their maximum
+    _check_step(ck, tr, out, losses, gold, cfg, name, depth_bar=0.99 if name == "r50_3f" else 0.998,
+                mvs_grad_tol=0.02, mono_grad_tol=3e-3, probe_tol=5e-3, loss_rtol=2e-3)
     ck.finish()
 
 
@@ -148,9 +151,10 @@ def test_benchmarked_configuration_matches_reference_golden(name):
     """The configuration behind every bench number -- 3xTF32 forward, single-pass TF32 gradients (operands truncated by the
     tensor core), whole step replayed as a CUDA graph -- against the REFERENCE's outputs AND gradients.  The trainer is
     stepped until the graph is captured, then weights / moments / BatchNorm buffers are restored and the captured graph
-    takes the golden step.  Bars: >= 97 % of depth_mvs pixels and every mono depth within 1e-3 relative; gradient norms
-    within 3 % (mono / pose branch) and 10 % (cost-volume branch: argmax flips feed the masked-consistency term); probed
-    gradients within 3 % / 30 % of their maximum (TF32 has 10 mantissa bits: ~1e-3 per product, accumulated)."""
+    takes the golden step.  Bars: >= 99 % of depth_mvs pixels and every mono depth within 1e-3 relative; gradient norms
+    within 1 % (mono / pose branch) and 5 % (cost-volume branch: argmax flips feed the masked-consistency term); probed
+    gradients within 1.5 % / 15 % of their maximum (TF32 has 10 mantissa bits: ~1e-3 per product, accumulated).
+    Measured (profiles/r02_parity_report.txt): depth 0.9978-1.0, gradient norms 2e-3 / 1.5e-2, probes 3.6e-3 / 6.2e-2."""
     cfg = C.STEP_CASES[name]
     gold = dict(np.load(os.path.join(GOLD, "step_%s.npz" % name)))
     tr = _trainer(cfg, "3xtf32", ["--b200_cuda_graph"])
@@ -163,7 +167,7 @@ def test_benchmarked_configuration_matches_reference_golden(name):
     out, losses = tr.train_step(dict(inputs), noise=noise, mask_xy=xy)       # a replay of the captured graph
     torch.cuda.synchronize()
     ck = _Checker("whole step %s, 3xtf32 + CUDA graph (the benchmarked configuration)" % name)
-    _check_step(ck, tr, out, losses, gold, cfg, name, depth_bar=0.97, mvs_grad_tol=0.10, mono_grad_tol=3e-2, probe_tol=3e-2,
+    _check_step(ck, tr, out, losses, gold, cfg, name, depth_bar=0.99, mvs_grad_tol=0.05, mono_grad_tol=1e-2, probe_tol=1.5e-2,
                 loss_rtol=1e-2)
     ck.finish()
 
@@ -173,8 +177,9 @@ def test_cuda_graph_step_is_the_eager_step():
     noise generators are re-seeded identically before every step, so the auto-mask sees identical noise): six steps --
     three side-stream warm-ups, the capture, two replays.  What remains between the two runs is the order of floating-point
     atomics (cost-volume / pose / BatchNorm reductions, cuDNN split-k), ~1e-6 relative, which the argmax of localmax can
-    amplify at isolated pixels of the cost-volume branch.  Bars: loss within 1e-4 relative; the mono / pose gradient arena
-    within 1e-4 of its maximum everywhere; the cost-volume arena within 1e-3 of its maximum on all but 1e-4 of its entries."""
+    amplify at isolated pixels of the cost-volume branch.  Bars: loss within 1e-5 relative; the mono / pose gradient arena
+    within 1e-5 of its maximum everywhere; the cost-volume arena within 1e-3 of its maximum on all but 1e-5 of its entries
+    (measured: 5e-6 of the maximum everywhere, profiles/r02_parity_report.txt)."""
     from movedepth_b200.trainer import SyntheticKITTI
     cfg = dict(C.STEP_CASES["r18_2f"], epoch=0)
     eager, graphed = _trainer(cfg), _trainer(cfg, extra=["--b200_cuda_graph"])
@@ -186,15 +191,15 @@ def test_cuda_graph_step_is_the_eager_step():
             np.random.seed(100 + i)
             tr.noise_generator.manual_seed(200 + i)
             losses.append(float(tr.train_step(batch)[1]["loss"].detach()))
-        ck.le("step %d: loss relative difference" % i, abs(losses[1] - losses[0]) / abs(losses[0]), 1e-4)
+        ck.le("step %d: loss relative difference" % i, abs(losses[1] - losses[0]) / abs(losses[0]), 1e-5)
         for j, (a, b) in enumerate(zip(eager.arenas, graphed.arenas)):
             scale = float(a.grad.abs().max())
             diff = (b.grad - a.grad).abs() / scale
             if j == 0:
-                ck.le("step %d: mono/pose gradient arena, max difference / max" % i, float(diff.max()), 1e-4)
+                ck.le("step %d: mono/pose gradient arena, max difference / max" % i, float(diff.max()), 1e-5)
             else:
                 ck.le("step %d: cost-volume gradient arena, fraction of entries off by > 1e-3 of max" % i,
-                      float((diff > 1e-3).float().mean()), 1e-4)
+                      float((diff > 1e-3).float().mean()), 1e-5)
                 ck.le("step %d: cost-volume gradient arena, max difference / max" % i, float(diff.max()), 5e-2)
     assert len(graphed._graphs) == 1, "the graph was never captured"
     ck.finish()
@@ -218,7 +223,7 @@ def test_checkpoint_round_trip_restores_weights_and_adam_state(tmp_path):
     ref_opt.load_state_dict(adam)                                              # the reference's optimizer accepts the file
     names = ["mono_encoder", "mono_depth", "pose_encoder", "pose", "mask_cnn", "mvs_encoder", "reg3d", "up"]
     b = _trainer(cfg, extra=["--model_name", "ckpt_b", "--log_dir", str(tmp_path), "--load_weights_folder", folder,
-                             "--models_to_load"] + names)
+                             "--models_to_load"] + names, fill=False)
     b.epoch = a.epoch
     assert b.opt_step == a.opt_step == 2
     for x, y in zip(a.arenas, b.arenas):

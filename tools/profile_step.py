@@ -33,7 +33,7 @@ def main():
     for _ in range(4):
         tr.train_step(batch)
     torch.cuda.synchronize()
-    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=a.ops) as prof:
         tr.train_step(batch)
         torch.cuda.synchronize()
     agg = collections.defaultdict(lambda: [0, 0.0])
@@ -59,6 +59,16 @@ def main():
         print("\nper-op self device time (top %d)" % a.top)
         for t, c, k in sorted(rows, reverse=True)[:a.top]:
             print("%9.1f us %5d %5.1f%%  %s" % (t, c, 100 * t / total, k[:100]))
+        rows = []
+        for e in prof.key_averages(group_by_input_shape=True):
+            t = getattr(e, "self_device_time_total", None)
+            if t is None:
+                t = e.self_cuda_time_total
+            if t > 0 and e.key.startswith("aten::") and "conv" not in e.key:
+                rows.append((t, e.count, e.key, str(e.input_shapes)[:110]))
+        print("\nnon-conv ATen ops by input shape (top 60): the eager tail")
+        for t, c, k, sh in sorted(rows, reverse=True)[:60]:
+            print("%9.1f us %5d %5.1f%%  %-28s %s" % (t, c, 100 * t / total, k, sh))
 
 
 if __name__ == "__main__":
