@@ -204,6 +204,17 @@ int mvd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   float grad_scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Gradient gather into the flat arena (replaces autograd's per-parameter accumulate kernels, i.e. the reference's
+ * optimizer.zero_grad() + AccumulateGrad of movedepth/trainer.py:270-271, with ONE launch per parameter group).
+ *   table     : device int64 [nseg][14] = {src pointer (0 = no gradient: zeros are written), dst offset (elements),
+ *               numel, linear (1: src is dense in the destination's order), dims[5] (destination physical order,
+ *               outermost first, padded with 1), src strides[5] (elements, same order)}
+ *   block_map : device int32 [nblocks][2] = {segment, chunk of mvd_gather_chunk() elements}
+ * ------------------------------------------------------------------------------------- */
+int mvd_gather_chunk(void);
+int mvd_gather_segments(const long long* table, const int* block_map, int nblocks, float* dst, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * 3xTF32 operand split for the tensor-core convolutions of movedepth_b200/precision.py:
  * x = hi + lo (hi = x rounded to TF32).  x: [rows, C] (channels-last), out: [rows, 3C] =
  * [hi, lo, hi] (pattern 0, activations) or [hi, hi, lo] (pattern 1, weights).  n = rows * C.
@@ -268,8 +279,10 @@ int mvd_conv3d_c16c16_wgrad(const float* gy, const float* x, float* gw, void* wo
  * the caller all-reduces `sums` / `sums2` (2C doubles) between the two kernels of a pass.
  *   mvd_bn_stats      sums = [sum x (C), sum x^2 (C)]                      (zeroed inside)
  *   mvd_bn_finalize   stats = [mean, invstd, scale = w*invstd, shift = b - mean*scale] (4C floats),
- *                     running_mean/var updated in place (unbiased variance), count = rows over all ranks
- *   mvd_bn_apply      y = relu?(x*scale + shift (+ residual))
+ *                     running_mean/var updated in place (unbiased variance), count = rows over all ranks;
+ *                     num_batches_tracked (device int64, nullable) is incremented by one
+ *   mvd_bn_apply      y = relu?(x*scale + shift (+ residual));  relu: bit 0 = ReLU, bit 1 = the residual is added AFTER
+ *                     the ReLU (U-Net skip, resnet_encoder.py:272-276) instead of before it (ResNet block)
  *   mvd_bn_bwd_reduce sums2 = [sum g (C), sum g*xhat (C)],  g = gy * (y > 0) when relu; y may be NULL when the forward had
  *                     no residual: the mask is then recomputed from x*scale + shift (bit-identical), saving one read
  *   mvd_bn_bwd_apply  gx = w*invstd*(g - sum g/count - xhat * sum g*xhat/count); gres = g (nullable);
@@ -278,7 +291,7 @@ int mvd_conv3d_c16c16_wgrad(const float* gy, const float* x, float* gw, void* wo
 int mvd_bn_stats(const float* x, long long M, int C, double* sums, void* stream);
 int mvd_bn_finalize(const double* sums, double count, const float* weight, const float* bias,
                     float* running_mean, float* running_var, float momentum, float eps, float* stats,
-                    int C, void* stream);
+                    int C, long long* num_batches_tracked, void* stream);
 int mvd_bn_apply(const float* x, const float* residual, const float* stats, float* y, long long M,
                  int C, int relu, void* stream);
 int mvd_bn_bwd_reduce(const float* gy, const float* x, const float* y, const float* stats,

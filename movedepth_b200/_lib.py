@@ -44,6 +44,8 @@ SIGNATURES = {
     "mvd_masked_smooth_l1_bwd": ([_P] * 7 + [_LL, _F, _P], _I),
     "mvd_decoder_prep_fwd": ([_P] * 5 + [_I] * 7 + [_P], _I),
     "mvd_decoder_prep_bwd": ([_P] * 6 + [_I] * 7 + [_P], _I),
+    "mvd_gather_chunk": ([], _I),
+    "mvd_gather_segments": ([_P, _P, _I, _P, _P], _I),
     "mvd_split_tf32": ([_P, _P, _LL, _I, _I, _P], _I),
     "mvd_conv3d_c16o1_fwd": ([_P] * 3 + [_I] * 4 + [_P], _I),
     "mvd_conv3d_c16o1_dgrad": ([_P] * 3 + [_I] * 4 + [_P], _I),
@@ -56,7 +58,7 @@ SIGNATURES = {
     "mvd_conv3d_c16c16_wgrad_workspace_bytes": ([_I] * 4, _LL),
     "mvd_conv3d_c16c16_wgrad": ([_P] * 4 + [_LL] + [_I] * 4 + [_P], _I),
     "mvd_bn_stats": ([_P, _LL, _I, _P, _P], _I),
-    "mvd_bn_finalize": ([_P, _D, _P, _P, _P, _P, _F, _F, _P, _I, _P], _I),
+    "mvd_bn_finalize": ([_P, _D, _P, _P, _P, _P, _F, _F, _P, _I, _P, _P], _I),
     "mvd_bn_apply": ([_P, _P, _P, _P, _LL, _I, _I, _P], _I),
     "mvd_bn_bwd_reduce": ([_P, _P, _P, _P, _P, _LL, _I, _I, _P], _I),
     "mvd_bn_bwd_apply": ([_P] * 6 + [_D] + [_P] * 4 + [_LL, _I, _I, _P], _I),

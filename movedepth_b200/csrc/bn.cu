@@ -5,7 +5,7 @@
 //   forward : stats   (1 read)          per-channel sum / sum of squares, fp32 per thread, fp64 across the grid
 //             [multi-GPU: the 2C fp64 sums are all-reduced between the two kernels == SyncBatchNorm]
 //             finalize                  mean, invstd, running statistics, scale/shift
-//             apply   (1 read, 1 write) y = relu(x*scale + shift (+ residual))
+//             apply   (1 read, 1 write) y = relu(x*scale + shift (+ residual))   or   relu(x*scale + shift) + residual (relu flag bit 1)
 //   backward: reduce  (2-3 reads)       sum(g), sum(g*xhat)  with g = gy * (y > 0)
 //             apply   (2-3 reads, 1-2 writes)  gx = scale*(g - mean(g) - xhat*mean(g*xhat)), gres = g; gw, gb
 // cuDNN's NHWC BatchNorm kernels move the 283 MB full-resolution reg3d activations at ~1.4 TB/s and need separate
@@ -72,8 +72,10 @@ __global__ void __launch_bounds__(THREADS) bn_stats_kernel(const float* __restri
 // one thread per channel.  stats: [mean C][invstd C][scale C][shift C]
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ weight,
                                    const float* __restrict__ bias, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, float momentum, float eps, float* __restrict__ stats, int C) {
+                                   float* __restrict__ running_var, float momentum, float eps, float* __restrict__ stats, int C,
+                                   long long* __restrict__ num_batches_tracked) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && num_batches_tracked != nullptr) num_batches_tracked[0] += 1;      // the module's step counter rides along
     if (c >= C) return;
     const double mean = sums[c] / count;
     double var = sums[C + c] / count - mean * mean;
@@ -106,12 +108,16 @@ __global__ void __launch_bounds__(THREADS) bn_apply_kernel(const float* __restri
         const long long i = r * m.q + m.quad;
         const float4 v = __ldg(xp + i);
         float4 o = make_float4(fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w));
-        if (rp) {
+        if (rp && !(relu & 2)) {                         // ResNet block: add, then ReLU
             const float4 rv = __ldg(rp + i);
             o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
         }
-        if (relu) {
+        if (relu & 1) {
             o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+        }
+        if (rp && (relu & 2)) {                          // U-Net skip: ReLU, then add (resnet_encoder.py:272-276)
+            const float4 rv = __ldg(rp + i);
+            o.x += rv.x; o.y += rv.y; o.z += rv.z; o.w += rv.w;
         }
         yp[i] = o;
     }
@@ -233,11 +239,11 @@ int mvd_bn_stats(const float* x, long long M, int C, double* sums, void* stream)
 }
 
 int mvd_bn_finalize(const double* sums, double count, const float* weight, const float* bias, float* running_mean,
-                    float* running_var, float momentum, float eps, float* stats, int C, void* stream) {
+                    float* running_var, float momentum, float eps, float* stats, int C, long long* num_batches_tracked, void* stream) {
     using namespace mvd::bn;
     MVD_REQUIRE(sums && stats && count > 0, "bad argument");
     bn_finalize_kernel<<<(C + 127) / 128, 128, 0, mvd::as_stream(stream)>>>(sums, count, weight, bias, running_mean, running_var,
-                                                                            momentum, eps, stats, C);
+                                                                            momentum, eps, stats, C, num_batches_tracked);
     return mvd::check_launch("bn_finalize");
 }
 

@@ -153,8 +153,9 @@ class ConvBnReLUSeq(nn.Sequential):
     """nn.Sequential(conv, BatchNorm, ReLU) -- the reference's container and state-dict keys (`{0,1}.*`) -- whose forward
     runs the fused BN+ReLU kernels."""
 
-    def forward(self, x):
-        return NM.bn_act(self[1], self[0](x), relu=True)
+    def forward(self, x, skip=None):
+        """relu(bn(conv(x))) [+ skip]: the U-Net skip addition (resnet_encoder.py:272-276) rides in the BN-apply kernel."""
+        return NM.bn_act(self[1], self[0](x), relu=True, residual=skip, post=True)
 
 
 def _up3d(cin, cout, k=3, p=1, op=1, s=2):
@@ -182,9 +183,9 @@ class _UNet3D(nn.Module):
         c2 = self.conv2(self.conv1(c0))
         c4 = self.conv4(self.conv3(c2))
         y = self.conv6(self.conv5(c4))
-        y = c4 + self.conv7(y)
-        y = c2 + self.conv9(y)
-        y = c0 + self.conv11(y)
+        y = self.conv7(y, c4)
+        y = self.conv9(y, c2)
+        y = self.conv11(y, c0)
         return self.prob(y).squeeze(1)
 
     def forward_volume(self, vol_bgdhw):

@@ -85,7 +85,7 @@ def _count_launch(n):
 
 class _BNAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, running_mean, running_var, momentum, eps, relu, sync):
+    def forward(ctx, x, weight, bias, residual, running_mean, running_var, momentum, eps, relu, sync, post=False, nbt=None):
         L = _lib.lib()
         C = x.shape[1]
         xc = x.contiguous(memory_format=_fmt(x))
@@ -99,18 +99,20 @@ class _BNAct(torch.autograd.Function):
             count *= dist.get_world_size()
         stats = torch.empty(4 * C, device=x.device, dtype=torch.float32)
         _lib.check(L.mvd_bn_finalize(_p(sums), count, _p(weight), _p(bias), _p(running_mean), _p(running_var), float(momentum),
-                                     float(eps), _p(stats), C, _stream()), "mvd_bn_finalize")
+                                     float(eps), _p(stats), C, _p(nbt), _stream()), "mvd_bn_finalize")
         y = torch.empty_like(xc)
-        _lib.check(L.mvd_bn_apply(_p(xc), _p(rc_), _p(stats), _p(y), M, C, int(relu), _stream()), "mvd_bn_apply")
+        post = bool(post and residual is not None)         # post: relu(bn(x)) + residual (U-Net skip); else relu(bn(x) + residual)
+        _lib.check(L.mvd_bn_apply(_p(xc), _p(rc_), _p(stats), _p(y), M, C, int(relu) | (2 if post else 0), _stream()), "mvd_bn_apply")
         _count_launch(4)
-        ctx.save_for_backward(xc, y if (relu and residual is not None) else None, stats, weight)   # no residual: mask from x
-        ctx.cfg = (M, C, count, bool(relu), bool(sync), residual is not None)
+        # the ReLU mask is the sign of bn(x), recomputed from x in the backward, unless a residual was added BEFORE the ReLU
+        ctx.save_for_backward(xc, y if (relu and residual is not None and not post) else None, stats, weight)
+        ctx.cfg = (M, C, count, bool(relu), bool(sync), residual is not None, post)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         xc, y, stats, weight = ctx.saved_tensors
-        M, C, count, relu, sync, has_res = ctx.cfg
+        M, C, count, relu, sync, has_res, post = ctx.cfg
         L = _lib.lib()
         gy = gy.contiguous(memory_format=_fmt(xc))
         sums2 = torch.empty(2 * C, device=xc.device, dtype=torch.float64)
@@ -123,16 +125,18 @@ class _BNAct(torch.autograd.Function):
             gw = torch.empty(C, device=xc.device, dtype=torch.float32)
             gb = torch.empty(C, device=xc.device, dtype=torch.float32)
         gx = torch.empty_like(xc)
-        gres = torch.empty_like(xc) if (has_res and ctx.needs_input_grad[3]) else None
+        gres = torch.empty_like(xc) if (has_res and not post and ctx.needs_input_grad[3]) else None
         _lib.check(L.mvd_bn_bwd_apply(_p(gy), _p(xc), _p(y), _p(stats), _p(weight), _p(sums2), count, _p(gx), _p(gres),
                                       _p(None if sync else gw), _p(None if sync else gb), M, C, int(relu), _stream()),
                    "mvd_bn_bwd_apply")
         _count_launch(3)
+        if post and ctx.needs_input_grad[3]:
+            gres = gy                                 # the skip was added after the ReLU: its gradient is gy itself
         if weight is None or not ctx.needs_input_grad[1]:
             gw = None
         if not ctx.needs_input_grad[2]:
             gb = None
-        return gx, gw, gb, gres, None, None, None, None, None, None
+        return gx, gw, gb, gres, None, None, None, None, None, None, None, None
 
 
 def _fusable(bn, x):
@@ -141,16 +145,21 @@ def _fusable(bn, x):
             and bn.momentum is not None and 4 <= C <= 1024 and (C & (C - 1)) == 0 and x.numel() > 0)
 
 
-def bn_act(bn, x, relu=False, residual=None):
-    """relu(bn(x) + residual) with `bn` a BatchNorm2d / BatchNorm3d / SyncBatchNorm module."""
+def bn_act(bn, x, relu=False, residual=None, post=False):
+    """relu(bn(x) + residual), or relu(bn(x)) + residual with post=True, with `bn` a BatchNorm2d / BatchNorm3d /
+    SyncBatchNorm module."""
     if not _fusable(bn, x):
         y = bn(x)
+        if post:
+            y = F.relu(y) if relu else y
+            return y + residual if residual is not None else y
         if residual is not None:
             y = y + residual
         return F.relu(y, inplace=True) if relu else y
     sync = isinstance(bn, nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-    bn.num_batches_tracked += 1
-    return _BNAct.apply(x, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu, sync)
+    # num_batches_tracked is bumped inside the finalize kernel (95 one-element add kernels per step otherwise)
+    return _BNAct.apply(x, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu, sync, post,
+                        bn.num_batches_tracked)
 
 
 # ---- torchvision ResNet blocks: same modules / parameters, forward routed through bn_act -----------------------------

@@ -90,6 +90,18 @@ class SyntheticKITTI:
             yield self.make(g)
 
 
+def _arena_view(flat, p):
+    """A view of `flat` with p's logical shape.  Convolution weights (4-D / 5-D) are stored channels-last (dim 1
+    innermost: [Co, k.., Ci]) -- the layout cuDNN's NHWC kernels and their weight gradients use -- so no per-step layout
+    conversion of weights or weight gradients is left; every other parameter is stored contiguously."""
+    if p.dim() in (4, 5):
+        shape = list(p.shape)
+        phys = [shape[0]] + shape[2:] + [shape[1]]
+        perm = [0, p.dim() - 1] + list(range(1, p.dim() - 1))
+        return flat.view(phys).permute(perm)
+    return flat.view_as(p)
+
+
 class FlatArena:
     """All trainable parameters of a group re-homed into one flat fp32 buffer (+ gradient and Adam
     moment buffers of the same shape), so the optimizer and the gradient all-reduce are single
@@ -107,15 +119,70 @@ class FlatArena:
         self.exp_avg = torch.zeros(n, device=device)
         self.exp_avg_sq = torch.zeros(n, device=device)
         for p, o in zip(self.params, offs):
-            view = self.data[o:o + p.numel()].view_as(p)
+            view = _arena_view(self.data[o:o + p.numel()], p)
             view.copy_(p.data)
             p.data = view
-            p.grad = self.grad[o:o + p.numel()].view_as(p)
+            p.grad = _arena_view(self.grad[o:o + p.numel()], p)
         self.offsets = offs
+        self._static, self._pinned_tab = None, None
 
     def rebind_grads(self):
         for p, o in zip(self.params, self.offsets):
-            p.grad = self.grad[o:o + p.numel()].view_as(p)
+            p.grad = _arena_view(self.grad[o:o + p.numel()], p)
+
+    def moment_view(self, buf, i):
+        """View of a moment / gradient buffer with parameter i's logical shape."""
+        p, o = self.params[i], self.offsets[i]
+        return _arena_view(buf[o:o + p.numel()], p)
+
+    # ---- one-launch gradient collection (mvd_gather_segments)
+    def _gather_static(self):
+        if self._static is None:
+            chunk = ops._lib.lib().mvd_gather_chunk()
+            rows, blocks = [], []
+            for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+                phys = list(p.grad.permute(*([0] + list(range(2, p.dim())) + [1])).shape) if p.dim() in (4, 5) else list(p.shape)
+                phys = [1] * (5 - len(phys)) + phys if len(phys) <= 5 else None
+                assert phys is not None, "parameters with more than 5 dimensions are not supported"
+                rows.append((o, p.numel(), phys))
+                blocks += [(i, c) for c in range((p.numel() + chunk - 1) // chunk)]
+            bm = torch.tensor(blocks, dtype=torch.int32, device=self.data.device)
+            self._static = (rows, bm, len(blocks))
+        return self._static
+
+    def gather_table(self, grads):
+        """Host int64 [nseg,14] segment table for `grads` (one tensor or None per parameter)."""
+        rows, _, _ = self._gather_static()
+        tab = torch.zeros(len(rows), 14, dtype=torch.int64)
+        for i, (g, p, (o, n, phys)) in enumerate(zip(grads, self.params, rows)):
+            tab[i, 1], tab[i, 2] = o, n
+            tab[i, 4:9] = torch.tensor(phys)
+            if g is None:
+                continue
+            assert g.shape == p.shape and g.dtype == torch.float32, (g.shape, p.shape, g.dtype)
+            gs = g.permute(*([0] + list(range(2, g.dim())) + [1])) if g.dim() in (4, 5) else g     # destination physical order
+            st = [0] * (5 - gs.dim()) + list(gs.stride())
+            tab[i, 0] = g.data_ptr()
+            tab[i, 3] = 1 if gs.is_contiguous() else 0
+            tab[i, 9:14] = torch.tensor(st)
+        return tab
+
+    def collect(self, grads, pinned=False):
+        """Write the gradient tensors returned by torch.autograd.grad into the flat gradient buffer with one kernel
+        (no zero_grad, no per-parameter accumulate).  `grads` must stay alive until the kernel has run; returns the
+        objects the caller has to keep alive (CUDA-graph capture: the pinned table is re-read at every replay)."""
+        _, bm, nblocks = self._gather_static()
+        tab = self.gather_table(grads)
+        if self._pinned_tab is None and self.data.is_cuda:
+            self._pinned_tab = torch.zeros_like(tab).pin_memory()        # allocated outside any capture (warm-up steps)
+        if pinned:                  # capture: the copy node re-reads this persistent pinned table at every replay
+            self._pinned_tab.copy_(tab)
+            tab = self._pinned_tab
+        dev_tab = tab.to(self.data.device, non_blocking=pinned)
+        rc = ops._lib.lib().mvd_gather_segments(ops._p(dev_tab), ops._p(bm), nblocks, ops._p(self.grad), ops._stream())
+        ops._lib.check(rc, "mvd_gather_segments")
+        ops.launch_counter["n"] += 1
+        return tab, dev_tab, list(grads)
 
 
 class Trainer:
@@ -279,20 +346,27 @@ class Trainer:
         return outputs, losses
 
     def _forward_backward(self, inputs, noise=None, mask_xy=None):
-        for a in self.arenas:
-            a.grad.zero_()
         outputs, losses = self.process_batch(inputs, is_train=True, noise=noise, mask_xy=mask_xy)
         multi = self.opt.ddp and self.world_size > 1
-        # the two graphs share nothing but detached tensors: back-propagate them separately so the
-        # cost-volume branch's gradients can be reduced while the mono/pose branch is still running
+        capturing = torch.cuda.is_current_stream_capturing()
+        # The two graphs share nothing but detached tensors: back-propagate them separately so the cost-volume branch's
+        # gradients can be reduced while the mono/pose branch is still running.  torch.autograd.grad hands back the raw
+        # gradient tensors (no zero_grad, no per-parameter accumulate kernels); one gather kernel per parameter group
+        # writes them into the flat arena the all-reduce and the fused Adam kernel work on.
         self._tf32("mvs")
-        losses["_mvs_total"].backward()
+        p0, p1 = self.arenas[0].params, self.arenas[1].params
+        g = torch.autograd.grad(losses["_mvs_total"], p1 + p0, allow_unused=True)    # group-0 members of this graph: `up`
+        g1, g0_mvs = g[:len(p1)], g[len(p1):]
+        keep = [self.arenas[1].collect(g1, pinned=capturing)]
         work = dist.all_reduce(self.arenas[1].grad, async_op=True) if multi else None
         self._tf32("mono")
-        losses["_mono_total"].backward()
+        g0 = torch.autograd.grad(losses["_mono_total"], p0, allow_unused=True)
+        g0 = [b if a is None else (a if b is None else a + b) for a, b in zip(g0, g0_mvs)]
+        keep.append(self.arenas[0].collect(g0, pinned=capturing))
         if multi:
             dist.all_reduce(self.arenas[0].grad)
             work.wait()
+        outputs["_keepalive"] = keep
         return outputs, losses
 
     def _optimizer_step(self):
@@ -704,10 +778,9 @@ class Trainer:
         step = torch.tensor(float(self.opt_step))
         for a, lr, base in zip(self.arenas, self.current_lrs(), self.base_lrs):
             ids = []
-            for p, o in zip(a.params, a.offsets):
-                n = p.numel()
-                state[idx] = {"step": step.clone(), "exp_avg": a.exp_avg[o:o + n].view_as(p).clone(),
-                              "exp_avg_sq": a.exp_avg_sq[o:o + n].view_as(p).clone()}
+            for i in range(len(a.params)):
+                state[idx] = {"step": step.clone(), "exp_avg": a.moment_view(a.exp_avg, i).clone(),
+                              "exp_avg_sq": a.moment_view(a.exp_avg_sq, i).clone()}
                 ids.append(idx)
                 idx += 1
             groups.append({"lr": lr, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": 0, "amsgrad": False, "maximize": False,
@@ -717,19 +790,20 @@ class Trainer:
 
     def load_adam_state_dict(self, st):
         """Restore the moments and the step count from an Adam state_dict (ours or the reference's)."""
-        flat = [(a, p, o) for a in self.arenas for p, o in zip(a.params, a.offsets)]
+        flat = [(a, j) for a in self.arenas for j in range(len(a.params))]
         n_given = sum(len(g["params"]) for g in st["param_groups"])
         if n_given != len(flat):
             raise ValueError("adam.pth holds %d parameter states, this model has %d" % (n_given, len(flat)))
         step = 0
-        for i, (a, p, o) in enumerate(flat):
+        for i, (a, j) in enumerate(flat):
             e = st["state"].get(i)
             if e is None:
                 continue
+            p = a.params[j]
             if tuple(e["exp_avg"].shape) != tuple(p.shape):
                 raise ValueError("adam.pth state %d has shape %s, parameter has %s" % (i, tuple(e["exp_avg"].shape), tuple(p.shape)))
-            a.exp_avg[o:o + p.numel()].view_as(p).copy_(e["exp_avg"])
-            a.exp_avg_sq[o:o + p.numel()].view_as(p).copy_(e["exp_avg_sq"])
+            a.moment_view(a.exp_avg, j).copy_(e["exp_avg"])
+            a.moment_view(a.exp_avg_sq, j).copy_(e["exp_avg_sq"])
             step = max(step, int(float(e["step"])))
         self.opt_step = step
 

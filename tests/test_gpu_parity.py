@@ -313,7 +313,8 @@ def test_conv3d_16_to_16_matches_torch_conv3d(ops, shape):
 
 # ---------------------------------------------------------------------------------------------- BatchNorm kernels
 @pytest.mark.parametrize("shape,relu,res", [((3, 16, 5, 6, 7), True, False), ((4, 64, 9, 11), True, True), ((2, 8, 6, 10), False, False),
-                                            ((2, 512, 3, 5), True, True)], ids=["3d-relu", "2d-relu-res", "2d-plain", "c512"])
+                                            ((2, 512, 3, 5), True, True), ((2, 32, 4, 6, 8), True, "post")],
+                         ids=["3d-relu", "2d-relu-res", "2d-plain", "c512", "3d-relu-then-skip"])
 def test_fused_batchnorm_matches_torch(shape, relu, res):
     """csrc/bn.cu (stats / finalize / apply, backward reduce / apply) vs torch's batch_norm + add + relu in fp64:
     outputs, input / residual / weight / bias gradients and the running statistics."""
@@ -336,14 +337,17 @@ def test_fused_batchnorm_matches_torch(shape, relu, res):
     xo = x.double().requires_grad_(True)
     ro = r.double().requires_grad_(True) if res else None
     yo = ref(xo)
-    if res:
-        yo = yo + ro
-    if relu:
-        yo = torch.relu(yo)
+    if res == "post":                                # U-Net skip: ReLU first, then the addition (reg3d conv7/9/11)
+        yo = torch.relu(yo) + ro
+    else:
+        if res:
+            yo = yo + ro
+        if relu:
+            yo = torch.relu(yo)
     (yo * gy.double()).sum().backward()
     xg = g(x).contiguous(memory_format=fmt).requires_grad_(True)
     rg = g(r).contiguous(memory_format=fmt).requires_grad_(True) if res else None
-    y = NM.bn_act(mine, xg, relu=relu, residual=rg)
+    y = NM.bn_act(mine, xg, relu=relu, residual=rg, post=(res == "post"))
     (y * g(gy)).sum().backward()
 
     def close(a, b, tol=2e-5):
