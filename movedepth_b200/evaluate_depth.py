@@ -117,27 +117,80 @@ def compute_fuse_errors(gt, pred1, pred2):
     return compute_errors(gt, np.where(pick, pred1, pred2))
 
 
-def evaluate(opt, dataloader, gt_depths=None, min_depth=1e-3, max_depth=80.0):
-    """Run the predictor over `dataloader` (item dicts of mono_dataset.py:134-154).  With `gt_depths` (list of [h,w] arrays,
-    0 = no measurement) returns the mean KITTI metrics of the multi-frame and the mono prediction with per-image median
-    scaling (evaluate_depth.py:259-331; prediction resized to the ground truth with bilinear interpolation, no Eigen crop
-    unless the caller crops `gt_depths`); otherwise returns the stacked disparities."""
+def kitti_metrics(pred_disps_z, pred_disps_mono, gt_depths, eval_split="eigen", median_scaling=True, min_depth=1e-3, max_depth=80.0):
+    """The metric stage of the reference's `evaluate` (movedepth/evaluate_depth.py:259-331): both disparity maps are resized
+    to the ground-truth size (cv2.resize, bilinear), inverted, masked (`eigen`: 1e-3 < gt < 80 inside the Eigen crop;
+    other splits: gt > 0), median-scaled per image unless `--disable_median_scaling`, clamped to [1e-3, 80] and scored
+    with the seven KITTI metrics; `upbound` is the per-pixel oracle fusion.  Returns {"mono", "mvs", "upbound"} mean rows."""
+    import cv2
+    rows = {"mono": [], "mvs": [], "upbound": []}
+    for i in range(len(pred_disps_mono)):
+        gt = np.asarray(gt_depths[i])
+        h, w = gt.shape[:2]
+        disp_m = cv2.resize(np.squeeze(np.asarray(pred_disps_mono[i], dtype=np.float32)), (w, h))
+        disp_z = cv2.resize(np.squeeze(np.asarray(pred_disps_z[i], dtype=np.float32)), (w, h))
+        depth_z, depth_m = 1 / disp_z, 1 / disp_m
+        if eval_split == "eigen":
+            box = np.array([0.40810811 * h, 0.99189189 * h, 0.03594771 * w, 0.96405229 * w]).astype(np.int32)
+            keep = np.zeros(gt.shape, dtype=bool)
+            keep[box[0]:box[1], box[2]:box[3]] = True
+            keep &= (gt > min_depth) & (gt < max_depth)
+        else:
+            keep = gt > 0
+        depth_z, depth_m, g = depth_z[keep], depth_m[keep], gt[keep]
+        if median_scaling:
+            depth_m = depth_m * (np.median(g) / np.median(depth_m))
+            depth_z = depth_z * (np.median(g) / np.median(depth_z))
+        depth_z, depth_m = np.clip(depth_z, min_depth, max_depth), np.clip(depth_m, min_depth, max_depth)
+        rows["mvs"].append(compute_errors(g, depth_z))
+        rows["mono"].append(compute_errors(g, depth_m))
+        rows["upbound"].append(compute_fuse_errors(g, depth_m, depth_z))
+    return {k: np.array(v).mean(0) for k, v in rows.items()}
+
+
+class GraphedPredictor:
+    """`DepthPredictor.predict` captured in a CUDA graph for fixed-shape inference (batch-1 latency): inputs are copied into
+    static device buffers, the whole forward (~330 launches) replays as one graph launch.  Note the reference takes the
+    z-translation of batch item 0 for the whole batch (evaluate_depth.py:218); at batch 1 that is the item itself."""
+
+    def __init__(self, predictor, example, warmup=2):
+        self.pred = predictor
+        dev = predictor.device
+        self.static = {k: v.to(dev).clone() for k, v in example.items() if torch.is_tensor(v)}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                      # cuDNN autotuning and lazy initialisation outside the capture
+                predictor.predict(self.static)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=side):
+            self.out = predictor.predict(self.static)
+
+    def predict(self, data):
+        for k, buf in self.static.items():
+            buf.copy_(data[k], non_blocking=True)
+        self.graph.replay()
+        return self.out
+
+
+def evaluate(opt, dataloader, gt_depths=None):
+    """movedepth/evaluate_depth.py:77-331 for any loader that yields the reference's item dicts (the KITTI datasets
+    themselves are out of scope): predictions with `DepthPredictor`, then `kitti_metrics` when ground truth is given
+    (`opt.eval_split`, `opt.disable_median_scaling` honoured); otherwise the stacked disparities are returned."""
     pred = DepthPredictor(opt)
     dz, dm = [], []
     for data in dataloader:
         r = pred.predict(data)
-        dz.append(r["pred_disp_z"].float().cpu())
-        dm.append(r["pred_disp_mono"].float().cpu())
-    dz, dm = torch.cat(dz), torch.cat(dm)
+        dz.append(r["pred_disp_z"].float().cpu().numpy())
+        dm.append(r["pred_disp_mono"].float().cpu().numpy())
+    dz, dm = np.concatenate(dz), np.concatenate(dm)
     if gt_depths is None:
-        return dz.numpy(), dm.numpy()
-    res = {"mvs": [], "mono": []}
-    for i, gt in enumerate(gt_depths):
-        mask = (gt > min_depth) & (gt < max_depth)
-        for key, d in (("mvs", dz[i]), ("mono", dm[i])):
-            disp = torch.nn.functional.interpolate(d[None, None], size=gt.shape, mode="bilinear", align_corners=False)[0, 0].numpy()
-            p = 1.0 / disp
-            p, g = p[mask], gt[mask]
-            p = np.clip(p * np.median(g) / np.median(p), min_depth, max_depth)
-            res[key].append(compute_errors(g, p))
-    return {k: np.array(v).mean(0) for k, v in res.items()}
+        return dz, dm
+    res = kitti_metrics(dz, dm, gt_depths, getattr(opt, "eval_split", "eigen"), not getattr(opt, "disable_median_scaling", False))
+    for name in ("mono", "mvs", "upbound"):
+        print("%s results:" % name)
+        print(("{:>8} | " * 7).format("abs_rel", "sq_rel", "rmse", "rmse_log", "a1", "a2", "a3"))
+        print(("&{: 8.3f}  " * 7).format(*res[name].tolist()) + "\\\\")
+    return res

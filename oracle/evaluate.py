@@ -51,3 +51,42 @@ def compute_errors(gt, pred):
     rmse = np.sqrt(((gt - pred) ** 2).mean())
     rmse_log = np.sqrt(((np.log(gt) - np.log(pred)) ** 2).mean())
     return np.mean(np.abs(gt - pred) / gt), np.mean((gt - pred) ** 2 / gt), rmse, rmse_log, a1, a2, a3
+
+
+def compute_fuse_errors(gt, pred1, pred2):
+    """movedepth/evaluate_depth.py:42-64 -- per pixel the prediction closer to the ground truth ("upbound" row)."""
+    pick = np.abs(gt - pred1) < np.abs(pred2 - gt)
+    return compute_errors(gt, np.where(pick, pred1, pred2))
+
+
+def kitti_metrics(pred_disps_z, pred_disps_mono, gt_depths, eval_split="eigen", median_scaling=True, min_depth=1e-3, max_depth=80.0):
+    """movedepth/evaluate_depth.py:259-331 -- per image: cv2.resize of both disparities to the ground-truth size, 1/disp,
+    Eigen crop (0.408..0.992 of the height, 0.036..0.964 of the width; int32 truncation) AND 1e-3 < gt < 80 mask for the
+    `eigen` split (gt > 0 otherwise), per-image median scaling unless disabled, clamp to [1e-3, 80], the seven metrics for
+    the multi-frame, the mono and the oracle-fused prediction; returns the three mean rows (mono, mvs, upbound)."""
+    import cv2
+    rows = {"mono": [], "mvs": [], "upbound": []}
+    for i in range(pred_disps_mono.shape[0]):
+        gt = gt_depths[i]
+        gh, gw = gt.shape[:2]
+        dm = cv2.resize(np.squeeze(pred_disps_mono[i]), (gw, gh))
+        dz = cv2.resize(np.squeeze(pred_disps_z[i]), (gw, gh))
+        pz, pm = 1 / dz, 1 / dm
+        if eval_split == "eigen":
+            mask = np.logical_and(gt > min_depth, gt < max_depth)
+            crop = np.array([0.40810811 * gh, 0.99189189 * gh, 0.03594771 * gw, 0.96405229 * gw]).astype(np.int32)
+            cm = np.zeros(mask.shape)
+            cm[crop[0]:crop[1], crop[2]:crop[3]] = 1
+            mask = np.logical_and(mask, cm)
+        else:
+            mask = gt > 0
+        pz, pm, g = pz[mask], pm[mask], gt[mask]
+        if median_scaling:
+            pm = pm * (np.median(g) / np.median(pm))
+            pz = pz * (np.median(g) / np.median(pz))
+        pz = np.clip(pz, min_depth, max_depth)
+        pm = np.clip(pm, min_depth, max_depth)
+        rows["mvs"].append(compute_errors(g, pz))
+        rows["mono"].append(compute_errors(g, pm))
+        rows["upbound"].append(compute_fuse_errors(g, pm, pz))
+    return {k: np.array(v).mean(0) for k, v in rows.items()}

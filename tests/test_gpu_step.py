@@ -299,3 +299,28 @@ def test_depth_predictor_matches_reference_golden():
     assert ED.compute_fuse_errors(gt, 1.0 / dz[0], gt)[0] == 0.0          # oracle fusion picks the exact prediction
 
 
+
+
+def test_graphed_predictor_replays_the_eager_prediction():
+    """GraphedPredictor (the batch-1 inference step captured as one CUDA graph) returns what DepthPredictor.predict returns,
+    on new inputs copied into its static buffers."""
+    from movedepth_b200 import evaluate_depth as ED
+    from movedepth_b200.options import MonodepthOptions
+    cfg = dict(C.EVAL_CASE, B=1)
+    argv = ["--height", str(cfg["H"]), "--width", str(cfg["W"]), "--num_depth_bins", str(cfg["D"]), "--batch_size", "1",
+            "--weights_init", "scratch", "--convex_up", "--frame_ids", "0", "-1"]
+    opt = MonodepthOptions().parse(argv)
+    models = ED.build_models(opt)
+    for k, m in models.items():
+        fill_deterministic(m, salt=k + "/")
+    pred = ED.DepthPredictor(opt, models=models)
+    data, _, _ = C.step_inputs(cfg)
+    other, _, _ = C.step_inputs(dict(cfg, W=cfg["W"]))                 # same shapes
+    other = {k: (v.flip(-1).contiguous() if k[0].startswith("color") else v) for k, v in other.items()}
+    gp = ED.GraphedPredictor(pred, data)
+    for d in (data, other, data):
+        want = {k: v.clone() for k, v in pred.predict(d).items()}
+        got = gp.predict(d)
+        torch.cuda.synchronize()
+        for k in ("pred_disp_z", "pred_disp_mono"):
+            torch.testing.assert_close(got[k], want[k], atol=1e-6, rtol=1e-5)

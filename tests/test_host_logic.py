@@ -261,3 +261,36 @@ def test_custom_conv_modules_keep_reference_state_dict_and_cpu_path():
     x = torch.randn(1, 16, 8, 8, 16)
     want = nn.functional.conv3d(x, reg.prob.weight, padding=1)
     torch.testing.assert_close(reg.prob(x), want)
+
+
+def test_kitti_metric_stage_matches_the_oracle_and_the_eigen_crop():
+    """movedepth_b200.evaluate_depth.kitti_metrics vs the oracle's restatement of evaluate_depth.py:259-331 (resize to the
+    ground truth, Eigen crop, median scaling, clamp, metrics, oracle fusion), plus known answers: the Eigen crop of a
+    375x1242 map is rows 153..370, columns 44..1196, and a perfect prediction scores zero error."""
+    import numpy as np
+    from movedepth_b200 import evaluate_depth as ED
+    from oracle import evaluate as OE
+    rng = np.random.default_rng(0)
+    gt = [np.where(rng.random((375, 1242)) < 0.3, rng.uniform(0.5, 90, (375, 1242)), 0).astype(np.float32) for _ in range(2)]
+    dz = rng.uniform(0.02, 1.0, (2, 48, 160)).astype(np.float32)
+    dm = rng.uniform(0.02, 1.0, (2, 48, 160)).astype(np.float32)
+    for split in ("eigen", "benchmark"):
+        for scaling in (True, False):
+            a, b = ED.kitti_metrics(dz, dm, gt, split, scaling), OE.kitti_metrics(dz, dm, gt, split, scaling)
+            for k in ("mono", "mvs", "upbound"):
+                np.testing.assert_allclose(a[k], b[k], rtol=1e-12)
+            assert a["upbound"][0] <= min(a["mono"][0], a["mvs"][0]) + 1e-12        # the oracle fusion is never worse
+    # only pixels inside the crop count: ground truth outside it may be anything
+    g0 = np.full((375, 1242), 10.0, dtype=np.float32)
+    g1 = g0.copy()
+    g1[:153] = 55.0
+    g1[371:] = 55.0
+    g1[:, :44] = 55.0
+    g1[:, 1197:] = 55.0
+    d = np.full((1, 24, 80), 0.1, dtype=np.float32)
+    r0, r1 = ED.kitti_metrics(d, d, [g0]), ED.kitti_metrics(d, d, [g1])
+    np.testing.assert_allclose(r0["mvs"], r1["mvs"])
+    np.testing.assert_allclose(r0["mvs"][:4], 0, atol=1e-6)                           # depth 10 everywhere == gt: zero errors
+    g2 = g0.copy()
+    g2[153, 44] = 55.0                                                                # first pixel inside the crop
+    assert ED.kitti_metrics(d, d, [g2])["mvs"][0] > 0

@@ -51,7 +51,7 @@ def main():
     cases = [("wgrad tc", lambda: ops.c16c16_wgrad_tc(x, x)), ("wgrad ffma2", lambda: ops.c16c16_wgrad(x, x)),
              ("tc 3-pass", lambda: ops.c16c16_conv_tc(x, w, 0, 3)), ("tc 1-pass", lambda: ops.c16c16_conv_tc(x, w, 1, 1)),
              ("mma.sync 1-pass", lambda: ops.c16c16_conv(x, w, 1, 1))]
-    for dbg, nm in ():
+    for dbg, nm in ((2, 'no MMA'), (4, 'no stores'), (8, 'no split'), (14, 'no MMA/stores/split')) if '--breakdown' in sys.argv else ():
         cases.append(("tc 3-pass dbg %s" % nm, lambda dbg=dbg: ops.c16c16_conv_tc(x, w, 0, 3, dbg)))
         cases.append(("tc 1-pass dbg %s" % nm, lambda dbg=dbg: ops.c16c16_conv_tc(x, w, 1, 1, dbg)))
     for name, fn in cases:
