@@ -277,25 +277,32 @@ int mvd_conv3d_c16c16_wgrad(const float* gy, const float* x, float* gw, void* wo
  * nn.BatchNorm2d + F.relu in Conv2d (453-475), bn/relu/add of the torchvision ResNet blocks
  * (74-121) and, under data-parallel training, nn.SyncBatchNorm (movedepth/trainer.py:69-129):
  * the caller all-reduces `sums` / `sums2` (2C doubles) between the two kernels of a pass.
- *   mvd_bn_stats      sums = [sum x (C), sum x^2 (C)]                      (zeroed inside)
+ *   mvd_bn_stats      sums = [sum x (C), sum x^2 (C), arrival counter (1)] = 2C+1 doubles  (zeroed inside)
+ *                     peers != NULL (data-parallel training): the last block of the reduction all-reduces the 2C sums
+ *                     over NVLink peer memory in place (peers / rank / world / nmax as for mvd_peer_allreduce_f64), so
+ *                     no separate exchange launch sits between the reduction and its consumer
  *   mvd_bn_finalize   stats = [mean, invstd, scale = w*invstd, shift = b - mean*scale] (4C floats),
  *                     running_mean/var updated in place (unbiased variance), count = rows over all ranks;
  *                     num_batches_tracked (device int64, nullable) is incremented by one
  *   mvd_bn_apply      y = relu?(x*scale + shift (+ residual));  relu: bit 0 = ReLU, bit 1 = the residual is added AFTER
  *                     the ReLU (U-Net skip, resnet_encoder.py:272-276) instead of before it (ResNet block)
- *   mvd_bn_bwd_reduce sums2 = [sum g (C), sum g*xhat (C)],  g = gy * (y > 0) when relu; y may be NULL when the forward had
+ *   mvd_bn_bwd_reduce sums2 = [sum g (C), sum g*xhat (C), counter] (2C+1 doubles; all-reduced in place when peers != NULL,
+ *                     this rank's own sums are then copied to local_sums2 (2C doubles) first),
+ *                     g = gy * (y > 0) when relu; y may be NULL when the forward had
  *                     no residual: the mask is then recomputed from x*scale + shift (bit-identical), saving one read
  *   mvd_bn_bwd_apply  gx = w*invstd*(g - sum g/count - xhat * sum g*xhat/count); gres = g (nullable);
  *                     gw = sum g*xhat, gb = sum g (nullable; pass NULL when sums2 was all-reduced)
  * ------------------------------------------------------------------------------------- */
-int mvd_bn_stats(const float* x, long long M, int C, double* sums, void* stream);
+int mvd_bn_stats(const float* x, long long M, int C, double* sums, const unsigned long long* peers, int rank,
+                 int world, int nmax, void* stream);
 int mvd_bn_finalize(const double* sums, double count, const float* weight, const float* bias,
                     float* running_mean, float* running_var, float momentum, float eps, float* stats,
                     int C, long long* num_batches_tracked, void* stream);
 int mvd_bn_apply(const float* x, const float* residual, const float* stats, float* y, long long M,
                  int C, int relu, void* stream);
-int mvd_bn_bwd_reduce(const float* gy, const float* x, const float* y, const float* stats,
-                      double* sums2, long long M, int C, int relu, void* stream);
+int mvd_bn_bwd_reduce(const float* gy, const float* x, const float* y, const float* stats, double* sums2,
+                      double* local_sums2, long long M, int C, int relu, const unsigned long long* peers, int rank,
+                      int world, int nmax, void* stream);
 int mvd_bn_bwd_apply(const float* gy, const float* x, const float* y, const float* stats,
                      const float* weight, const double* sums2, double count, float* gx, float* gres,
                      float* gw, float* gb, long long M, int C, int relu, void* stream);

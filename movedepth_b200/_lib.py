@@ -57,10 +57,10 @@ SIGNATURES = {
     "mvd_conv3d_c16c16_wgrad_tc": ([_P] * 4 + [_LL] + [_I] * 4 + [_P], _I),
     "mvd_conv3d_c16c16_wgrad_workspace_bytes": ([_I] * 4, _LL),
     "mvd_conv3d_c16c16_wgrad": ([_P] * 4 + [_LL] + [_I] * 4 + [_P], _I),
-    "mvd_bn_stats": ([_P, _LL, _I, _P, _P], _I),
+    "mvd_bn_stats": ([_P, _LL, _I, _P, _P, _I, _I, _I, _P], _I),
     "mvd_bn_finalize": ([_P, _D, _P, _P, _P, _P, _F, _F, _P, _I, _P, _P], _I),
     "mvd_bn_apply": ([_P, _P, _P, _P, _LL, _I, _I, _P], _I),
-    "mvd_bn_bwd_reduce": ([_P, _P, _P, _P, _P, _LL, _I, _I, _P], _I),
+    "mvd_bn_bwd_reduce": ([_P, _P, _P, _P, _P, _P, _LL, _I, _I, _P, _I, _I, _I, _P], _I),
     "mvd_bn_bwd_apply": ([_P] * 6 + [_D] + [_P] * 4 + [_LL, _I, _I, _P], _I),
     "mvd_peer_allreduce_buffer_bytes": ([_I, _I], _LL),
     "mvd_peer_allreduce_f64": ([_P, _P, _I, _P, _I, _I, _I, _P], _I),

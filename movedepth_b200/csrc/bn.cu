@@ -10,7 +10,7 @@
 //             apply   (2-3 reads, 1-2 writes)  gx = scale*(g - mean(g) - xhat*mean(g*xhat)), gres = g; gw, gb
 // cuDNN's NHWC BatchNorm kernels move the 283 MB full-resolution reg3d activations at ~1.4 TB/s and need separate
 // ReLU / add passes; these are plain HBM-bound float4 streams.
-#include "common.cuh"
+#include "peer.cuh"
 #include "../../include/movedepth_b200.h"
 
 namespace mvd {
@@ -55,8 +55,29 @@ __device__ __forceinline__ void block_reduce_to_global(const float (&a)[4], cons
     }
 }
 
+// Data-parallel training (SyncBatchNorm): the LAST block to finish the reduction exchanges the 2C fp64 sums with the other
+// ranks over NVLink peer memory (csrc/peer.cuh) and leaves the global sums in place -- no separate exchange launch between
+// the reduction and the kernel that consumes it.  sums[2C] is the arrival counter (zeroed with the sums).
+__device__ __forceinline__ void exchange_if_last(double* sums, int C, const PeerArgs pa, double* local_copy = nullptr) {
+    if (pa.peers == nullptr) return;
+    __shared__ int s_last;
+    __threadfence();                                   // this thread's atomics are visible device-wide
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(reinterpret_cast<unsigned int*>(sums + 2 * C), 1u);
+        s_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (local_copy != nullptr)                         // this rank's own sums (the BatchNorm parameter gradients)
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) local_copy[i] = ld_volatile_f64(sums + i);
+    peer_allreduce_block(sums, sums, 2 * C, pa);
+}
+
 // ---- forward
-__global__ void __launch_bounds__(THREADS) bn_stats_kernel(const float* __restrict__ x, long long M, int C, double* __restrict__ sums) {
+__global__ void __launch_bounds__(THREADS) bn_stats_kernel(const float* __restrict__ x, long long M, int C, double* __restrict__ sums,
+                                                           const PeerArgs pa) {
     const Map m = make_map(C);
     float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
     const float4* xp = reinterpret_cast<const float4*>(x);
@@ -67,6 +88,7 @@ __global__ void __launch_bounds__(THREADS) bn_stats_kernel(const float* __restri
         ss[0] = fmaf(v.x, v.x, ss[0]); ss[1] = fmaf(v.y, v.y, ss[1]); ss[2] = fmaf(v.z, v.z, ss[2]); ss[3] = fmaf(v.w, v.w, ss[3]);
     }
     block_reduce_to_global(s, ss, m, sums, C);
+    exchange_if_last(sums, C, pa);
 }
 
 // one thread per channel.  stats: [mean C][invstd C][scale C][shift C]
@@ -138,7 +160,8 @@ __device__ __forceinline__ float4 affine(const float4& v, const float4& sc, cons
 // sums2: [sum g (C)][sum g*xhat (C)]
 __global__ void __launch_bounds__(THREADS) bn_bwd_reduce_kernel(const float* __restrict__ gy, const float* __restrict__ x,
                                                                 const float* __restrict__ y, const float* __restrict__ stats,
-                                                                double* __restrict__ sums2, long long M, int C, int relu) {
+                                                                double* __restrict__ sums2, double* __restrict__ local_sums2,
+                                                                long long M, int C, int relu, const PeerArgs pa) {
     const Map m = make_map(C);
     const float4 mean = *reinterpret_cast<const float4*>(stats + 4 * m.quad);
     const float4 istd = *reinterpret_cast<const float4*>(stats + C + 4 * m.quad);
@@ -161,6 +184,7 @@ __global__ void __launch_bounds__(THREADS) bn_bwd_reduce_kernel(const float* __r
         sx[3] = fmaf(g.w, (v.w - mean.w) * istd.w, sx[3]);
     }
     block_reduce_to_global(s, sx, m, sums2, C);
+    exchange_if_last(sums2, C, pa, local_sums2);
 }
 
 __global__ void __launch_bounds__(THREADS) bn_bwd_apply_kernel(const float* __restrict__ gy, const float* __restrict__ x,
@@ -227,14 +251,23 @@ static int check(long long M, int C) {
 
 extern "C" {
 
-int mvd_bn_stats(const float* x, long long M, int C, double* sums, void* stream) {
+static int check_peer(const unsigned long long* peers, int rank, int world, int nmax, int C) {
+    if (peers == nullptr) return 0;
+    MVD_REQUIRE(world >= 1 && world <= 64 && rank >= 0 && rank < world, "bad rank %d / world %d", rank, world);
+    MVD_REQUIRE(2 * C <= nmax, "2C = %d statistics exceed the exchange buffer's %d", 2 * C, nmax);
+    return 0;
+}
+
+int mvd_bn_stats(const float* x, long long M, int C, double* sums, const unsigned long long* peers, int rank, int world, int nmax,
+                 void* stream) {
     using namespace mvd::bn;
     MVD_REQUIRE(x && sums, "null pointer argument");
     if (int rc = check(M, C)) return rc;
+    if (int rc = check_peer(peers, rank, world, nmax, C)) return rc;
     cudaStream_t st = mvd::as_stream(stream);
-    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C + 1), st);
     if (e != cudaSuccess) return mvd::fail(static_cast<int>(e), "bn_stats memset: %s", cudaGetErrorString(e));
-    bn_stats_kernel<<<grid_for(M, C), THREADS, 0, st>>>(x, M, C, sums);
+    bn_stats_kernel<<<grid_for(M, C), THREADS, 0, st>>>(x, M, C, sums, mvd::PeerArgs{peers, rank, world, nmax});
     return mvd::check_launch("bn_stats");
 }
 
@@ -255,15 +288,18 @@ int mvd_bn_apply(const float* x, const float* residual, const float* stats, floa
     return mvd::check_launch("bn_apply");
 }
 
-int mvd_bn_bwd_reduce(const float* gy, const float* x, const float* y, const float* stats, double* sums2, long long M, int C,
-                      int relu, void* stream) {
+int mvd_bn_bwd_reduce(const float* gy, const float* x, const float* y, const float* stats, double* sums2, double* local_sums2,
+                      long long M, int C, int relu, const unsigned long long* peers, int rank, int world, int nmax, void* stream) {
     using namespace mvd::bn;
     MVD_REQUIRE(gy && x && stats && sums2, "null pointer argument");
+    MVD_REQUIRE(peers == nullptr || local_sums2 != nullptr, "data-parallel reduce needs local_sums2 (this rank's own sums)");
     if (int rc = check(M, C)) return rc;
+    if (int rc = check_peer(peers, rank, world, nmax, C)) return rc;
     cudaStream_t st = mvd::as_stream(stream);
-    cudaError_t e = cudaMemsetAsync(sums2, 0, sizeof(double) * 2 * C, st);
+    cudaError_t e = cudaMemsetAsync(sums2, 0, sizeof(double) * (2 * C + 1), st);
     if (e != cudaSuccess) return mvd::fail(static_cast<int>(e), "bn_bwd_reduce memset: %s", cudaGetErrorString(e));
-    bn_bwd_reduce_kernel<<<grid_for(M, C), THREADS, 0, st>>>(gy, x, y, stats, sums2, M, C, relu);
+    bn_bwd_reduce_kernel<<<grid_for(M, C), THREADS, 0, st>>>(gy, x, y, stats, sums2, local_sums2, M, C, relu,
+                                                             mvd::PeerArgs{peers, rank, world, nmax});
     return mvd::check_launch("bn_bwd_reduce");
 }
 

@@ -70,12 +70,10 @@ class PeerExchange:
 peer_exchange = True      # SyncBN statistics over NVLink peer memory when available (else NCCL all_reduce)
 
 
-def _sync_sum_(v):
-    px = PeerExchange.get(v.device) if (peer_exchange and v.numel() <= PeerExchange.NMAX) else None
-    if px is not None:
-        px.allreduce_(v)
-    else:
-        dist.all_reduce(v)
+def _peer(device, C):
+    """(peers table pointer, rank, world, nmax) for the in-kernel exchange, or None -> NCCL all_reduce after the kernel."""
+    px = PeerExchange.get(device) if (peer_exchange and 2 * C <= PeerExchange.NMAX) else None
+    return px
 
 
 def _count_launch(n):
@@ -91,11 +89,14 @@ class _BNAct(torch.autograd.Function):
         xc = x.contiguous(memory_format=_fmt(x))
         M = xc.numel() // C
         rc_ = residual.contiguous(memory_format=_fmt(x)) if residual is not None else None
-        sums = torch.empty(2 * C, device=x.device, dtype=torch.float64)
-        _lib.check(L.mvd_bn_stats(_p(xc), M, C, _p(sums), _stream()), "mvd_bn_stats")
+        sums = torch.empty(2 * C + 1, device=x.device, dtype=torch.float64)      # [sum x, sum x^2, arrival counter]
+        px = _peer(x.device, C) if sync else None
+        _lib.check(L.mvd_bn_stats(_p(xc), M, C, _p(sums), _p(px.ptrs) if px else _p(None), px.rank if px else 0,
+                                  px.world if px else 1, px.NMAX if px else 0, _stream()), "mvd_bn_stats")
         count = float(M)
         if sync:
-            _sync_sum_(sums)
+            if px is None:                                # no peer memory: NCCL exchanges the sums
+                dist.all_reduce(sums[:2 * C])
             count *= dist.get_world_size()
         stats = torch.empty(4 * C, device=x.device, dtype=torch.float32)
         _lib.check(L.mvd_bn_finalize(_p(sums), count, _p(weight), _p(bias), _p(running_mean), _p(running_var), float(momentum),
@@ -115,12 +116,19 @@ class _BNAct(torch.autograd.Function):
         M, C, count, relu, sync, has_res, post = ctx.cfg
         L = _lib.lib()
         gy = gy.contiguous(memory_format=_fmt(xc))
-        sums2 = torch.empty(2 * C, device=xc.device, dtype=torch.float64)
-        _lib.check(L.mvd_bn_bwd_reduce(_p(gy), _p(xc), _p(y), _p(stats), _p(sums2), M, C, int(relu), _stream()), "mvd_bn_bwd_reduce")
+        sums2 = torch.empty(2 * C + 1, device=xc.device, dtype=torch.float64)
+        px = _peer(xc.device, C) if sync else None
+        local2 = torch.empty(2 * C, device=xc.device, dtype=torch.float64) if px else None
+        _lib.check(L.mvd_bn_bwd_reduce(_p(gy), _p(xc), _p(y), _p(stats), _p(sums2), _p(local2), M, C, int(relu),
+                                       _p(px.ptrs) if px else _p(None), px.rank if px else 0, px.world if px else 1,
+                                       px.NMAX if px else 0, _stream()), "mvd_bn_bwd_reduce")
         gw = gb = None
         if sync:                                  # parameter gradients are this rank's own sums (DDP averages them later)
-            gb, gw = sums2[:C].float(), sums2[C:].float()
-            _sync_sum_(sums2)
+            if px is None:
+                gb, gw = sums2[:C].float(), sums2[C:2 * C].float()
+                dist.all_reduce(sums2[:2 * C])
+            else:                                 # the reduction kernel exchanged in place and kept the local sums aside
+                gb, gw = local2[:C].float(), local2[C:].float()
         else:
             gw = torch.empty(C, device=xc.device, dtype=torch.float32)
             gb = torch.empty(C, device=xc.device, dtype=torch.float32)

@@ -124,7 +124,11 @@ class FlatArena:
             p.data = view
             p.grad = _arena_view(self.grad[o:o + p.numel()], p)
         self.offsets = offs
-        self._static, self._pinned_tab = None, None
+        self._static = None
+        # pinned tables for captured collects (allocated here, outside any capture); a graph holds at most a few per arena
+        self._pinned_tabs = [torch.zeros(len(self.params), 14, dtype=torch.int64).pin_memory() for _ in range(8)] \
+            if self.data.is_cuda else []
+        self._pinned_next = 0
 
     def rebind_grads(self):
         for p, o in zip(self.params, self.offsets):
@@ -155,10 +159,11 @@ class FlatArena:
         rows, _, _ = self._gather_static()
         tab = torch.zeros(len(rows), 14, dtype=torch.int64)
         for i, (g, p, (o, n, phys)) in enumerate(zip(grads, self.params, rows)):
-            tab[i, 1], tab[i, 2] = o, n
+            tab[i, 1] = o
             tab[i, 4:9] = torch.tensor(phys)
-            if g is None:
+            if g is None:               # numel 0: the segment is left untouched (zero from the start if it never gets a gradient)
                 continue
+            tab[i, 2] = n
             assert g.shape == p.shape and g.dtype == torch.float32, (g.shape, p.shape, g.dtype)
             gs = g.permute(*([0] + list(range(2, g.dim())) + [1])) if g.dim() in (4, 5) else g     # destination physical order
             st = [0] * (5 - gs.dim()) + list(gs.stride())
@@ -169,15 +174,16 @@ class FlatArena:
 
     def collect(self, grads, pinned=False):
         """Write the gradient tensors returned by torch.autograd.grad into the flat gradient buffer with one kernel
-        (no zero_grad, no per-parameter accumulate).  `grads` must stay alive until the kernel has run; returns the
-        objects the caller has to keep alive (CUDA-graph capture: the pinned table is re-read at every replay)."""
+        (no zero_grad, no per-parameter accumulate); parameters whose entry is None keep what the buffer holds.  `grads`
+        must stay alive until the kernel has run; returns the objects the caller has to keep alive (CUDA-graph capture:
+        the pinned table is re-read at every replay)."""
         _, bm, nblocks = self._gather_static()
         tab = self.gather_table(grads)
-        if self._pinned_tab is None and self.data.is_cuda:
-            self._pinned_tab = torch.zeros_like(tab).pin_memory()        # allocated outside any capture (warm-up steps)
-        if pinned:                  # capture: the copy node re-reads this persistent pinned table at every replay
-            self._pinned_tab.copy_(tab)
-            tab = self._pinned_tab
+        if pinned:                  # capture: the copy node re-reads a persistent pinned table at every replay
+            slot = self._pinned_tabs[self._pinned_next % len(self._pinned_tabs)]
+            self._pinned_next += 1
+            slot.copy_(tab)
+            tab = slot
         dev_tab = tab.to(self.data.device, non_blocking=pinned)
         rc = ops._lib.lib().mvd_gather_segments(ops._p(dev_tab), ops._p(bm), nblocks, ops._p(self.grad), ops._stream())
         ops._lib.check(rc, "mvd_gather_segments")
@@ -349,25 +355,38 @@ class Trainer:
         outputs, losses = self.process_batch(inputs, is_train=True, noise=noise, mask_xy=mask_xy)
         multi = self.opt.ddp and self.world_size > 1
         capturing = torch.cuda.is_current_stream_capturing()
-        # The two graphs share nothing but detached tensors: back-propagate them separately so the cost-volume branch's
-        # gradients can be reduced while the mono/pose branch is still running.  torch.autograd.grad hands back the raw
-        # gradient tensors (no zero_grad, no per-parameter accumulate kernels); one gather kernel per parameter group
-        # writes them into the flat arena the all-reduce and the fused Adam kernel work on.
-        self._tf32("mvs")
-        p0, p1 = self.arenas[0].params, self.arenas[1].params
-        g = torch.autograd.grad(losses["_mvs_total"], p1 + p0, allow_unused=True)    # group-0 members of this graph: `up`
-        g1, g0_mvs = g[:len(p1)], g[len(p1):]
-        keep = [self.arenas[1].collect(g1, pinned=capturing)]
-        work = dist.all_reduce(self.arenas[1].grad, async_op=True) if multi else None
+        # The two graphs share nothing but detached tensors: they are back-propagated separately.
+        # torch.autograd.grad hands back the raw gradient tensors (no zero_grad, no per-parameter accumulate kernels); one
+        # gather kernel per parameter group writes them into the flat arena the all-reduce and the fused Adam kernel work on.
+        # Order: the mono / pose graph first.  Its arena (27 M parameters, 107 MB) is all-reduced while the much longer
+        # cost-volume backward runs; the cost-volume arena (1.4 M parameters) and the `up` tail of arena 0, whose gradients come
+        # from the cost-volume graph, follow at the end as two small calls.
+        a0, a1 = self.arenas
+        p0, p1 = a0.params, a1.params
         self._tf32("mono")
         g0 = torch.autograd.grad(losses["_mono_total"], p0, allow_unused=True)
-        g0 = [b if a is None else (a if b is None else a + b) for a, b in zip(g0, g0_mvs)]
-        keep.append(self.arenas[0].collect(g0, pinned=capturing))
+        keep = [a0.collect(g0, pinned=capturing)]
+        tail = self._arena0_tail(g0)                      # first parameter of arena 0 the mono graph does not reach (`up`)
+        work = dist.all_reduce(a0.grad[:tail], async_op=True) if multi else None
+        self._tf32("mvs")
+        g = torch.autograd.grad(losses["_mvs_total"], p1 + p0, allow_unused=True)
+        g1, g0_mvs = g[:len(p1)], g[len(p1):]
+        assert all(a is None or b is None for a, b in zip(g0, g0_mvs)), "a parameter receives gradients from both graphs"
+        keep.append(a1.collect(g1, pinned=capturing))
+        keep.append(a0.collect(g0_mvs, pinned=capturing))
         if multi:
-            dist.all_reduce(self.arenas[0].grad)
+            dist.all_reduce(a1.grad)
+            if tail < a0.numel:
+                dist.all_reduce(a0.grad[tail:])
             work.wait()
         outputs["_keepalive"] = keep
         return outputs, losses
+
+    def _arena0_tail(self, g0):
+        """Offset of the first arena-0 parameter after which the mono graph produced no gradient (the `up` head)."""
+        a0 = self.arenas[0]
+        last = max((i for i, g in enumerate(g0) if g is not None), default=-1)
+        return a0.offsets[last + 1] if last + 1 < len(a0.offsets) else a0.numel
 
     def _optimizer_step(self):
         self.opt_step += 1

@@ -726,3 +726,48 @@ def test_split_tf32_vectorised_and_scalar_paths(ops):
             hi = PR.tf32_round(x)
             want = torch.cat([hi, hi, x - hi] if weight else [hi, x - hi, hi], 1)
             assert torch.equal(y, want) and y.shape[1] == 3 * C
+
+
+def test_batchnorm_reductions_exchange_inside_the_kernel_two_ranks_on_one_gpu(ops):
+    """Data-parallel BatchNorm: the last block of mvd_bn_stats / mvd_bn_bwd_reduce all-reduces the 2C fp64 sums over peer
+    memory itself (no separate exchange launch).  Two 'ranks' = two streams with their own symmetric buffers on this GPU:
+    both must end with the sums over BOTH halves of the batch, and the backward keeps each rank's own sums aside."""
+    import ctypes
+    L = ops._lib.lib()
+    world, nmax, C, M = 2, 2048, 16, 5000
+    nbytes = L.mvd_peer_allreduce_buffer_bytes(world, nmax)
+    bufs = [torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=DEV) for _ in range(world)]
+    ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=DEV)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    gen = torch.Generator(device=DEV).manual_seed(35)
+    P = lambda t: ctypes.c_void_p(t.data_ptr() if t is not None else 0)
+    for it in range(6):
+        xs = [torch.randn(M + 100 * r, C, device=DEV, generator=gen) * 2 + 0.5 for r in range(world)]
+        gs = [torch.randn(M + 100 * r, C, device=DEV, generator=gen) for r in range(world)]
+        sums = [torch.empty(2 * C + 1, dtype=torch.float64, device=DEV) for _ in range(world)]
+        torch.cuda.synchronize()
+        for r in range(world):
+            rc = L.mvd_bn_stats(P(xs[r]), xs[r].shape[0], C, P(sums[r]), P(ptrs), r, world, nmax, ctypes.c_void_p(streams[r].cuda_stream))
+            assert rc == 0
+        torch.cuda.synchronize()
+        allx = torch.cat(xs).double()
+        want = torch.cat([allx.sum(0), (allx * allx).sum(0)])
+        assert torch.equal(sums[0][:2 * C], sums[1][:2 * C])
+        torch.testing.assert_close(sums[0][:2 * C], want, rtol=1e-6, atol=1e-6)
+        # backward reduction: sum g and sum g * xhat (stats: mean 0.5, invstd 0.5, scale / shift unused without ReLU)
+        stats = torch.cat([torch.full((C,), 0.5), torch.full((C,), 0.5), torch.ones(C), torch.zeros(C)]).to(DEV)
+        sums2 = [torch.empty(2 * C + 1, dtype=torch.float64, device=DEV) for _ in range(world)]
+        local = [torch.empty(2 * C, dtype=torch.float64, device=DEV) for _ in range(world)]
+        torch.cuda.synchronize()
+        for r in range(world):
+            rc = L.mvd_bn_bwd_reduce(P(gs[r]), P(xs[r]), P(None), P(stats), P(sums2[r]), P(local[r]), xs[r].shape[0], C, 0, P(ptrs), r,
+                                     world, nmax, ctypes.c_void_p(streams[r].cuda_stream))
+            assert rc == 0
+        torch.cuda.synchronize()
+        mine = [torch.cat([gs[r].double().sum(0), (gs[r].double() * (xs[r].double() - 0.5) * 0.5).sum(0)]) for r in range(world)]
+        for r in range(world):
+            torch.testing.assert_close(local[r], mine[r], rtol=1e-5, atol=1e-5)
+        assert torch.equal(sums2[0][:2 * C], sums2[1][:2 * C])
+        torch.testing.assert_close(sums2[0][:2 * C], mine[0] + mine[1], rtol=1e-5, atol=1e-5)
+    for b in bufs:
+        assert int(b.view(torch.int64)[1]) == 0 and int(b.view(torch.int64)[0]) == 12
