@@ -627,3 +627,51 @@ def decoder_prep(z, bias=None, skip=None, act=True, up=1, want_split=False):
     Returns (xp [B,C1+C2,up*h+2,up*w+2], x3 [B,3(C1+C2),...] or an empty tensor).
     Reference: movedepth/networks/depth_decoder.py:72-101, layers.py:521-553, 624-627."""
     return _DecoderPrep.apply(z, bias, skip, bool(act), int(up), bool(want_split))
+
+
+# ------------------------------------------------------------------------------------- skinny 2-D convolutions (FPN4 / UncertNet)
+def conv2d_small_supported(cin, cout, k, stride):
+    return bool(_lib.lib().mvd_conv2d_small_supported(int(cin), int(cout), int(k), int(stride)))
+
+
+class _Conv2dSmall(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, k, stride):
+        B, cin, H, W = x.shape
+        cout = weight.shape[0]
+        x = _nhwc(x)
+        w = _f32(weight).contiguous(memory_format=torch.channels_last)           # [cout][k][k][cin] in memory
+        Ho, Wo = (H + 2 * (k // 2) - k) // stride + 1, (W + 2 * (k // 2) - k) // stride + 1
+        y = torch.empty((B, cout, Ho, Wo), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+        rc = _lib.lib().mvd_conv2d_small_fwd(_p(x), _p(w), _p(y), B, H, W, cin, cout, k, stride, _stream())
+        _lib.check(rc, "mvd_conv2d_small_fwd")
+        launch_counter["n"] += 1
+        ctx.save_for_backward(x, w)
+        ctx.meta = (B, H, W, cin, cout, k, stride)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        B, H, W, cin, cout, k, stride = ctx.meta
+        gy = _nhwc(gy)
+        gx = gw = None
+        L = _lib.lib()
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            _lib.check(L.mvd_conv2d_small_dgrad(_p(gy), _p(w), _p(gx), B, H, W, cin, cout, k, stride, _stream()), "mvd_conv2d_small_dgrad")
+            launch_counter["n"] += 1
+        if ctx.needs_input_grad[1]:
+            nbytes = L.mvd_conv2d_small_wgrad_workspace_bytes(B, H, W, cin, cout, k, stride)
+            ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32)
+            gw = torch.empty_like(w)                                             # channels-last strides, logical [cout,cin,k,k]
+            _lib.check(L.mvd_conv2d_small_wgrad(_p(x), _p(gy), _p(gw), _p(ws), nbytes, B, H, W, cin, cout, k, stride, _stream()),
+                       "mvd_conv2d_small_wgrad")
+            launch_counter["n"] += 2
+        return gx, gw, None, None
+
+
+def conv2d_small(x, weight, k, stride):
+    """Exact-fp32 direct convolution (zero padding k//2, no bias) for the skinny FPN4 / UncertNet layers; x [B,cin,H,W]
+    (channels-last storage), weight [cout,cin,k,k].  Reference: movedepth/networks/resnet_encoder.py:325-341, 453-475."""
+    return _Conv2dSmall.apply(x, weight, int(k), int(stride))

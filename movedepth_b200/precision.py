@@ -24,6 +24,7 @@ import torch
 import torch.nn as nn
 
 _policy = {"mode": "fp32", "split_backward": False}
+small_direct = True      # skinny 2-D layers (<= 16 channels) on the exact-fp32 direct kernels of csrc/conv2d_small.cu
 
 
 def set_policy(mode, split_backward=None):
@@ -173,7 +174,22 @@ def _tup(v, n):
 class _PolicyMixin:
     _transposed = False
 
+    def _small(self, x):
+        """(k, stride) when this is one of the skinny 2-D layers the direct fp32 kernels cover, else None."""
+        if not (small_direct and x.is_cuda and x.dim() == 4 and not self._transposed and self.bias is None and self.groups == 1
+                and x.dtype == torch.float32 and getattr(self, "padding_mode", "zeros") == "zeros"):
+            return None
+        k, s, p, d = _tup(self.kernel_size, 2), _tup(self.stride, 2), _tup(self.padding, 2), _tup(self.dilation, 2)
+        if k[0] != k[1] or s[0] != s[1] or p != (k[0] // 2, k[0] // 2) or d != (1, 1):
+            return None
+        from . import ops
+        return (k[0], s[0]) if ops.conv2d_small_supported(self.in_channels, self.out_channels, k[0], s[0]) else None
+
     def forward(self, x):
+        small = self._small(x)
+        if small is not None and (self.in_channels > 3 or not x.requires_grad):      # the 3-channel layer has no data gradient
+            from . import ops
+            return ops.conv2d_small(x, self.weight, *small)
         if _policy["mode"] != "3xtf32" or getattr(self, "padding_mode", "zeros") != "zeros" or self.groups != 1 \
                 or any(d != 1 for d in _tup(self.dilation, x.dim() - 2)):
             return super().forward(x)

@@ -771,3 +771,60 @@ def test_batchnorm_reductions_exchange_inside_the_kernel_two_ranks_on_one_gpu(op
         torch.testing.assert_close(sums2[0][:2 * C], mine[0] + mine[1], rtol=1e-5, atol=1e-5)
     for b in bufs:
         assert int(b.view(torch.int64)[1]) == 0 and int(b.view(torch.int64)[0]) == 12
+
+
+# ---------------------------------------------------------------------------------------------- skinny 2-D convolutions
+@pytest.mark.parametrize("cfg", [(3, 8, 3, 1), (8, 8, 3, 1), (8, 16, 5, 2), (16, 16, 3, 1)], ids=["3-8", "8-8", "8-16-k5s2", "16-16"])
+@pytest.mark.parametrize("hw", [(16, 32), (13, 45), (48, 160)], ids=["aligned", "ragged", "multi-tile"])
+def test_conv2d_small_matches_torch_conv2d(ops, cfg, hw):
+    """csrc/conv2d_small.cu (FPN4's conv0 / conv1 stages, UncertNet's 8->8 layer): exact-fp32 direct forward, data gradient
+    (flipped-filter forward kernel for stride 1, parity gather for stride 2) and weight gradient vs torch's CPU conv2d in
+    fp64; 1e-5 of the output scale (fp32 accumulation of <= 400 products)."""
+    import torch.nn.functional as F
+    cin, cout, k, s = cfg
+    H, W = hw
+    if s == 2:
+        H, W = H & ~1, W & ~1
+    gen = torch.Generator().manual_seed(41)
+    x = torch.randn(2, cin, H, W, generator=gen)
+    w = torch.randn(cout, cin, k, k, generator=gen) * 0.2
+    xo, wo = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    yo = F.conv2d(xo, wo, stride=s, padding=k // 2)
+    gy = torch.randn(yo.shape, generator=gen)
+    (yo * gy.double()).sum().backward()
+    need_gx = cin > 3
+    xg = g(x).contiguous(memory_format=torch.channels_last).requires_grad_(need_gx)
+    wg = g(w).requires_grad_(True)
+    assert ops.conv2d_small_supported(cin, cout, k, s)
+    y = ops.conv2d_small(xg, wg, k, s)
+    assert y.shape == yo.shape
+    (y * g(gy)).sum().backward()
+    pairs = [(y, yo), (wg.grad, wo.grad)] + ([(xg.grad, xo.grad)] if need_gx else [])
+    for got, want in pairs:
+        want = want.detach().float()
+        torch.testing.assert_close(got.detach().cpu(), want, atol=1e-5 * float(want.abs().max()), rtol=1e-5)
+
+
+def test_fpn4_routes_its_skinny_layers_through_the_direct_kernels(ops):
+    """FPN4 (fp32 policy) with the direct kernels vs the oracle FPN4 on the CPU: both outputs and every parameter gradient;
+    the launch counter proves the conv0 / conv1 stages took the direct path."""
+    from movedepth_b200 import networks as PN, precision as PR
+    from oracle import networks as ON
+    PR.set_policy("fp32")
+    gen = torch.Generator().manual_seed(43)
+    img = torch.rand(2, 3, 64, 96, generator=gen)
+    a, b = PN.FPN4(8, 2), ON.FPN4(8, 2)
+    fill_deterministic(a)
+    fill_deterministic(b)
+    a.to(DEV)
+    n0 = ops.launch_counter["n"]
+    fa, ca = a(g(img).contiguous(memory_format=torch.channels_last))
+    assert ops.launch_counter["n"] - n0 >= 5                      # five skinny convolutions + the BatchNorm kernels
+    fb, cb = b(img)
+    torch.testing.assert_close(fa.detach().cpu(), fb.detach(), atol=1e-4 * float(fb.abs().max()), rtol=1e-4)
+    torch.testing.assert_close(ca.detach().cpu(), cb.detach(), atol=1e-4 * float(cb.abs().max()), rtol=1e-4)
+    gf, gc = torch.randn(fb.shape, generator=gen), torch.randn(cb.shape, generator=gen)
+    ((fa * g(gf)).sum() + (ca * g(gc)).sum()).backward()
+    ((fb * gf).sum() + (cb * gc).sum()).backward()
+    for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        torch.testing.assert_close(pa.grad.cpu(), pb.grad, atol=1e-3 * float(pb.grad.abs().max()) + 1e-7, rtol=1e-3, msg=n)

@@ -66,6 +66,16 @@ def main():
                 t = e.self_cuda_time_total
             if t > 0 and e.key.startswith("aten::") and "conv" not in e.key:
                 rows.append((t, e.count, e.key, str(e.input_shapes)[:110]))
+        crow = []
+        for e in prof.key_averages(group_by_input_shape=True):
+            t = getattr(e, "device_time_total", None)
+            if t is None:
+                t = e.cuda_time_total
+            if t > 0 and ("convolution" in e.key or e.key in ("_SplitConv", "_PreparedConv", "_SplitConvBackward", "_PreparedConvBackward")):
+                crow.append((t, e.count, e.key, str(e.input_shapes)[:130]))
+        print("\nconvolution ops by input shape (total device time incl. children, top 70)")
+        for t, c, k, sh in sorted(crow, reverse=True)[:70]:
+            print("%9.1f us %5d %5.1f%%  %-30s %s" % (t, c, 100 * t / total, k, sh))
         print("\nnon-conv ATen ops by input shape (top 60): the eager tail")
         for t, c, k, sh in sorted(rows, reverse=True)[:60]:
             print("%9.1f us %5d %5.1f%%  %-28s %s" % (t, c, 100 * t / total, k, sh))
