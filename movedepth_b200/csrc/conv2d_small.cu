@@ -31,7 +31,7 @@ template <int CIN, int COUT, int K, int S, int PR>
 struct FwdCfg {
     static constexpr int ROWS = 4 * PR;
     static constexpr int IH = (ROWS - 1) * S + K, IW = 31 * S + K, IWP = IW | 1;
-    static constexpr int XS = CIN * IH * IWP, WS = K * K * CIN * COUT;
+    static constexpr int XS = (CIN * IH * IWP + 3) & ~3, WS = K * K * CIN * COUT;      // float4 alignment of the filter behind it
     static constexpr int SMEM = (XS + WS) * 4;
     static constexpr int COL = (PR - 1) * S + K;          // input rows one thread touches per (ci, kx)
 };
@@ -39,7 +39,7 @@ struct FwdCfg {
 template <int CIN, int COUT, int K, int S, int PR>
 __global__ void __launch_bounds__(128) small_fwd_kernel(const Args a) {
     using CF = FwdCfg<CIN, COUT, K, S, PR>;
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     float* xs = smem;
     float* ws = smem + CF::XS;
     const int tid = threadIdx.x, lane = tid & 31, q = tid >> 5;
@@ -121,14 +121,14 @@ template <int CIN, int COUT, int K>
 struct Dg2Cfg {
     static constexpr int ROWS = 8;                            // input rows per block (4 warps x 2)
     static constexpr int GH = ROWS / 2 + K / 2 + 1, GW = 32 + K / 2 + 1, GWP = GW | 1;
-    static constexpr int GS = COUT * GH * GWP, WS = K * K * COUT * CIN;
+    static constexpr int GS = (COUT * GH * GWP + 3) & ~3, WS = K * K * COUT * CIN;
     static constexpr int SMEM = (GS + WS) * 4;
 };
 
 template <int CIN, int COUT, int K>
 __global__ void __launch_bounds__(128) small_dgrad_s2_kernel(const Args a) {   // a.x = gy [B,Ho,Wo,COUT], a.y = gx [B,H,W,CIN]
     using CF = Dg2Cfg<CIN, COUT, K>;
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     float* gs = smem;
     float* ws = smem + CF::GS;                                // [tap][co][ci], ci fastest
     const int tid = threadIdx.x, lane = tid & 31, q = tid >> 5;
@@ -199,7 +199,7 @@ struct WgCfg {
     static constexpr int THREADS = NT * PG;
     static constexpr int TH = 8, TW = 32;
     static constexpr int IH = (TH - 1) * S + K, IW = (TW - 1) * S + K;
-    static constexpr int XS = IH * IW * CIN, GS = TH * TW * COUT;
+    static constexpr int XN = IH * IW * CIN, XS = (XN + 3) & ~3, GS = TH * TW * COUT;
     static constexpr int SMEM = (XS + GS) * 4;
     static constexpr int NW = K * K * CIN * COUT;
 };
@@ -214,7 +214,7 @@ struct WArgs {
 template <int CIN, int COUT, int K, int S>
 __global__ void __launch_bounds__(WgCfg<CIN, COUT, K, S>::THREADS) small_wgrad_kernel(const WArgs a) {
     using CF = WgCfg<CIN, COUT, K, S>;
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     float* xs = smem;                  // [r][c][ci]
     float* gs = smem + CF::XS;         // [pixel][co]
     const int tid = threadIdx.x;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(WgCfg<CIN, COUT, K, S>::THREADS) small_wgrad_k
         const int ox0 = tx * CF::TW, oy0 = ty * CF::TH;
         const int iy0 = oy0 * S - P, ix0 = ox0 * S - P;
         __syncthreads();               // previous tile fully consumed
-        for (int e = tid; e < CF::XS; e += CF::THREADS) {
+        for (int e = tid; e < CF::XN; e += CF::THREADS) {
             const int c_ = e % CIN, p = e / CIN, c = p % CF::IW, r = p / CF::IW;
             const int gy_ = iy0 + r, gx_ = ix0 + c;
             float v = 0.f;
