@@ -58,12 +58,28 @@ __global__ void __launch_bounds__(128) small_fwd_kernel(const Args a) {
     }
     // input tile -> xs[ci][r][c], zero padded
     const int iy0 = oy0 * S - P, ix0 = ox0 * S - P;
-    for (int e = tid; e < CF::IH * CF::IW * CIN; e += 128) {
-        const int ci = e % CIN, p = e / CIN, c = p % CF::IW, r = p / CF::IW;
-        const int gy = iy0 + r, gx = ix0 + c;
-        float v = 0.f;
-        if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) v = __ldg(a.x + ((static_cast<size_t>(b) * a.H + gy) * a.W + gx) * CIN + ci);
-        xs[(ci * CF::IH + r) * CF::IWP + c] = v;
+    if (CIN % 4 == 0) {                // 16-byte global loads, scattered to the channel planes
+        constexpr int C4 = CIN / 4 > 0 ? CIN / 4 : 1;
+        for (int e = tid; e < CF::IH * CF::IW * C4; e += 128) {
+            const int c4 = e % C4, p = e / C4, c = p % CF::IW, r = p / CF::IW;
+            const int gy = iy0 + r, gx = ix0 + c;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W)
+                v = __ldg(reinterpret_cast<const float4*>(a.x + ((static_cast<size_t>(b) * a.H + gy) * a.W + gx) * CIN) + c4);
+            float* d = xs + ((4 * c4) * CF::IH + r) * CF::IWP + c;
+            d[0] = v.x;
+            d[CF::IH * CF::IWP] = v.y;
+            d[2 * CF::IH * CF::IWP] = v.z;
+            d[3 * CF::IH * CF::IWP] = v.w;
+        }
+    } else {
+        for (int e = tid; e < CF::IH * CF::IW * CIN; e += 128) {
+            const int ci = e % CIN, p = e / CIN, c = p % CF::IW, r = p / CF::IW;
+            const int gy = iy0 + r, gx = ix0 + c;
+            float v = 0.f;
+            if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) v = __ldg(a.x + ((static_cast<size_t>(b) * a.H + gy) * a.W + gx) * CIN + ci);
+            xs[(ci * CF::IH + r) * CF::IWP + c] = v;
+        }
     }
     __syncthreads();
     float acc[PR][COUT];
@@ -141,12 +157,17 @@ __global__ void __launch_bounds__(128) small_dgrad_s2_kernel(const Args a) {   /
     // gy tile: rows oy in [(iy0 + P - (K-1)) / 2 floor, ...]: start at floor((iy0 - P) / 2) (iy0 is even)
     const int oy_base = (iy0 - P) / 2 - ((iy0 - P) < 0 && ((iy0 - P) & 1) ? 1 : 0);
     const int ox_base = (ix0 - P) / 2 - ((ix0 - P) < 0 && ((ix0 - P) & 1) ? 1 : 0);
-    for (int e = tid; e < CF::GH * CF::GW * COUT; e += 128) {
-        const int co = e % COUT, p = e / COUT, c = p % CF::GW, r = p / CF::GW;
+    for (int e = tid; e < CF::GH * CF::GW * (COUT / 4); e += 128) {
+        const int c4 = e % (COUT / 4), p = e / (COUT / 4), c = p % CF::GW, r = p / CF::GW;
         const int oy = oy_base + r, ox = ox_base + c;
-        float v = 0.f;
-        if (oy >= 0 && oy < a.Ho && ox >= 0 && ox < a.Wo) v = __ldg(a.x + ((static_cast<size_t>(b) * a.Ho + oy) * a.Wo + ox) * COUT + co);
-        gs[(co * CF::GH + r) * CF::GWP + c] = v;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (oy >= 0 && oy < a.Ho && ox >= 0 && ox < a.Wo)
+            v = __ldg(reinterpret_cast<const float4*>(a.x + ((static_cast<size_t>(b) * a.Ho + oy) * a.Wo + ox) * COUT) + c4);
+        float* d = gs + ((4 * c4) * CF::GH + r) * CF::GWP + c;
+        d[0] = v.x;
+        d[CF::GH * CF::GWP] = v.y;
+        d[2 * CF::GH * CF::GWP] = v.z;
+        d[3 * CF::GH * CF::GWP] = v.w;
     }
     __syncthreads();
 #pragma unroll 1
@@ -229,24 +250,38 @@ __global__ void __launch_bounds__(WgCfg<CIN, COUT, K, S>::THREADS) small_wgrad_k
         const int ox0 = tx * CF::TW, oy0 = ty * CF::TH;
         const int iy0 = oy0 * S - P, ix0 = ox0 * S - P;
         __syncthreads();               // previous tile fully consumed
-        for (int e = tid; e < CF::XN; e += CF::THREADS) {
-            const int c_ = e % CIN, p = e / CIN, c = p % CF::IW, r = p / CF::IW;
-            const int gy_ = iy0 + r, gx_ = ix0 + c;
-            float v = 0.f;
-            if (gy_ >= 0 && gy_ < a.H && gx_ >= 0 && gx_ < a.W) v = __ldg(a.x + ((static_cast<size_t>(b) * a.H + gy_) * a.W + gx_) * CIN + c_);
-            xs[e] = v;
+        if (CIN % 4 == 0) {
+            constexpr int C4 = CIN / 4 > 0 ? CIN / 4 : 1;
+            for (int e = tid; e < CF::IH * CF::IW * C4; e += CF::THREADS) {
+                const int c4 = e % C4, p = e / C4, c = p % CF::IW, r = p / CF::IW;
+                const int gy_ = iy0 + r, gx_ = ix0 + c;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gy_ >= 0 && gy_ < a.H && gx_ >= 0 && gx_ < a.W)
+                    v = __ldg(reinterpret_cast<const float4*>(a.x + ((static_cast<size_t>(b) * a.H + gy_) * a.W + gx_) * CIN) + c4);
+                reinterpret_cast<float4*>(xs)[e] = v;
+            }
+        } else {
+            for (int e = tid; e < CF::XN; e += CF::THREADS) {
+                const int c_ = e % CIN, p = e / CIN, c = p % CF::IW, r = p / CF::IW;
+                const int gy_ = iy0 + r, gx_ = ix0 + c;
+                float v = 0.f;
+                if (gy_ >= 0 && gy_ < a.H && gx_ >= 0 && gx_ < a.W) v = __ldg(a.x + ((static_cast<size_t>(b) * a.H + gy_) * a.W + gx_) * CIN + c_);
+                xs[e] = v;
+            }
         }
-        for (int e = tid; e < CF::GS; e += CF::THREADS) {
-            const int co = e % COUT, p = e / COUT, c = p % CF::TW, r = p / CF::TW;
+        for (int e = tid; e < CF::TH * CF::TW * (COUT / 4); e += CF::THREADS) {
+            const int c4 = e % (COUT / 4), p = e / (COUT / 4), c = p % CF::TW, r = p / CF::TW;
             const int oy = oy0 + r, ox = ox0 + c;
-            float v = 0.f;                                                     // pixels outside the output contribute nothing
-            if (oy < a.Ho && ox < a.Wo) v = __ldg(a.gy + ((static_cast<size_t>(b) * a.Ho + oy) * a.Wo + ox) * COUT + co);
-            gs[e] = v;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);                        // pixels outside the output contribute nothing
+            if (oy < a.Ho && ox < a.Wo) v = __ldg(reinterpret_cast<const float4*>(a.gy + ((static_cast<size_t>(b) * a.Ho + oy) * a.Wo + ox) * COUT) + c4);
+            reinterpret_cast<float4*>(gs)[e] = v;
         }
         __syncthreads();
+        const float* xb = xs + (ky * CF::IW + kx) * CIN + ci;
+#pragma unroll 2
         for (int p = grp; p < CF::TH * CF::TW; p += CF::PG) {
-            const int r = p / CF::TW, c = p % CF::TW;
-            const float v = xs[((r * S + ky) * CF::IW + (c * S + kx)) * CIN + ci];
+            const int r = p / CF::TW, c = p % CF::TW;                           // TW = 32: shift / mask
+            const float v = xb[((r * S) * CF::IW + c * S) * CIN];
             const float* gp = gs + p * COUT;
 #pragma unroll
             for (int c4 = 0; c4 < COUT; c4 += 4) {
@@ -294,7 +329,7 @@ template <int CIN, int COUT, int K, int S>
 static int wgrad_ctas(int B, int Ho, int Wo) {
     using CF = WgCfg<CIN, COUT, K, S>;
     const int tiles = B * ((Ho + CF::TH - 1) / CF::TH) * ((Wo + CF::TW - 1) / CF::TW);
-    const int cap = sm_count() * 2;
+    const int cap = sm_count() * 4;
     return tiles < cap ? tiles : cap;
 }
 
