@@ -274,8 +274,11 @@ int mvd_conv3d_c16c16(const float* in, const float* w, float* out, int B, int D,
 /* The same contract on the 5th-generation tensor cores: tcgen05.mma kind::tf32, accumulators in TMEM, every tap's
  * A operand = the TMA-staged slice at a shifted start address.  flags: 0; profiling only (results become meaningless):
  * 2 = skip the MMAs, 4 = skip the global stores, 8 = skip the hi/lo operand split. */
-int mvd_conv3d_c16c16_tc(const float* in, const float* w, float* out, int B, int D, int H, int W,
+int mvd_conv3d_c16c16_tc(const float* in, const float* w, float* out, double* bn_sums, int B, int D, int H, int W,
                          int mode, int passes, int flags, void* stream);
+/* bn_sums (nullable, 32 doubles, ZEROED BY THE CALLER): the epilogue adds the per-channel sums [sum y (16), sum y^2 (16)] of
+ * the output it writes -- the BatchNorm statistics of ConvBnReLU3D (resnet_encoder.py:175-182) without another pass over
+ * the 283 MB volume; feed them to mvd_bn_finalize. */
 /* Weight gradient on tcgen05 (single-pass TF32; MN-major operands, the four M-groups of A are the x slice shifted by
  * kw positions); same workspace / reduction scheme as mvd_conv3d_c16c16_wgrad. */
 long long mvd_conv3d_c16c16_wgrad_tc_workspace_bytes(int B, int D, int H, int W);

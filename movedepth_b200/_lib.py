@@ -57,7 +57,7 @@ SIGNATURES = {
     "mvd_conv3d_c16o1_wgrad_workspace_bytes": ([_I] * 4, _LL),
     "mvd_conv3d_c16o1_wgrad": ([_P] * 4 + [_LL] + [_I] * 4 + [_P], _I),
     "mvd_conv3d_c16c16": ([_P] * 3 + [_I] * 6 + [_P], _I),
-    "mvd_conv3d_c16c16_tc": ([_P] * 3 + [_I] * 7 + [_P], _I),
+    "mvd_conv3d_c16c16_tc": ([_P] * 4 + [_I] * 7 + [_P], _I),
     "mvd_conv3d_c16c16_wgrad_tc_workspace_bytes": ([_I] * 4, _LL),
     "mvd_conv3d_c16c16_wgrad_tc": ([_P] * 4 + [_LL] + [_I] * 4 + [_P], _I),
     "mvd_conv3d_c16c16_wgrad_workspace_bytes": ([_I] * 4, _LL),

@@ -307,12 +307,14 @@ __global__ void __launch_bounds__(WgCfg<CIN, COUT, K, S>::THREADS) small_wgrad_k
     }
 }
 
-__global__ void __launch_bounds__(128) small_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ gw, int nw, int ctas) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per weight element: lanes stride over the per-CTA partials, shuffle reduction (fixed order: deterministic)
+__global__ void __launch_bounds__(256) small_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ gw, int nw, int ctas) {
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= nw) return;
-    double s = 0.0;
-    for (int c = 0; c < ctas; ++c) s += static_cast<double>(part[static_cast<size_t>(c) * nw + i]);
-    gw[i] = static_cast<float>(s);
+    float s = 0.f;
+    for (int c = lane; c < ctas; c += 32) s += __ldg(part + static_cast<size_t>(c) * nw + i);
+    s = warp_sum(s);
+    if (lane == 0) gw[i] = s;
 }
 
 // ------------------------------------------------------------------------------------------------ host dispatch
@@ -329,7 +331,7 @@ template <int CIN, int COUT, int K, int S>
 static int wgrad_ctas(int B, int Ho, int Wo) {
     using CF = WgCfg<CIN, COUT, K, S>;
     const int tiles = B * ((Ho + CF::TH - 1) / CF::TH) * ((Wo + CF::TW - 1) / CF::TW);
-    const int cap = sm_count() * 4;
+    const int cap = sm_count() * 3;
     return tiles < cap ? tiles : cap;
 }
 
@@ -346,7 +348,7 @@ static int launch_wgrad(const float* x, const float* gy, float* gw, float* ws, l
     cudaFuncSetAttribute(small_wgrad_kernel<CIN, COUT, K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     small_wgrad_kernel<CIN, COUT, K, S><<<ctas, CF::THREADS, smem, st>>>(a);
     if (int rc = check_launch("conv2d_small_wgrad")) return rc;
-    small_wgrad_reduce_kernel<<<(CF::NW + 127) / 128, 128, 0, st>>>(ws, gw, CF::NW, ctas);
+    small_wgrad_reduce_kernel<<<(CF::NW + 7) / 8, 256, 0, st>>>(ws, gw, CF::NW, ctas);
     return check_launch("conv2d_small_wgrad_reduce");
 }
 

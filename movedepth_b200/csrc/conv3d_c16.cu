@@ -743,6 +743,7 @@ __device__ __forceinline__ void tmem_zero16(uint32_t taddr) {
 struct TArgs {
     const float* w;
     float* out;
+    double* bn_sums;     // nullable: [sum y (16), sum y^2 (16)] accumulated over the whole output (fused BatchNorm statistics)
     int mode, dbg;
     int B, D, H, W;
     int tiles_h, tiles_w, dsplit, dlen;
@@ -849,6 +850,9 @@ conv3d_c16c16_tc_kernel(const __grid_constant__ CUtensorMap map_in, const TArgs 
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     const uint64_t bh_desc = smem_desc(smem_u32(smem + CF::OFF_BH)), bi_desc = smem_desc(smem_u32(smem + CF::OFF_BI));
 
+    float bn_s[16], bn_ss[16];                                   // this thread's share of the BatchNorm statistics of the output
+#pragma unroll
+    for (int q = 0; q < 16; ++q) bn_s[q] = bn_ss[q] = 0.f;
     // epilogue of input slice j: output slice d = (d0-1+j) - 1 is complete (it received kd = 2 from slice j)
     auto epilogue = [&](int j) {
         const int d = it.d0 - 2 + j;
@@ -875,6 +879,13 @@ conv3d_c16c16_tc_kernel(const __grid_constant__ CUtensorMap map_in, const TArgs 
                 }
                 const int v = mb * 128 + tid, rr = v / HW, cc = v - rr * HW;
                 const int h = it.h0 + rr, w = it.w0 + cc;
+                if (a.bn_sums != nullptr && rr < TH && cc < TW && h < a.H && w < a.W) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        bn_s[q] += o[q];
+                        bn_ss[q] = fmaf(o[q], o[q], bn_ss[q]);
+                    }
+                }
                 if (rr < TH && cc < TW && h < a.H && w < a.W && !(a.dbg & 4)) {
                     float4* op = reinterpret_cast<float4*>(a.out + (((static_cast<size_t>(it.b) * a.D + d) * a.H + h) * a.W + w) * C);
                     op[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -946,6 +957,20 @@ conv3d_c16c16_tc_kernel(const __grid_constant__ CUtensorMap map_in, const TArgs 
     epilogue(count - 1);
     tc_fence_before();
     __syncthreads();
+    if (a.bn_sums != nullptr) {                                  // block reduction in the (now idle) slice ring, 32 fp64 atomics per item
+        float* red = reinterpret_cast<float*>(smem + CF::OFF_A);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            red[q * THREADS + tid] = bn_s[q];
+            red[(16 + q) * THREADS + tid] = bn_ss[q];
+        }
+        __syncthreads();
+        if (tid < 32) {
+            double t = 0.0;
+            for (int k = 0; k < THREADS; ++k) t += static_cast<double>(red[tid * THREADS + ((k + tid) & (THREADS - 1))]);
+            atomicAdd(a.bn_sums + tid, t);
+        }
+    }
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(CF::TMEM_COLS) : "memory");
 }
 
@@ -981,17 +1006,19 @@ static_assert((2 * (WP / 2) + (WG_KSTEPS - 1) * 8 + 8 + 3) * 128 <= SLICE_BYTES,
 
 // MN-major SWIZZLE_128B_BASE32B descriptor: LBO = byte stride between 32-element (128 B) groups along M/N,
 // SBO = stride between groups of 4 K rows (512 B)
-__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t saddr) {
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes = 128) {
     uint64_t d = 0;
     d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
-    d |= static_cast<uint64_t>(128 >> 4) << 16;
+    d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
     d |= static_cast<uint64_t>(512 >> 4) << 32;
     d |= static_cast<uint64_t>(1) << 46;
     d |= static_cast<uint64_t>(1) << 61;
     return d;
 }
-// D = F32, A = B = TF32, both MN-major, M = 128, N = 32
-constexpr uint32_t WG_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+// D = F32, A = B = TF32, both MN-major, M = 128, N = n (32, 64 or 96: one 32-column group per gy slice)
+__device__ __forceinline__ constexpr uint32_t wg_idesc(uint32_t n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
 
 struct WTArgs {
     float* part;         // [2 * items][6912]: even-position and odd-position halves of every item
@@ -1074,17 +1101,24 @@ conv3d_c16c16_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const _
         tc_fence_after();
         if (elect_one()) {
             const uint32_t xaddr = smem_u32(smem + WgCfg::OFF_X + xb * SLICE_BYTES);
-#pragma unroll
-            for (int acc = 0; acc < 9; ++acc) {
-                if ((acc * 4) / 9 != warp) continue;                   // the nine (kd,kh) accumulators are dealt to the four warps
-                const int kd = acc / 3, kh = acc - kd * 3;
-                const int d = s + 1 - kd;
-                if (d < it.d0 || d >= it.d1) continue;
+            // x slice s meets the gy slices d = s-1, s, s+1 (kd = 2, 1, 0).  The kd taps are folded into the MMA's N dimension:
+            // the gy ring slots are GY_BYTES apart (= the descriptor's leading-dimension offset between 32-column groups), so
+            // slices in consecutive slots are ONE MMA of N = 32 * run and the 4 KB x operand is read once for up to three kd
+            // (the operand reads, not the tensor pipe, bound this kernel).  Accumulator of (kh): columns kh*96 + (2-kd)*32.
+            const int lo = max(s - 1, it.d0), hi = min(s + 1, it.d1 - 1);
+            if (warp < 3 && lo <= hi) {                                // kh = warp
+                const int kh = warp;
                 const uint64_t ad = smem_desc_mn(xaddr + static_cast<uint32_t>(kh * WP) * 64u);       // kh tile rows down = 18 smem rows
-                const uint64_t bd = smem_desc_mn(smem_u32(smem + WgCfg::OFF_G + (d & 3) * GY_BYTES));
+                for (int d = lo; d <= hi;) {
+                    const int slot = d & 3, run = min(hi - d + 1, 4 - slot);
+                    const uint32_t col = static_cast<uint32_t>(kh * 96 + (d - (s - 1)) * 32);
+                    const uint64_t bd = smem_desc_mn(smem_u32(smem + WgCfg::OFF_G + slot * GY_BYTES), GY_BYTES);
+                    const uint32_t id = wg_idesc(32u * run);
 #pragma unroll 4
-                for (int ks = 0; ks < WG_KSTEPS; ++ks)                 // 8 rows = 16 positions = 1 KB per MMA
-                    umma_tf32(tmem_base + acc * 32, ad + static_cast<uint64_t>(ks * 64), bd + static_cast<uint64_t>(ks * 64), WG_IDESC);
+                    for (int ks = 0; ks < WG_KSTEPS; ++ks)             // 8 rows = 16 positions = 1 KB of x per MMA
+                        umma_tf32(tmem_base + col, ad + static_cast<uint64_t>(ks * 64), bd + static_cast<uint64_t>(ks * 64), id);
+                    d += run;
+                }
             }
             umma_commit(done + (i & 1));
         }
@@ -1105,10 +1139,11 @@ conv3d_c16c16_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_x, const _
         float* p1 = p0 + NW16;                                                 // j = 1: kw = s - 2
         const int sh = tid >> 4, ci = tid & 15;
 #pragma unroll 1
-        for (int acc = 0; acc < 9; ++acc) {
+        for (int acc = 0; acc < 9; ++acc) {                            // acc = kd*3 + kh lives in columns kh*96 + (2-kd)*32
             uint32_t r0[16], r1[16];
-            tmem_ld16(lane_addr + acc * 32, r0);
-            tmem_ld16(lane_addr + acc * 32 + 16, r1);
+            const uint32_t col = static_cast<uint32_t>((acc % 3) * 96 + (2 - acc / 3) * 32);
+            tmem_ld16(lane_addr + col, r0);
+            tmem_ld16(lane_addr + col + 16, r1);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int co = 0; co < 16; ++co) {
@@ -1308,8 +1343,8 @@ int mvd_conv3d_c16c16_wgrad(const float* gy, const float* x, float* gw, void* wo
 }
 
 
-int mvd_conv3d_c16c16_tc(const float* in, const float* w, float* out, int B, int D, int H, int W, int mode, int passes,
-                         int flags, void* stream) {
+int mvd_conv3d_c16c16_tc(const float* in, const float* w, float* out, double* bn_sums, int B, int D, int H, int W, int mode,
+                         int passes, int flags, void* stream) {
     using namespace mvd::c16;
     MVD_REQUIRE(in && w && out, "null pointer argument");
     if (int rc = check_shape(B, D, H, W)) return rc;
@@ -1318,7 +1353,7 @@ int mvd_conv3d_c16c16_tc(const float* in, const float* w, float* out, int B, int
     MVD_REQUIRE(mvd::aligned16(in) && mvd::aligned16(out), "activation pointers must be 16-byte aligned");
     cudaStream_t st = mvd::as_stream(stream);
     tc::TArgs a{};
-    a.w = w; a.out = out; a.mode = mode; a.B = B; a.D = D; a.H = H; a.W = W;
+    a.w = w; a.out = out; a.bn_sums = bn_sums; a.mode = mode; a.B = B; a.D = D; a.H = H; a.W = W;
     a.tiles_h = (H + tc::TH - 1) / tc::TH;
     a.tiles_w = (W + tc::TW - 1) / tc::TW;
     a.dbg = flags;

@@ -146,6 +146,13 @@ class ConvBnReLU3D(nn.Module):
         self.bn = nn.BatchNorm3d(out_channels)
 
     def forward(self, x):
+        c = self.conv
+        if (PR.get_policy() == "3xtf32" and self.bn.training and x.is_cuda and x.dim() == 5 and tuple(c.weight.shape) == (16, 16, 3, 3, 3)
+                and c.bias is None and tuple(c.stride) == (1, 1, 1) and tuple(c.padding) == (1, 1, 1) and not PR._policy["split_backward"]):
+            # reg3d's full-resolution first layer: the tcgen05 conv's epilogue sums the BatchNorm statistics of its output
+            from .. import ops
+            y, sums = ops.conv3d_c16_to_16_with_stats(x, c.weight, 3)
+            return NM.bn_act(self.bn, y, relu=True, sums=sums)
         return NM.bn_act(self.bn, self.conv(x), relu=True)
 
 

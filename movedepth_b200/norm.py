@@ -83,19 +83,24 @@ def _count_launch(n):
 
 class _BNAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, running_mean, running_var, momentum, eps, relu, sync, post=False, nbt=None):
+    def forward(ctx, x, weight, bias, residual, running_mean, running_var, momentum, eps, relu, sync, post=False, nbt=None,
+                sums=None):
         L = _lib.lib()
         C = x.shape[1]
         xc = x.contiguous(memory_format=_fmt(x))
         M = xc.numel() // C
         rc_ = residual.contiguous(memory_format=_fmt(x)) if residual is not None else None
-        sums = torch.empty(2 * C + 1, device=x.device, dtype=torch.float64)      # [sum x, sum x^2, arrival counter]
         px = _peer(x.device, C) if sync else None
-        _lib.check(L.mvd_bn_stats(_p(xc), M, C, _p(sums), _p(px.ptrs) if px else _p(None), px.rank if px else 0,
-                                  px.world if px else 1, px.NMAX if px else 0, _stream()), "mvd_bn_stats")
+        precomputed = sums is not None and sums.numel() >= 2 * C       # the producing conv's epilogue already summed its output
+        if not precomputed:
+            sums = torch.empty(2 * C + 1, device=x.device, dtype=torch.float64)      # [sum x, sum x^2, arrival counter]
+            _lib.check(L.mvd_bn_stats(_p(xc), M, C, _p(sums), _p(px.ptrs) if px else _p(None), px.rank if px else 0,
+                                      px.world if px else 1, px.NMAX if px else 0, _stream()), "mvd_bn_stats")
         count = float(M)
         if sync:
-            if px is None:                                # no peer memory: NCCL exchanges the sums
+            if precomputed and px is not None:            # fused statistics: the exchange is its own (single-CTA) kernel
+                px.allreduce_(sums[:2 * C])
+            elif px is None:                              # no peer memory: NCCL exchanges the sums
                 dist.all_reduce(sums[:2 * C])
             count *= dist.get_world_size()
         stats = torch.empty(4 * C, device=x.device, dtype=torch.float32)
@@ -144,7 +149,7 @@ class _BNAct(torch.autograd.Function):
             gw = None
         if not ctx.needs_input_grad[2]:
             gb = None
-        return gx, gw, gb, gres, None, None, None, None, None, None, None, None
+        return gx, gw, gb, gres, None, None, None, None, None, None, None, None, None
 
 
 def _fusable(bn, x):
@@ -153,7 +158,7 @@ def _fusable(bn, x):
             and bn.momentum is not None and 4 <= C <= 1024 and (C & (C - 1)) == 0 and x.numel() > 0)
 
 
-def bn_act(bn, x, relu=False, residual=None, post=False):
+def bn_act(bn, x, relu=False, residual=None, post=False, sums=None):
     """relu(bn(x) + residual), or relu(bn(x)) + residual with post=True, with `bn` a BatchNorm2d / BatchNorm3d /
     SyncBatchNorm module."""
     if not _fusable(bn, x):
@@ -167,7 +172,7 @@ def bn_act(bn, x, relu=False, residual=None, post=False):
     sync = isinstance(bn, nn.SyncBatchNorm) and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     # num_batches_tracked is bumped inside the finalize kernel (95 one-element add kernels per step otherwise)
     return _BNAct.apply(x, bn.weight, bn.bias, residual, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu, sync, post,
-                        bn.num_batches_tracked)
+                        bn.num_batches_tracked, sums)
 
 
 # ---- torchvision ResNet blocks: same modules / parameters, forward routed through bn_act -----------------------------

@@ -337,14 +337,15 @@ def c16c16_conv(inp, weight, mode, passes):
     return out
 
 
-def c16c16_conv_tc(inp, weight, mode, passes, flags=0):
-    """Same contract as c16c16_conv on tcgen05 / TMEM (csrc/conv3d_c16.cu, namespace tc)."""
+def c16c16_conv_tc(inp, weight, mode, passes, flags=0, bn_sums=None):
+    """Same contract as c16c16_conv on tcgen05 / TMEM (csrc/conv3d_c16.cu, namespace tc).  `bn_sums` (zeroed fp64 [>= 32]):
+    the epilogue accumulates the output's per-channel sum and sum of squares into it (fused BatchNorm statistics)."""
     B, C, D, H, W = inp.shape
     assert C == 16 and tuple(weight.shape) == (16, 16, 3, 3, 3), (inp.shape, weight.shape)
     inp = _f32(inp).contiguous(memory_format=torch.channels_last_3d)
     w = _f32(weight).contiguous()
     out = torch.empty_like(inp)
-    rc = _lib.lib().mvd_conv3d_c16c16_tc(_p(inp), _p(w), _p(out), B, D, H, W, mode, passes, flags, _stream())
+    rc = _lib.lib().mvd_conv3d_c16c16_tc(_p(inp), _p(w), _p(out), _p(bn_sums), B, D, H, W, mode, passes, flags, _stream())
     _lib.check(rc, "mvd_conv3d_c16c16_tc")
     launch_counter["n"] += 1
     return out
@@ -382,24 +383,36 @@ def c16c16_wgrad_tc(gy, x):
 
 class _Conv3dC16C16(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, passes):
-        y = c16c16_conv_tc(x, weight, 0, passes)                                # tcgen05 / TMEM implicit GEMM
+    def forward(ctx, x, weight, passes, want_stats):
+        sums = torch.zeros(33, device=x.device, dtype=torch.float64) if want_stats else None   # [sum, sum sq, BN arrival counter]
+        y = c16c16_conv_tc(x, weight, 0, passes, bn_sums=sums)                  # tcgen05 / TMEM implicit GEMM
+        if want_stats:
+            launch_counter["n"] += 1                                            # the zero fill
         ctx.save_for_backward(x.contiguous(memory_format=torch.channels_last_3d), weight)
-        return y
+        if sums is None:
+            sums = y.new_empty(0, dtype=torch.float64)
+        ctx.mark_non_differentiable(sums)
+        return y, sums
 
     @staticmethod
-    def backward(ctx, gy):
+    def backward(ctx, gy, _gsums):
         x, w = ctx.saved_tensors
         gx = c16c16_conv_tc(gy, w, 1, 1) if ctx.needs_input_grad[0] else None   # single-pass TF32 data gradient (tcgen05)
         gw = c16c16_wgrad_tc(gy, x) if ctx.needs_input_grad[1] else None        # single-pass TF32 weight gradient (tcgen05)
-        return gx, gw, None
+        return gx, gw, None, None
 
 
 def conv3d_c16_to_16(x, weight, passes=3):
     """Conv3d(16 -> 16, k=3, stride 1, padding 1, no bias) on a channels-last-3d volume, all three passes hand-written:
     tcgen05/TMEM implicit GEMM forward (3xTF32 split with passes=3, plain TF32 with passes=1), TF32 data gradient and
     TF32 weight gradient (MN-major operands); `c16c16_wgrad` is the exact-fp32 FFMA2 weight gradient.  Reference: reg3d.conv0.conv, movedepth/networks/resnet_encoder.py:178, 231."""
-    return _Conv3dC16C16.apply(x, weight, passes)
+    return _Conv3dC16C16.apply(x, weight, passes, False)[0]
+
+
+def conv3d_c16_to_16_with_stats(x, weight, passes=3):
+    """conv3d_c16_to_16 whose epilogue also accumulates the BatchNorm statistics of its output: returns (y, sums) with
+    sums = fp64 [sum y (16), sum y^2 (16), 0] ready for `norm.bn_act(..., sums=sums)` (no separate statistics pass)."""
+    return _Conv3dC16C16.apply(x, weight, passes, True)
 
 
 # ------------------------------------------------------------------------------------- Adam
