@@ -213,6 +213,14 @@ int mvd_decoder_prep_bwd(const float* gxp, const float* z, const float* bias, fl
                          int B, int h, int w, int C1, int C2, int up, int act, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * ResNet stem max-pool: MaxPool2d(kernel 3, stride 2, padding 1) on channels-last activations (torchvision resnet,
+ * used by ResnetEncoder.forward, movedepth/networks/resnet_encoder.py:113).  x [B,H,W,C] -> y [B,Ho,Wo,C],
+ * Ho = (H-1)/2+1; idx [B,Ho,Wo,C] bytes = window position (ky*3+kx) of the first maximum; bwd: gx [B,H,W,C] OVERWRITTEN.
+ * ------------------------------------------------------------------------------------- */
+int mvd_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* idx, int B, int H, int W, int C, void* stream);
+int mvd_maxpool3x3s2_bwd(const float* gy, const unsigned char* idx, float* gx, int B, int H, int W, int C, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Fused multi-tensor Adam on a flat fp32 arena (torch.optim.Adam semantics, no amsgrad, no
  * weight decay; replaces optimizer.step() movedepth/trainer.py:137-141, 272).
  *   step_size = lr / (1 - beta1^t);  bias2 = sqrt(1 - beta2^t)

@@ -51,6 +51,8 @@ SIGNATURES = {
     "mvd_decoder_prep_bwd": ([_P] * 6 + [_I] * 7 + [_P], _I),
     "mvd_gather_chunk": ([], _I),
     "mvd_gather_segments": ([_P, _P, _I, _P, _P], _I),
+    "mvd_maxpool3x3s2_fwd": ([_P] * 3 + [_I] * 4 + [_P], _I),
+    "mvd_maxpool3x3s2_bwd": ([_P] * 3 + [_I] * 4 + [_P], _I),
     "mvd_split_tf32": ([_P, _P, _LL, _I, _I, _P], _I),
     "mvd_conv3d_c16o1_fwd": ([_P] * 3 + [_I] * 4 + [_P], _I),
     "mvd_conv3d_c16o1_dgrad": ([_P] * 3 + [_I] * 4 + [_P], _I),

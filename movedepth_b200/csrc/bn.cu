@@ -241,6 +241,16 @@ static int grid_for(long long M, int C) {
     return static_cast<int>(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
 }
 
+// Reductions end with 2C fp64 atomics per block on the SAME 2C addresses: with one block per 256/q rows a mid-sized tensor
+// (e.g. [6,64,48,160]) launched 1184 blocks of ~2 iterations each and spent its time in 150 k contended atomics.  Give every
+// thread >= 16 rows (the full-resolution volumes still fill 8 blocks per SM).
+static int reduce_grid_for(long long M, int C) {
+    const int rows_per_iter = THREADS / (C >> 2);
+    const long long blocks = (M + 16LL * rows_per_iter - 1) / (16LL * rows_per_iter);
+    const long long cap = static_cast<long long>(sm_count()) * 8;
+    return static_cast<int>(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
+}
+
 static int check(long long M, int C) {
     MVD_REQUIRE(M > 0 && C >= 4 && C <= 1024 && (C & (C - 1)) == 0, "BatchNorm kernels need C a power of two in [4,1024] (got M=%lld C=%d)", M, C);
     return 0;
@@ -267,7 +277,7 @@ int mvd_bn_stats(const float* x, long long M, int C, double* sums, const unsigne
     cudaStream_t st = mvd::as_stream(stream);
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C + 1), st);
     if (e != cudaSuccess) return mvd::fail(static_cast<int>(e), "bn_stats memset: %s", cudaGetErrorString(e));
-    bn_stats_kernel<<<grid_for(M, C), THREADS, 0, st>>>(x, M, C, sums, mvd::PeerArgs{peers, rank, world, nmax});
+    bn_stats_kernel<<<reduce_grid_for(M, C), THREADS, 0, st>>>(x, M, C, sums, mvd::PeerArgs{peers, rank, world, nmax});
     return mvd::check_launch("bn_stats");
 }
 
@@ -298,7 +308,7 @@ int mvd_bn_bwd_reduce(const float* gy, const float* x, const float* y, const flo
     cudaStream_t st = mvd::as_stream(stream);
     cudaError_t e = cudaMemsetAsync(sums2, 0, sizeof(double) * (2 * C + 1), st);
     if (e != cudaSuccess) return mvd::fail(static_cast<int>(e), "bn_bwd_reduce memset: %s", cudaGetErrorString(e));
-    bn_bwd_reduce_kernel<<<grid_for(M, C), THREADS, 0, st>>>(gy, x, y, stats, sums2, local_sums2, M, C, relu,
+    bn_bwd_reduce_kernel<<<reduce_grid_for(M, C), THREADS, 0, st>>>(gy, x, y, stats, sums2, local_sums2, M, C, relu,
                                                              mvd::PeerArgs{peers, rank, world, nmax});
     return mvd::check_launch("bn_bwd_reduce");
 }

@@ -327,3 +327,100 @@ int mvd_masked_smooth_l1_bwd(const float* gloss, const float* a, const float* b,
 }
 
 }
+
+// ------------------------------------------------------------------------------------------------ ResNet stem max-pool
+// MaxPool2d(kernel 3, stride 2, padding 1) of the ResNet stem (torchvision resnet; movedepth/networks/resnet_encoder.py:113)
+// on channels-last activations: forward keeps the window position of the maximum (first maximum in scan order, like ATen),
+// backward is a gather over the <= 4 windows that contain an input pixel.  ATen's NHWC kernels need 130 + 200 us for the
+// 47 MB stem activation; these are plain float4 streams.
+namespace mvd {
+namespace glue {
+
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(const float4* __restrict__ x, float4* __restrict__ y, uchar4* __restrict__ idx, int B, int H, int W, int C4, int Ho, int Wo) {
+    const long long total = static_cast<long long>(B) * Ho * Wo * C4;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C4);
+        long long r = i / C4;
+        const int ox = static_cast<int>(r % Wo);
+        r /= Wo;
+        const int oy = static_cast<int>(r % Ho), b = static_cast<int>(r / Ho);
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        uchar4 k = make_uchar4(0, 0, 0, 0);
+        bool first = true;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int iy = 2 * oy - 1 + ky;
+            if (iy < 0 || iy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int ix = 2 * ox - 1 + kx;
+                if (ix < 0 || ix >= W) continue;
+                const float4 v = __ldg(x + ((static_cast<long long>(b) * H + iy) * W + ix) * C4 + c);
+                const unsigned char t = static_cast<unsigned char>(ky * 3 + kx);
+                if (first || v.x > m.x || v.x != v.x) { m.x = v.x; k.x = t; }
+                if (first || v.y > m.y || v.y != v.y) { m.y = v.y; k.y = t; }
+                if (first || v.z > m.z || v.z != v.z) { m.z = v.z; k.z = t; }
+                if (first || v.w > m.w || v.w != v.w) { m.w = v.w; k.w = t; }
+                first = false;
+            }
+        }
+        y[i] = m;
+        idx[i] = k;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const float4* __restrict__ gy, const uchar4* __restrict__ idx, float4* __restrict__ gx, int B, int H, int W, int C4,
+                   int Ho, int Wo) {
+    const long long total = static_cast<long long>(B) * H * W * C4;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C4);
+        long long r = i / C4;
+        const int ix = static_cast<int>(r % W);
+        r /= W;
+        const int iy = static_cast<int>(r % H), b = static_cast<int>(r / H);
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int oy = iy / 2; oy <= (iy + 1) / 2 && oy < Ho; ++oy) {           // windows with 2*oy-1 <= iy <= 2*oy+1
+            const int ky = iy - (2 * oy - 1);
+            for (int ox = ix / 2; ox <= (ix + 1) / 2 && ox < Wo; ++ox) {
+                const unsigned char t = static_cast<unsigned char>(ky * 3 + (ix - (2 * ox - 1)));
+                const long long o = ((static_cast<long long>(b) * Ho + oy) * Wo + ox) * C4 + c;
+                const uchar4 k = idx[o];
+                const float4 v = __ldg(gy + o);
+                if (k.x == t) g.x += v.x;
+                if (k.y == t) g.y += v.y;
+                if (k.z == t) g.z += v.z;
+                if (k.w == t) g.w += v.w;
+            }
+        }
+        gx[i] = g;
+    }
+}
+
+}  // namespace glue
+}  // namespace mvd
+
+extern "C" {
+
+int mvd_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* idx, int B, int H, int W, int C, void* stream) {
+    MVD_REQUIRE(x && y && idx && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "bad argument (C must be a multiple of 4)");
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const long long total = static_cast<long long>(B) * Ho * Wo * (C / 4);
+    glue::maxpool_fwd_kernel<<<glue::blocks_for(total, 256, 8), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<float4*>(y), reinterpret_cast<uchar4*>(idx), B, H, W, C / 4, Ho, Wo);
+    return check_launch("maxpool3x3s2_fwd");
+}
+
+int mvd_maxpool3x3s2_bwd(const float* gy, const unsigned char* idx, float* gx, int B, int H, int W, int C, void* stream) {
+    MVD_REQUIRE(gy && gx && idx && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0, "bad argument (C must be a multiple of 4)");
+    const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+    const long long total = static_cast<long long>(B) * H * W * (C / 4);
+    glue::maxpool_bwd_kernel<<<glue::blocks_for(total, 256, 8), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(gy), reinterpret_cast<const uchar4*>(idx), reinterpret_cast<float4*>(gx), B, H, W, C / 4, Ho, Wo);
+    return check_launch("maxpool3x3s2_bwd");
+}
+
+}

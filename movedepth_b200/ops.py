@@ -688,3 +688,36 @@ def conv2d_small(x, weight, k, stride):
     """Exact-fp32 direct convolution (zero padding k//2, no bias) for the skinny FPN4 / UncertNet layers; x [B,cin,H,W]
     (channels-last storage), weight [cout,cin,k,k].  Reference: movedepth/networks/resnet_encoder.py:325-341, 453-475."""
     return _Conv2dSmall.apply(x, weight, int(k), int(stride))
+
+
+# ------------------------------------------------------------------------------------- ResNet stem max-pool
+class _MaxPool3x3S2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        B, C, H, W = x.shape
+        x = _nhwc(x)
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = torch.empty((B, C, Ho, Wo), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
+        idx = torch.empty((B, Ho, Wo, C), device=x.device, dtype=torch.uint8)
+        rc = _lib.lib().mvd_maxpool3x3s2_fwd(_p(x), _p(y), _p(idx), B, H, W, C, _stream())
+        _lib.check(rc, "mvd_maxpool3x3s2_fwd")
+        launch_counter["n"] += 1
+        ctx.save_for_backward(idx)
+        ctx.meta = (B, C, H, W)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        idx, = ctx.saved_tensors
+        B, C, H, W = ctx.meta
+        gy = _nhwc(gy)
+        gx = torch.empty((B, C, H, W), device=gy.device, dtype=torch.float32, memory_format=torch.channels_last)
+        rc = _lib.lib().mvd_maxpool3x3s2_bwd(_p(gy), _p(idx), _p(gx), B, H, W, C, _stream())
+        _lib.check(rc, "mvd_maxpool3x3s2_bwd")
+        launch_counter["n"] += 1
+        return gx
+
+
+def maxpool3x3s2(x):
+    """MaxPool2d(3, stride 2, padding 1) of the ResNet stem on a channels-last activation (C % 4 == 0)."""
+    return _MaxPool3x3S2.apply(x)

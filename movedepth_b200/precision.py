@@ -24,6 +24,15 @@ import torch
 import torch.nn as nn
 
 _policy = {"mode": "fp32", "split_backward": False}
+conv_recorder = None     # bench.py's step model: when a list, code paths that bypass nn.Module.__call__ of a conv append
+                         # (weight shape, input shape, output shape, transposed) here so that every convolution is counted
+
+
+def record_conv(weight, x, y, transposed=False):
+    if conv_recorder is not None:
+        conv_recorder.append((tuple(weight.shape), tuple(x.shape), tuple(y.shape), bool(transposed)))
+
+
 small_direct = True      # skinny 2-D layers (<= 16 channels) on the exact-fp32 direct kernels of csrc/conv2d_small.cu
 
 
@@ -161,10 +170,13 @@ def prepared_conv(xp, x3, weight):
     """3x3 (or any) stride-1 convolution, no padding, no bias, of a pre-padded channels-last input following the
     precision policy; `x3` is the pre-split operand the DepthDecoder glue kernel wrote (used under 3xtf32 only)."""
     if _policy["mode"] == "3xtf32" and not _policy["split_backward"] and x3.numel():
-        return _PreparedConv.apply(xp, x3, weight)
-    if _policy["mode"] == "3xtf32":
-        return _SplitConv.apply(xp, weight, (1, 1), (0, 0), (0, 0), False)
-    return torch.nn.functional.conv2d(xp, weight)
+        y = _PreparedConv.apply(xp, x3, weight)
+    elif _policy["mode"] == "3xtf32":
+        y = _SplitConv.apply(xp, weight, (1, 1), (0, 0), (0, 0), False)
+    else:
+        y = torch.nn.functional.conv2d(xp, weight)
+    record_conv(weight, xp, y)
+    return y
 
 
 def _tup(v, n):

@@ -847,7 +847,8 @@ def test_conv0_epilogue_accumulates_the_batchnorm_statistics(ops):
     yd = y.double()
     torch.testing.assert_close(sums[:16], yd.sum((0, 2, 3, 4)), rtol=1e-5, atol=1e-4)
     torch.testing.assert_close(sums[16:32], (yd * yd).sum((0, 2, 3, 4)), rtol=1e-5, atol=1e-4)
-    assert torch.equal(y, ops.conv3d_c16_to_16(x, w, 3))
+    # (not bitwise: the taps are issued by four warps into one accumulator, the hardware's accumulation order may differ)
+    torch.testing.assert_close(y, ops.conv3d_c16_to_16(x, w, 3), atol=1e-5, rtol=1e-5)
     blocks = []
     for policy in ("3xtf32", "fp32"):                    # fused statistics under the default policy, separate kernel otherwise
         PR.set_policy(policy)
@@ -861,3 +862,21 @@ def test_conv0_epilogue_accumulates_the_batchnorm_statistics(ops):
     torch.testing.assert_close(y0, y1, atol=2e-5, rtol=1e-4)
     torch.testing.assert_close(b0.bn.running_var, b1.bn.running_var, atol=1e-6, rtol=1e-5)
     torch.testing.assert_close(b0.bn.running_mean, b1.bn.running_mean, atol=1e-6, rtol=1e-5)
+
+
+@pytest.mark.parametrize("shape", [(2, 64, 24, 40), (1, 8, 7, 9), (2, 16, 1, 5)], ids=["even", "odd", "one-row"])
+def test_maxpool3x3s2_matches_torch(ops, shape):
+    """ResNet stem MaxPool2d(3, 2, 1): forward values and the gradient routed to the (first) maximum of every window."""
+    import torch.nn.functional as F
+    gen = torch.Generator().manual_seed(53)
+    x = torch.randn(shape, generator=gen)
+    x[0, :, 0, :3] = 1.5                                   # ties: the first maximum in scan order takes the gradient
+    xo = x.clone().requires_grad_(True)
+    yo = F.max_pool2d(xo, 3, 2, 1)
+    gy = torch.randn(yo.shape, generator=gen)
+    (yo * gy).sum().backward()
+    xg = g(x).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = ops.maxpool3x3s2(xg)
+    (y * g(gy)).sum().backward()
+    assert torch.equal(y.detach().cpu(), yo.detach())
+    torch.testing.assert_close(xg.grad.cpu(), xo.grad, atol=1e-6, rtol=1e-6)
