@@ -1,16 +1,16 @@
-// Small all-reduce over NVLink peer memory for the SyncBatchNorm statistics: the 2C fp64 sums of one BatchNorm pass
-// are exchanged by ONE single-CTA kernel per rank -- every rank stores its vector into its slot of every peer's
-// symmetric buffer (remote st.global over NVLink/NVSwitch), raises a per-peer epoch flag (st.release.sys), spins on the
-// flags the peers raise in its own buffer (ld.acquire.sys) and adds the slots in rank order (bitwise identical result on
-// every rank).  190 of these per training step replace 190 NCCL calls (launch + protocol latency ~30 us each at 8
-// GPUs); being plain kernels they live inside the step's CUDA graph.
+// Small all-reduce over NVLink peer memory for the SyncBatchNorm statistics: the 2C fp64 sums of one BatchNorm pass are
+// exchanged by ONE thread block per rank -- every rank stores its vector into its entries of every peer's symmetric buffer
+// (remote st.volatile over NVLink/NVSwitch), each double as two 8-byte words tagged with the call's epoch; the receiver
+// polls the words of its own buffer until the tags match and adds the contributions in rank order (bitwise identical result
+// on every rank).  No fence, no separate flag (NCCL's LL idea).  190 of these per training step replace 190 NCCL calls
+// (launch + protocol latency ~25-30 us each); inside the BatchNorm reduction kernels (csrc/bn.cu) they are not even a
+// launch of their own, and being plain kernels they live inside the step's CUDA graph.
 //
 // Symmetric buffer layout (same on every rank; allocated by the caller, zero-initialised):
-//   [0, 8)                       epoch counter of this rank (local)
-//   [8, 16)                      time-out marker: set to the epoch at which a peer's flag did not arrive within ~4 s
-//                                (the wait is bounded so that a dead or never-launched peer cannot hang the GPU)
-//   [64, 64 + 8*world)           flags: flag[p] = last epoch rank p has published into this buffer
-//   [4096, ...)                  data [2 slots][world][nmax] doubles      (slot = epoch & 1)
+//   [0, 8)       epoch counter of this rank (local; the 32-bit tag of a call is its low word, never 0)
+//   [8, 16)      time-out marker: set to the epoch at which a peer's data did not arrive within ~4 s (the wait is bounded
+//                so that a dead or never-launched peer cannot hang the GPU)
+//   [4096, ...)  entries [2 slots = epoch parity][world][nmax] x 16 B = {low half, tag, high half, tag}
 #include "peer.cuh"
 #include "../../include/movedepth_b200.h"
 
@@ -27,7 +27,7 @@ extern "C" {
 
 long long mvd_peer_allreduce_buffer_bytes(int world, int nmax) {
     if (world <= 0 || nmax <= 0) return 0;
-    return static_cast<long long>(mvd::PEER_HEADER) + 2ll * world * nmax * static_cast<long long>(sizeof(double));
+    return static_cast<long long>(mvd::PEER_HEADER) + 2ll * world * nmax * mvd::PEER_ENTRY;
 }
 
 int mvd_peer_allreduce_f64(const double* local, double* out, int n, const unsigned long long* peers, int rank, int world, int nmax,

@@ -7,6 +7,7 @@
 namespace mvd {
 
 constexpr int PEER_HEADER = 4096;
+constexpr int PEER_ENTRY = 16;                            // bytes per double in flight: {low, tag, high, tag}
 constexpr long long PEER_SPIN_LIMIT = 8000000000ll;       // SM clocks (~4 s at 1.97 GHz)
 
 struct PeerArgs {
@@ -28,7 +29,18 @@ __device__ __forceinline__ double ld_volatile_f64(const double* p) {
     return v;
 }
 
+__device__ __forceinline__ void st_volatile_v4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void ld_volatile_v4(const void* p, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "l"(p) : "memory");
+}
+
 // out[i] = sum over ranks of local[i], i < n (out may alias local).  Called by every thread of one block.
+// Low-latency protocol (flag-in-data, as NCCL's LL): every double travels as two 8-byte words {low half, epoch},
+// {high half, epoch}; an aligned 8-byte store is one NVLink transaction, so the receiver simply polls each word until its
+// epoch tag matches -- no __threadfence_system() and no separate flag round trip (they cost ~8 of the former 13 us).
+// Entry layout per rank buffer: [2 slots (epoch parity)][world][nmax] x 16 B.
 __device__ __forceinline__ void peer_allreduce_block(const double* local, double* out, int n, const PeerArgs pa) {
     __shared__ unsigned long long s_epoch;
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -40,34 +52,44 @@ __device__ __forceinline__ void peer_allreduce_block(const double* local, double
         *ctr = s_epoch;
     }
     __syncthreads();
-    const unsigned long long epoch = s_epoch;
-    const size_t slot = static_cast<size_t>(epoch & 1ull);
-    // 1. publish: my vector into slot [slot][rank] of every rank's buffer (the local copy included)
-    for (int p = 0; p < pa.world; ++p) {
-        double* dst = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(pa.peers[p]) + PEER_HEADER) +
-                      (slot * pa.world + pa.rank) * pa.nmax;
-        for (int i = tid; i < n; i += nthr) dst[i] = ld_volatile_f64(local + i);
-    }
-    __threadfence_system();
-    __syncthreads();
-    // 2. raise my flag on peer `tid`, then wait for peer `tid`'s flag in my buffer
-    if (tid < pa.world) {
-        st_release_sys(reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(pa.peers[tid]) + 64) + pa.rank, epoch);
-        const unsigned long long* f = reinterpret_cast<const unsigned long long*>(mine + 64) + tid;
-        const long long t0 = clock64();
-        while (ld_acquire_sys(f) < epoch) {
-            if (clock64() - t0 > PEER_SPIN_LIMIT) {
-                reinterpret_cast<unsigned long long*>(mine)[1] = epoch;
-                break;
-            }
+    const uint32_t tag = static_cast<uint32_t>(s_epoch);             // never 0: the buffers start zeroed
+    const size_t slot = static_cast<size_t>(s_epoch & 1ull);
+    // 1. publish my vector into entry [slot][rank] of every OTHER rank's buffer; my own values stay in registers / local
+    for (int i = tid; i < n; i += nthr) {
+        const double v = ld_volatile_f64(local + i);
+        const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(v));
+        const uint32_t lo = static_cast<uint32_t>(bits), hi = static_cast<uint32_t>(bits >> 32);
+        for (int p = 0; p < pa.world; ++p) {
+            if (p == pa.rank) continue;
+            unsigned char* dst = reinterpret_cast<unsigned char*>(pa.peers[p]) + PEER_HEADER +
+                                 ((slot * pa.world + pa.rank) * pa.nmax + i) * 16;
+            st_volatile_v4(dst, lo, tag, hi, tag);
         }
     }
-    __syncthreads();
-    // 3. reduce in rank order (bitwise identical on every rank)
-    const double* src = reinterpret_cast<const double*>(mine + PEER_HEADER) + slot * pa.world * pa.nmax;
+    // 2. gather: poll the other ranks' entries in my buffer until their tags match, add in rank order (bitwise identical
+    //    on every rank: the own contribution enters at its rank position)
+    const long long t0 = clock64();
+    bool timed_out = false;
     for (int i = tid; i < n; i += nthr) {
+        const double own = ld_volatile_f64(local + i);
         double s = 0.0;
-        for (int p = 0; p < pa.world; ++p) s += ld_volatile_f64(src + static_cast<size_t>(p) * pa.nmax + i);
+        for (int p = 0; p < pa.world; ++p) {
+            if (p == pa.rank) {
+                s += own;
+                continue;
+            }
+            const unsigned char* src = mine + PEER_HEADER + ((slot * pa.world + p) * pa.nmax + i) * 16;
+            uint32_t lo, t1, hi, t2;
+            ld_volatile_v4(src, lo, t1, hi, t2);
+            while ((t1 != tag || t2 != tag) && !timed_out) {
+                if (clock64() - t0 > PEER_SPIN_LIMIT) {
+                    timed_out = true;
+                    reinterpret_cast<unsigned long long*>(mine)[1] = s_epoch;
+                }
+                ld_volatile_v4(src, lo, t1, hi, t2);
+            }
+            s += __longlong_as_double(static_cast<long long>((static_cast<unsigned long long>(hi) << 32) | lo));
+        }
         out[i] = s;
     }
 }
