@@ -343,6 +343,9 @@ int mvd_bn_bwd_apply(const float* gy, const float* x, const float* y, const floa
  * buffer (mvd_peer_allreduce_buffer_bytes(world, nmax) bytes, zero-initialised once) as mapped
  * on this GPU for every rank.  out[i] = sum over ranks of local[i], added in rank order (bitwise
  * identical on all ranks).  Collective: every rank must launch it the same number of times.
+ * Protocol: flag-in-data (every double = two 8-byte words {half, epoch tag} stored into the peers'
+ * buffers, the receiver polls its own buffer until the tags match); waits are bounded (~4 s of SM
+ * clocks: a time-out writes the epoch to byte 8 of the rank's buffer instead of hanging the GPU).
  * ------------------------------------------------------------------------------------- */
 long long mvd_peer_allreduce_buffer_bytes(int world, int nmax);
 int mvd_peer_allreduce_f64(const double* local, double* out, int n, const unsigned long long* peers,
