@@ -37,7 +37,7 @@ class PeerExchange:
     (csrc/peer.cu) instead of NCCL.  One symmetric buffer per process (torch symmetric memory: CUDA VMM
     allocations mapped into every rank of the node)."""
     NMAX = 2048
-    _inst = None
+    _inst = {}               # one exchange buffer (and epoch counter) per channel: concurrent streams must not share one
     _failed = False
 
     def __init__(self, device):
@@ -52,14 +52,14 @@ class PeerExchange:
         dist.barrier()
 
     @classmethod
-    def get(cls, device):
-        if cls._inst is None and not cls._failed:
+    def get(cls, device, chan=0):
+        if chan not in cls._inst and not cls._failed:
             try:
-                cls._inst = cls(device)
+                cls._inst[chan] = cls(device)
             except Exception as e:                      # no peer access / symmetric memory: NCCL does the exchange
                 cls._failed = True
                 print("movedepth_b200: peer-memory SyncBN exchange unavailable (%s: %s); using NCCL" % (type(e).__name__, e))
-        return cls._inst
+        return cls._inst.get(chan)
 
     def allreduce_(self, v):
         rc = _lib.lib().mvd_peer_allreduce_f64(_p(v), _p(v), v.numel(), _p(self.ptrs), self.rank, self.world, self.NMAX, _stream())
@@ -68,11 +68,14 @@ class PeerExchange:
 
 
 peer_exchange = True      # SyncBN statistics over NVLink peer memory when available (else NCCL all_reduce)
+channel = 0               # exchange channel of the BatchNorm layers being built right now: the trainer runs its two independent
+                          # autograd graphs on two streams, each with its own exchange buffer (the epochs of one buffer must
+                          # advance in the same order on every rank)
 
 
-def _peer(device, C):
+def _peer(device, C, chan=0):
     """(peers table pointer, rank, world, nmax) for the in-kernel exchange, or None -> NCCL all_reduce after the kernel."""
-    px = PeerExchange.get(device) if (peer_exchange and 2 * C <= PeerExchange.NMAX) else None
+    px = PeerExchange.get(device, chan) if (peer_exchange and 2 * C <= PeerExchange.NMAX) else None
     return px
 
 
@@ -90,7 +93,8 @@ class _BNAct(torch.autograd.Function):
         xc = x.contiguous(memory_format=_fmt(x))
         M = xc.numel() // C
         rc_ = residual.contiguous(memory_format=_fmt(x)) if residual is not None else None
-        px = _peer(x.device, C) if sync else None
+        ctx.channel = channel
+        px = _peer(x.device, C, channel) if sync else None
         precomputed = sums is not None and sums.numel() >= 2 * C       # the producing conv's epilogue already summed its output
         if not precomputed:
             sums = torch.empty(2 * C + 1, device=x.device, dtype=torch.float64)      # [sum x, sum x^2, arrival counter]
@@ -122,7 +126,7 @@ class _BNAct(torch.autograd.Function):
         L = _lib.lib()
         gy = gy.contiguous(memory_format=_fmt(xc))
         sums2 = torch.empty(2 * C + 1, device=xc.device, dtype=torch.float64)
-        px = _peer(xc.device, C) if sync else None
+        px = _peer(xc.device, C, ctx.channel) if sync else None
         local2 = torch.empty(2 * C, device=xc.device, dtype=torch.float64) if px else None
         _lib.check(L.mvd_bn_bwd_reduce(_p(gy), _p(xc), _p(y), _p(stats), _p(sums2), _p(local2), M, C, int(relu),
                                        _p(px.ptrs) if px else _p(None), px.rank if px else 0, px.world if px else 1,

@@ -64,6 +64,8 @@ class MonodepthOptions:
                             "tf32 = PyTorch's default conv policy")
         p.add_argument("--b200_split_backward", action="store_true", help="3xtf32: split dgrad/wgrad as well")
         p.add_argument("--b200_cuda_graph", action="store_true", help="capture the training step in a CUDA graph")
+        p.add_argument("--b200_one_stream", action="store_true",
+                       help="issue the mono/pose graph and the cost-volume graph on ONE stream (default: two concurrent streams)")
         p.add_argument("--b200_synthetic", action="store_true", help="train on synthetic KITTI-shape tensors")
         self.parser = p
 

@@ -19,6 +19,7 @@ files.  What differs is how a step executes:
 
 There is no CPU path: `--no_cuda` raises.
 """
+import contextlib
 import json
 import os
 import time
@@ -30,6 +31,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import networks, ops
+from . import norm as NM
 from . import precision as PR
 from . import photometric as photo
 from .layers import (disp_to_depth, get_smooth_loss, transformation_from_parameters, hypothesis_ratios,
@@ -286,6 +288,8 @@ class Trainer:
         # auto-mask tie-break noise (trainer.py:600,641,698 draw it on the CPU and copy it over): a device generator of this
         # trainer fills static buffers OUTSIDE the captured graph, so eager and graph steps with the same seed see the same
         # noise and a replay never re-uses the noise of the capture
+        self._two_streams = not getattr(o, "b200_one_stream", False)
+        self._mvs_stream = torch.cuda.Stream() if self._two_streams else None
         self.noise_generator = torch.Generator(device=self.device)
         self.noise_generator.manual_seed(torch.initial_seed() + self.rank)
         self._noise_buf = None
@@ -358,35 +362,46 @@ class Trainer:
         # The two graphs share nothing but detached tensors: they are back-propagated separately.
         # torch.autograd.grad hands back the raw gradient tensors (no zero_grad, no per-parameter accumulate kernels); one
         # gather kernel per parameter group writes them into the flat arena the all-reduce and the fused Adam kernel work on.
-        # Order: the mono / pose graph first.  Its arena (27 M parameters, 107 MB) is all-reduced while the much longer
-        # cost-volume backward runs; the cost-volume arena (1.4 M parameters) and the `up` tail of arena 0, whose gradients come
-        # from the cost-volume graph, follow at the end as two small calls.
+        # Data-parallel training: the mono / pose arena (27 M parameters, 107 MB) is all-reduced as soon as its (shorter)
+        # back-propagation is done, overlapping the rest of the cost-volume backward; the cost-volume arena (1.4 M parameters)
+        # and the `up` tail of arena 0, whose gradients come from the cost-volume graph, are two small calls.
         a0, a1 = self.arenas
         p0, p1 = a0.params, a1.params
+        main = torch.cuda.current_stream()
+        side = self._mvs_stream if self._two_streams else None
+        keep = []
+        # cost-volume graph: issued first (host order) on its own stream; the mono / pose graph follows on the main stream,
+        # so the two back-propagations run concurrently on the device
+        if side is not None:
+            side.wait_stream(main)
+        with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+            self._tf32("mvs")
+            g = torch.autograd.grad(losses["_mvs_total"], p1 + p0, allow_unused=True)
+            g1, g0_mvs = g[:len(p1)], g[len(p1):]
+            keep.append(a1.collect(g1, pinned=capturing))
+            keep.append(a0.collect(g0_mvs, pinned=capturing))         # the `up` head: arena 0's tail, nothing else
+            tail = self._arena0_tail(g0_mvs)
+            if multi:
+                dist.all_reduce(a1.grad)
+                if tail < a0.numel:
+                    dist.all_reduce(a0.grad[tail:])
         self._tf32("mono")
         g0 = torch.autograd.grad(losses["_mono_total"], p0, allow_unused=True)
-        keep = [a0.collect(g0, pinned=capturing)]
-        tail = self._arena0_tail(g0)                      # first parameter of arena 0 the mono graph does not reach (`up`)
-        work = dist.all_reduce(a0.grad[:tail], async_op=True) if multi else None
-        self._tf32("mvs")
-        g = torch.autograd.grad(losses["_mvs_total"], p1 + p0, allow_unused=True)
-        g1, g0_mvs = g[:len(p1)], g[len(p1):]
-        assert all(a is None or b is None for a, b in zip(g0, g0_mvs)), "a parameter receives gradients from both graphs"
-        keep.append(a1.collect(g1, pinned=capturing))
-        keep.append(a0.collect(g0_mvs, pinned=capturing))
+        assert all(x is None or y is None for x, y in zip(g0, g0_mvs)), "a parameter receives gradients from both graphs"
+        keep.append(a0.collect(g0, pinned=capturing))
         if multi:
-            dist.all_reduce(a1.grad)
-            if tail < a0.numel:
-                dist.all_reduce(a0.grad[tail:])
-            work.wait()
+            dist.all_reduce(a0.grad[:tail])          # 107 MB: overlaps whatever is left of the cost-volume backward
+        if side is not None:
+            main.wait_stream(side)
         outputs["_keepalive"] = keep
         return outputs, losses
 
-    def _arena0_tail(self, g0):
-        """Offset of the first arena-0 parameter after which the mono graph produced no gradient (the `up` head)."""
+    def _arena0_tail(self, g0_mvs):
+        """Offset of the first arena-0 parameter that gets its gradient from the cost-volume graph (the `up` head sits at
+        the end of the arena); arena 0's numel when there is none."""
         a0 = self.arenas[0]
-        last = max((i for i, g in enumerate(g0) if g is not None), default=-1)
-        return a0.offsets[last + 1] if last + 1 < len(a0.offsets) else a0.numel
+        first = min((i for i, g in enumerate(g0_mvs) if g is not None), default=None)
+        return a0.offsets[first] if first is not None else a0.numel
 
     def _optimizer_step(self):
         self.opt_step += 1
@@ -505,7 +520,13 @@ class Trainer:
     def process_batch(self, inputs, is_train=False, noise=None, mask_xy=None):
         """Forward pass and all losses for one minibatch (movedepth/trainer.py:297-442).
         `noise` (list of [B,1,H,W] N(0,1) tensors) and `mask_xy` (box corner) override the random
-        draws so that parity tests can reproduce the reference bit for bit."""
+        draws so that parity tests can reproduce the reference bit for bit.
+
+        The step is two autograd graphs joined only by detached tensors: the mono / pose graph and the
+        cost-volume graph.  With `--b200_two_streams` (default) they are issued on two CUDA streams -- the matching-feature
+        network starts at once, the cost-volume part waits for the mono prior and the poses -- so that the small kernels of
+        one graph fill the tails of the other and, in data-parallel training, one graph's SyncBatchNorm exchange latency
+        hides behind the other's compute.  Captured in the step's CUDA graph the two streams become parallel branches."""
         o = self.opt
         inputs = {k: (v.to(self.device, non_blocking=True) if torch.is_tensor(v) else v) for k, v in inputs.items()}
         B = inputs[("color_aug", 0, 0)].shape[0]
@@ -513,79 +534,105 @@ class Trainer:
             noise = [self._noise_buf[i] for i in range(self._num_noise_maps())]
         elif is_train or noise is not None:
             noise = self._draw_noise(B, noise)
+        fh, fw = o.height // 3, o.width // 3
+        if not isinstance(mask_xy, str):     # "preset": the caller already wrote the box corner into self._aug_box (graph step)
+            self._set_aug_box(mask_xy)
+
+        main = torch.cuda.current_stream()
+        side = self._mvs_stream if self._two_streams else None
+
+        def on_mvs():
+            return torch.cuda.stream(side) if side is not None else contextlib.nullcontext()
+
+        # ---------------- cost-volume graph, part 1: matching features (independent of the mono / pose graph)
+        if side is not None:
+            side.wait_stream(main)
+        with on_mvs():
+            NM.channel = 1
+            self._tf32("mvs")
+            enc = self.models["mvs_encoder"]
+            cl = torch.channels_last   # NHWC through FPN4: its output is then already the layout K1's TMA boxes read
+            ref_img = inputs[("color_aug", 0, 0)].contiguous(memory_format=cl)
+            ref_feat, ref_ctx = enc(ref_img)
+            src_feats = [enc(inputs[("color_aug", f, 0)].contiguous(memory_format=cl))[0] for f in self.matching_ids[1:]]
+            # masked augmentation (trainer.py:374-376): zero a random box of the reference image
+            ys = torch.arange(o.height, device=self.device).view(1, 1, -1, 1)
+            xs = torch.arange(o.width, device=self.device).view(1, 1, 1, -1)
+            inside = (xs >= self._aug_box[0]) & (xs < self._aug_box[0] + fw) & (ys >= self._aug_box[1]) & (ys < self._aug_box[1] + fh)
+            aug_mask = (~inside).float().expand(B, 3, o.height, o.width)
+            aug_feat, _ = enc((ref_img * aug_mask).contiguous(memory_format=cl))
 
         # ---------------- mono / pose graph
+        NM.channel = 0
         self._tf32("mono")
         outputs = self.predict_poses(inputs)
         poses = torch.stack([inputs[("relative_pose", f)] for f in self.matching_ids[1:]], 1)   # [B,M,4,4]
         ref_cl = inputs[("color_aug", 0, 0)].contiguous(memory_format=torch.channels_last)    # NHWC for cuDNN's tensor-core kernels
         outputs.update(self.models["mono_depth"](self.models["mono_encoder"](ref_cl)))
+        disp_prior = outputs[("disp", o.prior_scale)].detach()
+        _, mono_depth = disp_to_depth(outputs[("disp", 0)].detach(), o.min_depth, o.max_depth)
+        if side is not None:
+            prior_ready = torch.cuda.Event()
+            prior_ready.record(main)
         losses = self.compute_losses(inputs, outputs, is_mvs=False, noise=noise)
 
-        # ---------------- hypotheses around the mono prior (trainer.py:333-346), separable form
-        disp_prior = outputs[("disp", o.prior_scale)].detach()
-        prior = 1.0 / (1.0 / o.max_depth + disp_prior * (1.0 / o.min_depth - 1.0 / o.max_depth))
-        if self.epoch > o.ztrans_start_epc:
-            s = o.depth_bin_fac * o.z_scale * poses[:, 0, 2, 3]
-        else:
-            s = torch.full((B,), float(o.depth_bin_fac), device=self.device)
-        ratio = hypothesis_ratios(o.num_depth_bins, s, self.device, o.schedule_type)          # [B,D]
-        inv_a = 1.0 / (prior[:, 0] * ratio[:, -1].view(B, 1, 1))
-        inv_b = 1.0 / (prior[:, 0] * ratio[:, 0].view(B, 1, 1))
-        outputs["depth_prior"], outputs["hypothesis_ratio"] = prior, ratio
+        # ---------------- cost-volume graph, part 2
+        with on_mvs():
+            if side is not None:
+                side.wait_event(prior_ready)
+            NM.channel = 1
+            self._tf32("mvs")
+            # hypotheses around the mono prior (trainer.py:333-346), separable form
+            prior = 1.0 / (1.0 / o.max_depth + disp_prior * (1.0 / o.min_depth - 1.0 / o.max_depth))
+            if self.epoch > o.ztrans_start_epc:
+                s = o.depth_bin_fac * o.z_scale * poses[:, 0, 2, 3]
+            else:
+                s = torch.full((B,), float(o.depth_bin_fac), device=self.device)
+            ratio = hypothesis_ratios(o.num_depth_bins, s, self.device, o.schedule_type)          # [B,D]
+            inv_a = 1.0 / (prior[:, 0] * ratio[:, -1].view(B, 1, 1))
+            inv_b = 1.0 / (prior[:, 0] * ratio[:, 0].view(B, 1, 1))
+            outputs["depth_prior"], outputs["hypothesis_ratio"] = prior, ratio
 
-        # ---------------- cost-volume graph
-        self._tf32("mvs")
-        enc = self.models["mvs_encoder"]
-        cl = torch.channels_last       # NHWC through FPN4: its output is then already the layout K1's TMA boxes read
-        ref_img = inputs[("color_aug", 0, 0)].contiguous(memory_format=cl)
-        ref_feat, ref_ctx = enc(ref_img)
-        src_feats = [enc(inputs[("color_aug", f, 0)].contiguous(memory_format=cl))[0] for f in self.matching_ids[1:]]
-        logits, vol = self._volume_logits(ref_feat, src_feats, inputs, prior, ratio, poses)
-        cost_prob, ent, depth_mvs = ops.regress_depth(logits, inv_a, inv_b, o.norm_radius, want_prob=bool(o.mask_mvs_conf))
-        trust = self.models["mask_cnn"](ent)
-        outputs["cost_volume"], outputs["cost_logits"], outputs["depth_mvs_lowres"] = vol, logits, depth_mvs
+            logits, vol = self._volume_logits(ref_feat, src_feats, inputs, prior, ratio, poses)
+            cost_prob, ent, depth_mvs = ops.regress_depth(logits, inv_a, inv_b, o.norm_radius, want_prob=bool(o.mask_mvs_conf))
+            trust = self.models["mask_cnn"](ent)
+            outputs["cost_volume"], outputs["cost_logits"], outputs["depth_mvs_lowres"] = vol, logits, depth_mvs
 
-        # masked-augmentation consistency (trainer.py:374-403): zero a random box of the reference image
-        fh, fw = o.height // 3, o.width // 3
-        if not isinstance(mask_xy, str):     # "preset": the caller already wrote the box corner into self._aug_box (graph step)
-            self._set_aug_box(mask_xy)
-        ys = torch.arange(o.height, device=self.device).view(1, 1, -1, 1)
-        xs = torch.arange(o.width, device=self.device).view(1, 1, 1, -1)
-        inside = (xs >= self._aug_box[0]) & (xs < self._aug_box[0] + fw) & (ys >= self._aug_box[1]) & (ys < self._aug_box[1] + fh)
-        aug_mask = (~inside).float().expand(B, 3, o.height, o.width)
-        aug_feat, _ = enc((ref_img * aug_mask).contiguous(memory_format=cl))
-        logits_aug, _ = self._volume_logits(aug_feat, src_feats, inputs, prior, ratio, poses)
-        _, _, depth_aug = ops.regress_depth(logits_aug, inv_a, inv_b, o.norm_radius)
-        # mean smooth-L1 over the pixels the resized box mask selects, one kernel; the weight is applied twice in the
-        # reference (trainer.py:399-400)
-        masked = ops.masked_smooth_l1(depth_aug, depth_mvs, self._aug_box, o.height, o.width, fh, fw, o.mask_lw * o.mask_lw)
-        outputs["masked_depth"], outputs["masked_aug"] = depth_aug, aug_mask
+            # masked-augmentation consistency (trainer.py:377-403)
+            logits_aug, _ = self._volume_logits(aug_feat, src_feats, inputs, prior, ratio, poses)
+            _, _, depth_aug = ops.regress_depth(logits_aug, inv_a, inv_b, o.norm_radius)
+            # mean smooth-L1 over the pixels the resized box mask selects, one kernel; the weight is applied twice in the
+            # reference (trainer.py:399-400)
+            masked = ops.masked_smooth_l1(depth_aug, depth_mvs, self._aug_box, o.height, o.width, fh, fw, o.mask_lw * o.mask_lw)
+            outputs["masked_depth"], outputs["masked_aug"] = depth_aug, aug_mask
 
-        # upsample + fuse (trainer.py:405-416)
-        if o.convex_up:
-            depth_up = self.models["up"](depth_mvs, ref_ctx)
-        else:
-            depth_up = F.interpolate(depth_mvs.unsqueeze(1), [o.height, o.width], mode="bilinear", align_corners=True)[:, 0]
-        outputs["depth_mvs"] = depth_up
-        _, mono_depth = disp_to_depth(outputs[("disp", 0)], o.min_depth, o.max_depth)
-        trust = F.interpolate(trust, [o.height, o.width], mode="bilinear", align_corners=True)
-        outputs["trust_mono_mask"] = trust
-        outputs["fused_depth"] = (1 - trust) * depth_up.unsqueeze(1).detach() + trust * mono_depth.detach()
-        fuse_loss = self.compute_fuse_losses(inputs, outputs, noise=noise)
-        if o.mask_mvs_conf:                  # trainer.py:419-422: trilinear-upsampled probability peak above photo_conf
-            up = F.interpolate(cost_prob.unsqueeze(1), [o.num_depth_bins, o.height, o.width], mode="trilinear", align_corners=True)
-            outputs["photo_conf_map"] = up.max(2)[0] > o.photo_conf
-        if o.mask_mvs_dist:                  # trainer.py:423-425
-            outputs["dist_mask"] = outputs[("disp", 0)] > o.dist_thres
-        mvs_losses = self.compute_losses(inputs, outputs, is_mvs=True, noise=noise)
+            # upsample + fuse (trainer.py:405-416)
+            if o.convex_up:
+                depth_up = self.models["up"](depth_mvs, ref_ctx)
+            else:
+                depth_up = F.interpolate(depth_mvs.unsqueeze(1), [o.height, o.width], mode="bilinear", align_corners=True)[:, 0]
+            outputs["depth_mvs"] = depth_up
+            trust = F.interpolate(trust, [o.height, o.width], mode="bilinear", align_corners=True)
+            outputs["trust_mono_mask"] = trust
+            outputs["fused_depth"] = (1 - trust) * depth_up.unsqueeze(1).detach() + trust * mono_depth
+            fuse_loss = self.compute_fuse_losses(inputs, outputs, noise=noise)
+            if o.mask_mvs_conf:                  # trainer.py:419-422: trilinear-upsampled probability peak above photo_conf
+                up = F.interpolate(cost_prob.unsqueeze(1), [o.num_depth_bins, o.height, o.width], mode="trilinear", align_corners=True)
+                outputs["photo_conf_map"] = up.max(2)[0] > o.photo_conf
+            if o.mask_mvs_dist:                  # trainer.py:423-425
+                outputs["dist_mask"] = outputs[("disp", 0)] > o.dist_thres
+            mvs_losses = self.compute_losses(inputs, outputs, is_mvs=True, noise=noise)
+            mvs_total = mvs_losses["loss"] + masked + fuse_loss
+        NM.channel = 0
+        if side is not None:
+            main.wait_stream(side)
 
         # ---------------- totals (trainer.py:429-440): loss = mvs + (mono + masked) + fuse
         losses["masked_loss"] = masked
         losses["fuse_reproj_loss"] = fuse_loss
         losses.update({k: v for k, v in mvs_losses.items() if k != "loss"})
         losses["_mono_total"] = losses["loss"]
-        losses["_mvs_total"] = mvs_losses["loss"] + masked + fuse_loss
+        losses["_mvs_total"] = mvs_total
         losses["loss"] = losses["_mono_total"] + losses["_mvs_total"]
         return outputs, losses
 
