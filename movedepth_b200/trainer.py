@@ -540,6 +540,15 @@ class Trainer:
 
         main = torch.cuda.current_stream()
         side = self._mvs_stream if self._two_streams else None
+        # Cross-stream discipline: a tensor that the OTHER stream's graph saves for its backward must not be allocated on this
+        # stream -- when autograd releases it the caching allocator would hand the block to the next allocation of its own
+        # stream while the other stream's kernel may still be pending (inside a captured graph: a genuine race between the two
+        # branches).  So everything the cost-volume graph keeps is either allocated on its stream (copies below) or outlives
+        # the step (`outputs`, static inputs); freshly staged input copies are marked as used by both streams.
+        if side is not None:
+            for v in inputs.values():
+                if torch.is_tensor(v) and v.is_cuda:
+                    v.record_stream(side)
 
         def on_mvs():
             return torch.cuda.stream(side) if side is not None else contextlib.nullcontext()
@@ -569,8 +578,8 @@ class Trainer:
         poses = torch.stack([inputs[("relative_pose", f)] for f in self.matching_ids[1:]], 1)   # [B,M,4,4]
         ref_cl = inputs[("color_aug", 0, 0)].contiguous(memory_format=torch.channels_last)    # NHWC for cuDNN's tensor-core kernels
         outputs.update(self.models["mono_depth"](self.models["mono_encoder"](ref_cl)))
-        disp_prior = outputs[("disp", o.prior_scale)].detach()
-        _, mono_depth = disp_to_depth(outputs[("disp", 0)].detach(), o.min_depth, o.max_depth)
+        disp_prior = outputs[("disp", o.prior_scale)].detach()          # views of tensors `outputs` keeps alive
+        disp_full = outputs[("disp", 0)].detach()
         if side is not None:
             prior_ready = torch.cuda.Event()
             prior_ready.record(main)
@@ -582,6 +591,8 @@ class Trainer:
                 side.wait_event(prior_ready)
             NM.channel = 1
             self._tf32("mvs")
+            poses = poses.clone()                                       # this stream's own copies (see above)
+            _, mono_depth = disp_to_depth(disp_full, o.min_depth, o.max_depth)
             # hypotheses around the mono prior (trainer.py:333-346), separable form
             prior = 1.0 / (1.0 / o.max_depth + disp_prior * (1.0 / o.min_depth - 1.0 / o.max_depth))
             if self.epoch > o.ztrans_start_epc:
