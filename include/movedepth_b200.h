@@ -221,6 +221,31 @@ int mvd_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* idx, int B, in
 int mvd_maxpool3x3s2_bwd(const float* gy, const unsigned char* idx, float* gx, int B, int H, int W, int C, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Device-side image pre-processing (csrc/datapipe.cu): what MonoDataset.preprocess does on the CPU through
+ * Pillow / torchvision (movedepth/datasets/mono_dataset.py:104-126 pyramid of `transforms.Resize(..., ANTIALIAS)`,
+ * 164/206 flip, 220-223 `transforms.ColorJitter`), on uint8 channels-last images, bit-exact.
+ *   mvd_resample_u8   one pass of Pillow's ImagingResample: src [outer][n_in][inner] -> dst [outer][n_out][inner];
+ *                     bounds [n_out][2] = (first tap, count), coeff [n_out][ksize] = 22-bit fixed-point Lanczos taps
+ *                     (host-computed as Resample.c does); flip (nullable, one byte per image of `outer_per_image`
+ *                     rows): taps are read through the mirrored index (horizontal pass of a flipped image)
+ *   mvd_flip_copy_u8  copy [N,H,W,C] with the optional per-image mirrored x index
+ *   mvd_u8_to_tensor  ToTensor: [N,H,W,3] uint8 -> [N,3,H,W] float, x / 255.0f
+ *   mvd_jitter_blend_u8  in place, mode 0 brightness / 1 contrast / 2 saturation = Image.blend(degenerate, img, factor[n]);
+ *                     sums: N uint64 of scratch (contrast); active (nullable): images with active[n] == 0 are skipped
+ *   mvd_jitter_hue_u8 in place, torchvision adjust_hue: rgb2hsv, h += shift[n] (uint8 wrap), hsv2rgb (Convert.c)
+ * ------------------------------------------------------------------------------------- */
+int mvd_resample_u8(const unsigned char* src, unsigned char* dst, const int* bounds, const int* coeff, int ksize,
+                    long long outer, int n_in, int n_out, int inner, const unsigned char* flip,
+                    long long outer_per_image, void* stream);
+int mvd_flip_copy_u8(const unsigned char* src, unsigned char* dst, int N, int H, int W, int C,
+                     const unsigned char* flip, void* stream);
+int mvd_u8_to_tensor(const unsigned char* src, float* dst, int N, int H, int W, void* stream);
+int mvd_jitter_blend_u8(unsigned char* img, int N, int H, int W, int mode, const float* factor,
+                        unsigned long long* sums, const unsigned char* active, void* stream);
+int mvd_jitter_hue_u8(unsigned char* img, int N, int H, int W, const unsigned char* shift,
+                      const unsigned char* active, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Fused multi-tensor Adam on a flat fp32 arena (torch.optim.Adam semantics, no amsgrad, no
  * weight decay; replaces optimizer.step() movedepth/trainer.py:137-141, 272).
  *   step_size = lr / (1 - beta1^t);  bias2 = sqrt(1 - beta2^t)

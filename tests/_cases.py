@@ -143,6 +143,17 @@ def case_masked(B=2, h=12, w=20, H=48, W=80):
                 boxes=[(0, 0), (17, 9), (W - W // 3 - 1, H - H // 3 - 1), (31, 2)])
 
 
+def case_frames(H=32, W=96, Hn=75, Wn=250, seed=9):
+    """Two synthetic 'decoded' uint8 frames at a native resolution (data pipeline tests), numpy generator."""
+    import numpy as np
+    rng = np.random.default_rng(111)
+    frames = {}
+    for f in (0, -1):
+        walk = np.cumsum(rng.normal(0, 6, (Hn, Wn, 3)), 1) + np.cumsum(rng.normal(0, 4, (Hn, Wn, 3)), 0)
+        frames[f] = np.clip(walk + 128, 0, 255).astype(np.uint8)
+    return dict(H=H, W=W, Hn=Hn, Wn=Wn, seed=seed, frames=frames)
+
+
 # ---------------------------------------------------------------- whole-step cases
 STEP_CASES = {
     "r18_2f": dict(H=64, W=96, D=8, B=2, frame_ids=[0, -1], epoch=0, arch=18),

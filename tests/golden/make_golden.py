@@ -262,13 +262,48 @@ def eval_vectors(rl, rn):
     print("eval_r18.npz:", {k: v.shape for k, v in g.items()}, "tz0", float(g["tz0"]))
 
 
+def datapipe_vectors():
+    """The reference's own MonoDataset.preprocess (movedepth/datasets/mono_dataset.py:104-126) on two synthetic frames:
+    pyramid of PIL LANCZOS resizes + ToTensor, with and without the horizontal flip of `get_color` (kitti_dataset.py) and
+    with `transforms.ColorJitter` seeded through torch's global RNG."""
+    import _cases as C
+    import movedepth.datasets as ds
+    from PIL import Image
+    from torchvision import transforms
+    c = C.case_frames()
+    d = ds.KITTIRAWDataset("/nonexistent", ["2011_09_26/x 0 l"], c["H"], c["W"], [0, -1], 4, is_train=True, img_ext=".png")
+    g = {}
+    for tag, flip, seed in (("plain", False, None), ("flip", True, None), ("jitter", False, c["seed"])):
+        inputs = {}
+        for f in (0, -1):
+            im = Image.fromarray(c["frames"][f], "RGB")
+            inputs[("color", f, -1)] = im.transpose(Image.FLIP_LEFT_RIGHT) if flip else im
+        if seed is None:
+            aug = (lambda x: x)
+        else:
+            torch.manual_seed(seed)
+            aug = transforms.ColorJitter(d.brightness, d.contrast, d.saturation, d.hue)
+        d.preprocess(inputs, aug)
+        for f in (0, -1):
+            for s_ in range(4):
+                g["%s_color_%d_%d" % (tag, f, s_)] = np32(inputs[("color", f, s_)])
+                if seed is not None:
+                    g["%s_color_aug_%d_%d" % (tag, f, s_)] = np32(inputs[("color_aug", f, s_)])
+    np.savez_compressed(os.path.join(HERE, "datapipe.npz"), **g)
+    print("datapipe.npz:", len(g), "arrays")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     rl, rn, rt, Options = import_reference()
-    if "--eval-only" not in sys.argv:
+    if "--eval-only" not in sys.argv and "--datapipe-only" not in sys.argv:
         if "--steps-only" not in sys.argv:
             op_vectors(rl)
         if "--ops-only" not in sys.argv:
             step_vectors(rl, rn, rt, Options)
+    if "--datapipe-only" in sys.argv:
+        datapipe_vectors()
+        sys.exit(0)
     if "--ops-only" not in sys.argv and "--steps-only" not in sys.argv:
         eval_vectors(rl, rn)
+        datapipe_vectors()

@@ -880,3 +880,58 @@ def test_maxpool3x3s2_matches_torch(ops, shape):
     (y * g(gy)).sum().backward()
     assert torch.equal(y.detach().cpu(), yo.detach())
     torch.testing.assert_close(xg.grad.cpu(), xo.grad, atol=1e-6, rtol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------- device data pipeline
+def test_device_pipeline_is_bit_exact_to_the_reference_preprocess(ops):
+    """movedepth_b200.datapipe.DevicePipeline (Lanczos pyramid, flip, ToTensor, ColorJitter on the GPU) vs the reference's own
+    MonoDataset.preprocess output (tests/golden/datapipe.npz): every pixel of every scale identical, with and without the
+    flip, and with the jitter parameters drawn from the same torch seed in the same order."""
+    from movedepth_b200.datapipe import DevicePipeline
+    gold = dict(np.load(os.path.join(GOLD, "datapipe.npz")))
+    c = C.case_frames()
+    pipe = DevicePipeline(c["H"], c["W"], device=DEV)
+    K = [[0.58, 0, 0.5, 0], [0, 1.92, 0.5, 0], [0, 0, 1, 0], [0, 0, 0, 1]]
+    frames = {f: torch.from_numpy(c["frames"][f].copy())[None].to(DEV) for f in (0, -1)}
+    plain = pipe(frames, K)
+    flipped = pipe(frames, K, flip=[1])
+    torch.manual_seed(c["seed"])
+    jit = pipe(frames, K, color_aug=[1])
+    for f in (0, -1):
+        for s in range(4):
+            assert np.array_equal(plain[("color", f, s)][0].cpu().numpy(), gold["plain_color_%d_%d" % (f, s)])
+            assert np.array_equal(plain[("color_aug", f, s)][0].cpu().numpy(), gold["plain_color_%d_%d" % (f, s)])
+            assert np.array_equal(flipped[("color", f, s)][0].cpu().numpy(), gold["flip_color_%d_%d" % (f, s)])
+            assert np.array_equal(jit[("color", f, s)][0].cpu().numpy(), gold["jitter_color_%d_%d" % (f, s)])
+            assert np.array_equal(jit[("color_aug", f, s)][0].cpu().numpy(), gold["jitter_color_aug_%d_%d" % (f, s)]), (f, s)
+    assert plain[("K", 2)].shape == (1, 4, 4) and abs(float(plain[("K", 2)][0, 0, 0]) - 0.58 * 24) < 1e-5
+
+
+def test_device_pipeline_matches_the_oracle_at_kitti_size(ops):
+    """375x1242 'decoded' frames -> 192x640 pyramid, batch of 3 with mixed flips and per-image jitter (random orders, all four
+    operations, extrapolating and interpolating factors): bit-exact against oracle/datapipe.py (pinned to Pillow)."""
+    from movedepth_b200.datapipe import DevicePipeline
+    from oracle import datapipe as OD
+    rng = np.random.default_rng(5)
+    B, Hn, Wn, H, W = 3, 375, 1242, 192, 640
+    walk = np.cumsum(rng.normal(0, 5, (B, Hn, Wn, 3)), 2) + rng.normal(0, 8, (B, Hn, Wn, 3))
+    native = np.clip(walk + 120, 0, 255).astype(np.uint8)
+    pipe = DevicePipeline(H, W, device=DEV)
+    dev = torch.from_numpy(native).to(DEV)
+    flip = [0, 1, 0]
+    img = dev
+    for s in range(4):
+        img = pipe.resize(img, H >> s, W >> s, torch.tensor(flip, dtype=torch.uint8, device=DEV) if s == 0 else None)
+        for n in range(B):
+            src = native[n][:, ::-1] if flip[n] else native[n]
+            want = OD.pyramid(src, H, W)[s] if s < 2 else None
+            if want is not None:
+                assert np.array_equal(img[n].cpu().numpy(), want), (s, n)
+    base = pipe.resize(dev, H, W)
+    orders = [[0, 1, 2, 3], [3, 2, 1, 0], [2, 0, 3, 1]]
+    factors = [[0.8, 1.2, 0.93, -0.1], [1.17, 0.85, 1.2, 0.07], [1.0, 1.0, 0.8, 0.0]]
+    got = pipe.color_jitter(base, orders, factors, [1, 1, 1]).cpu().numpy()
+    for n in range(B):
+        assert np.array_equal(got[n], OD.color_jitter(base[n].cpu().numpy(), orders[n], factors[n])), n
+    t = pipe.to_tensor(base)
+    assert np.array_equal(t[1].cpu().numpy(), OD.to_tensor(base[1].cpu().numpy()))
