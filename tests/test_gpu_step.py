@@ -324,3 +324,28 @@ def test_graphed_predictor_replays_the_eager_prediction():
         torch.cuda.synchronize()
         for k in ("pred_disp_z", "pred_disp_mono"):
             torch.testing.assert_close(got[k], want[k], atol=1e-6, rtol=1e-5)
+
+
+def test_train_loop_logs_validates_and_saves(tmp_path):
+    """Trainer.train() (movedepth/trainer.py:244-295) over a three-batch synthetic loader: the step loop, the log / val cadence
+    (every `log_frequency` batches early on), `opt.json`, the jsonl scalars, and a checkpoint at the end of the last epoch."""
+    import json
+    from movedepth_b200.trainer import SyntheticKITTI
+    cfg = C.STEP_CASES["r18_2f"]
+    tr = _trainer(cfg, precision="3xtf32", extra=["--model_name", "loop", "--log_dir", str(tmp_path), "--num_epochs", "17",
+                                                  "--log_frequency", "1", "--b200_cuda_graph"])
+    tr.train_loader = SyntheticKITTI(tr.opt, cfg["B"], 6, seed=5, smooth=True)
+    tr.val_loader = SyntheticKITTI(tr.opt, cfg["B"], 2, seed=6, smooth=True)
+    tr.val_iter = iter(tr.val_loader)
+    tr.opt.num_epochs = 17                 # epochs 0..16: save_model fires once (epoch 16 > 15), tagged "last"
+    tr.epoch = 16
+    tr.start_time = __import__("time").time()
+    tr.run_epoch()
+    tr.save_model()
+    root = os.path.join(str(tmp_path), "loop")
+    assert os.path.isfile(os.path.join(root, "models", "opt.json"))
+    rows = [json.loads(l) for l in open(os.path.join(root, "train", "scalars.jsonl"))]
+    assert len(rows) == 6 and all(np.isfinite(r["loss"]) for r in rows) and rows[-1]["step"] == 5
+    assert os.path.isfile(os.path.join(root, "val", "scalars.jsonl"))
+    assert os.path.isfile(os.path.join(root, "models", "last", "reg3d.pth")) and os.path.isfile(os.path.join(root, "models", "last", "adam.pth"))
+    assert tr.step == 6 and tr.opt_step == 6 and len(tr._graphs) == 1
