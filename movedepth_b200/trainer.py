@@ -30,7 +30,7 @@ import torch.distributed as dist
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import networks, ops
+from . import eventlog, networks, ops
 from . import norm as NM
 from . import precision as PR
 from . import photometric as photo
@@ -197,6 +197,7 @@ class Trainer:
     def __init__(self, options, train_loader=None, val_loader=None):
         self.opt = o = options
         self.log_path = os.path.join(o.log_dir, o.model_name)
+        self.writers = {}                      # mode -> eventlog.SummaryWriter (movedepth/trainer.py:147-151), opened on first use
         assert o.height % 32 == 0, "'height' must be a multiple of 32"
         assert o.width % 32 == 0, "'width' must be a multiple of 32"
         assert o.frame_ids[0] == 0, "frame_ids must start with 0"
@@ -815,16 +816,31 @@ class Trainer:
             self.epoch, batch_idx, rate, loss, spent))
 
     def log(self, mode, inputs, outputs, losses):
-        """Scalars go to <log_path>/<mode>/scalars.jsonl (tensorboardX is not a dependency here;
-        movedepth/trainer.py:772-793 writes the same scalars to tensorboard)."""
+        """movedepth/trainer.py:772-793: scalars per loss plus the colour frames, warped predictions and colour-mapped
+        disparities of up to four samples, written as a tensorboard events file under <log_path>/<mode>/ by
+        `eventlog.SummaryWriter` (this image has no tensorboardX); the scalars also go to scalars.jsonl."""
         d = os.path.join(self.log_path, mode)
-        os.makedirs(d, exist_ok=True)
+        if mode not in self.writers:
+            self.writers[mode] = eventlog.SummaryWriter(d)
+        writer = self.writers[mode]
         row = {"step": self.step}
         for k, v in losses.items():
             if not k.startswith("_"):
                 row[k] = float(v)
+                writer.add_scalar(k, row[k], self.step)
         with open(os.path.join(d, "scalars.jsonl"), "a") as f:
             f.write(json.dumps(row) + "\n")
+        for j in range(min(4, self.opt.batch_size)):
+            for f_id in self.opt.frame_ids:
+                if ("color", f_id, 0) in inputs:
+                    writer.add_image("color_{}_0/{}".format(f_id, j), inputs[("color", f_id, 0)][j], self.step)
+                if f_id != 0 and torch.is_tensor(outputs.get(("color", f_id, 0))):
+                    writer.add_image("color_pred_{}_0/{}".format(f_id, j), outputs[("color", f_id, 0)][j], self.step)
+            if ("disp", 0) in outputs:
+                writer.add_image("disp_mono/{}".format(j), eventlog.colormap(outputs[("disp", 0)][j, 0]), self.step)
+            if "depth_mvs" in outputs:
+                writer.add_image("disp_mvs/{}".format(j), eventlog.colormap(1 / outputs["depth_mvs"][j].squeeze(0)), self.step)
+        writer.flush()
 
     def save_opts(self):
         """movedepth/trainer.py:796-805."""

@@ -347,5 +347,15 @@ def test_train_loop_logs_validates_and_saves(tmp_path):
     rows = [json.loads(l) for l in open(os.path.join(root, "train", "scalars.jsonl"))]
     assert len(rows) == 6 and all(np.isfinite(r["loss"]) for r in rows) and rows[-1]["step"] == 5
     assert os.path.isfile(os.path.join(root, "val", "scalars.jsonl"))
+    from movedepth_b200 import eventlog                                 # tensorboard events: same scalars, plus the images of trainer.py:779-793
+    for mode in ("train", "val"):
+        tr.writers[mode].close()
+        ev = list(eventlog.read_events(tr.writers[mode].path))
+        scal = [e for e in ev if "loss" in e["scalars"]]
+        assert len(scal) == 6 and [e["step"] for e in scal] == list(range(6))
+        tags = set().union(*(e["images"].keys() for e in ev))
+        assert {"color_0_0/0", "color_-1_0/0", "disp_mono/0", "disp_mvs/0"} <= tags, tags
+        if mode == "train":
+            assert abs(scal[-1]["scalars"]["loss"] - rows[-1]["loss"]) <= 1e-6 * max(1.0, abs(rows[-1]["loss"]))
     assert os.path.isfile(os.path.join(root, "models", "last", "reg3d.pth")) and os.path.isfile(os.path.join(root, "models", "last", "adam.pth"))
     assert tr.step == 6 and tr.opt_step == 6 and len(tr._graphs) == 1

@@ -294,3 +294,49 @@ def test_kitti_metric_stage_matches_the_oracle_and_the_eigen_crop():
     g2 = g0.copy()
     g2[153, 44] = 55.0                                                                # first pixel inside the crop
     assert ED.kitti_metrics(d, d, [g2])["mvs"][0] > 0
+
+
+def test_event_writer_tfrecord_and_protobuf_round_trip(tmp_path):
+    """eventlog.SummaryWriter (replaces tensorboardX at movedepth/trainer.py:147-151, 772-793): CRC-32C known answer, TFRecord
+    framing, scalar and image summaries read back, PNG payload decodes to the pixels written."""
+    import struct
+    import zlib
+    from movedepth_b200 import eventlog
+    assert eventlog.crc32c(b"123456789") == 0xE3069283                  # the Castagnoli check value
+    assert eventlog.crc32c(b"") == 0
+    w = eventlog.SummaryWriter(str(tmp_path))
+    w.add_scalar("loss", 0.125, 7)
+    w.add_scalar("abs_rel", 3.5, 2 ** 40)                               # a step that needs a multi-byte varint
+    img = np.random.default_rng(0).random((3, 5, 9)).astype(np.float32)
+    w.add_image("color_0_0/0", img, 8)
+    w.add_image("disp_mono/0", eventlog.colormap(np.arange(12.0).reshape(3, 4)), 8)
+    w.close()
+    ev = list(eventlog.read_events(w.path))
+    assert ev[0]["file_version"] == "brain.Event:2" and ev[0]["step"] == 0
+    assert ev[1]["step"] == 7 and ev[1]["scalars"] == {"loss": 0.125}
+    assert ev[2]["step"] == 2 ** 40 and ev[2]["scalars"] == {"abs_rel": 3.5}
+    h, wd, c, png = ev[3]["images"]["color_0_0/0"]
+    assert (h, wd, c) == (5, 9, 3) and png[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat = 8, b""
+    while pos < len(png):                                               # chunk walk: length, type, data, CRC-32
+        (n,) = struct.unpack(">I", png[pos:pos + 4])
+        kind, body = png[pos + 4:pos + 8], png[pos + 8:pos + 8 + n]
+        assert struct.unpack(">I", png[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(kind + body)
+        if kind == b"IDAT":
+            idat += body
+        pos += 12 + n
+    rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(5, 1 + 9 * 3)
+    assert (rows[:, 0] == 0).all()
+    np.testing.assert_array_equal(rows[:, 1:].reshape(5, 9, 3), (np.moveaxis(img, 0, -1) * 255.0).astype(np.uint8))
+    assert ev[4]["images"]["disp_mono/0"][:3] == (3, 4, 3)
+    cm = eventlog.colormap(np.array([[0.0, 0.5, 1.0]]), normalize=False)
+    np.testing.assert_allclose(cm[:, 0, 0] * 255, (13, 8, 135), atol=1e-4)
+    np.testing.assert_allclose(cm[:, 0, 1] * 255, (204, 71, 120), atol=1e-4)
+    np.testing.assert_allclose(cm[:, 0, 2] * 255, (240, 249, 33), atol=1e-4)
+    with open(w.path, "r+b") as f:                                      # a flipped payload byte must be caught by the CRC
+        f.seek(30)
+        b = f.read(1)
+        f.seek(30)
+        f.write(bytes([b[0] ^ 1]))
+    with pytest.raises(ValueError):
+        list(eventlog.read_events(w.path))
