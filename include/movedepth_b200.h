@@ -361,6 +361,20 @@ int mvd_bn_bwd_apply(const float* gy, const float* x, const float* y, const floa
                      const float* weight, const double* sums2, double count, float* gx, float* gres,
                      float* gw, float* gb, long long M, int C, int relu, void* stream);
 
+/* One-kernel forms for activations that fit the L2 (most layers of the step): phase 1 reduces, a grid barrier (the last block
+ * to arrive performs the SyncBatchNorm exchange when peers != NULL), phase 2 applies with x re-read from the L2.  Same
+ * arithmetic and outputs as stats + finalize + apply / bwd_reduce + bwd_apply above.  `workspace` = mvd_bn_workspace_doubles()
+ * doubles, zeroed ONCE by the caller; the kernels hand it back zeroed, so consecutive calls on one stream share it (calls
+ * that can run concurrently need their own).  The grid never exceeds 2/3 of the SM count at two resident blocks per SM. */
+int mvd_bn_workspace_doubles(void);
+int mvd_bn_fwd_fused(const float* x, const float* residual, const float* weight, const float* bias, float* running_mean,
+                     float* running_var, long long* num_batches_tracked, float momentum, float eps, double count,
+                     float* stats, float* y, long long M, int C, int relu, double* workspace,
+                     const unsigned long long* peers, int rank, int world, int nmax, void* stream);
+int mvd_bn_bwd_fused(const float* gy, const float* x, const float* y, const float* stats, const float* weight, double count,
+                     float* gx, float* gres, float* gw, float* gb, double* local_sums2, long long M, int C, int relu,
+                     double* workspace, const unsigned long long* peers, int rank, int world, int nmax, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * SyncBatchNorm statistics exchange over NVLink peer memory (replaces the all_gather / all_reduce
  * of nn.SyncBatchNorm, movedepth/trainer.py:69-129, for the 2C-double vectors of mvd_bn_stats /

@@ -74,6 +74,9 @@ SIGNATURES = {
     "mvd_bn_apply": ([_P, _P, _P, _P, _LL, _I, _I, _P], _I),
     "mvd_bn_bwd_reduce": ([_P, _P, _P, _P, _P, _P, _LL, _I, _I, _P, _I, _I, _I, _P], _I),
     "mvd_bn_bwd_apply": ([_P] * 6 + [_D] + [_P] * 4 + [_LL, _I, _I, _P], _I),
+    "mvd_bn_workspace_doubles": ([], _I),
+    "mvd_bn_fwd_fused": ([_P] * 7 + [_F, _F, _D, _P, _P, _LL, _I, _I, _P, _P, _I, _I, _I, _P], _I),
+    "mvd_bn_bwd_fused": ([_P] * 5 + [_D] + [_P] * 5 + [_LL, _I, _I, _P, _P, _I, _I, _I, _P], _I),
     "mvd_peer_allreduce_buffer_bytes": ([_I, _I], _LL),
     "mvd_peer_allreduce_f64": ([_P, _P, _I, _P, _I, _I, _I, _P], _I),
     "mvd_event_create": ([], _P),

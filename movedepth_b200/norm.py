@@ -8,6 +8,7 @@ fp64 sums are all-reduced between the statistics and the apply kernels -- one sm
 SyncBatchNorm's all_gather + gather_stats pipeline.  Evaluation mode and CPU tensors use torch's own batch_norm.
 """
 import ctypes
+import os
 import types
 
 import torch
@@ -79,6 +80,33 @@ def _peer(device, C, chan=0):
     return px
 
 
+fuse_bytes = int(float(os.environ.get("MVD_BN_FUSE_MB", "24")) * (1 << 20))
+"""Activations up to this size take the one-kernel forward / backward (csrc/bn.cu: reduce, grid barrier with the SyncBN exchange,
+apply from the L2); larger ones stream through the separate reduction / apply kernels at full-grid bandwidth."""
+_workspaces = {}
+
+
+def workspace(device, chan=0):
+    """The zero-initialised statistics workspace of the one-kernel BatchNorm (handed back zeroed by every call).  One per
+    exchange channel: layers on one stream share it, the trainer's two concurrent streams use channels 0 and 1.  Created
+    outside any CUDA-graph capture (`Trainer.__init__` touches both channels)."""
+    key = (torch.device(device).index or 0, chan)
+    ws = _workspaces.get(key)
+    if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("movedepth_b200.norm.workspace(%r, %d) must be created before CUDA-graph capture" % (device, chan))
+        ws = _workspaces[key] = torch.zeros(_lib.lib().mvd_bn_workspace_doubles(), device=device, dtype=torch.float64)
+    return ws
+
+
+def check_workspaces():
+    """Raises if a grid barrier of the one-kernel BatchNorm ever timed out (control word 3 is sticky).  Synchronises: the
+    trainer calls it on its log steps."""
+    for (dev, chan), ws in _workspaces.items():
+        if int(ws[-2:].view(torch.int32)[3]) != 0:
+            raise RuntimeError("movedepth_b200: a BatchNorm grid barrier timed out on cuda:%d (channel %d)" % (dev, chan))
+
+
 def _count_launch(n):
     from . import ops
     ops.launch_counter["n"] += n
@@ -96,57 +124,74 @@ class _BNAct(torch.autograd.Function):
         ctx.channel = channel
         px = _peer(x.device, C, channel) if sync else None
         precomputed = sums is not None and sums.numel() >= 2 * C       # the producing conv's epilogue already summed its output
-        if not precomputed:
-            sums = torch.empty(2 * C + 1, device=x.device, dtype=torch.float64)      # [sum x, sum x^2, arrival counter]
-            _lib.check(L.mvd_bn_stats(_p(xc), M, C, _p(sums), _p(px.ptrs) if px else _p(None), px.rank if px else 0,
-                                      px.world if px else 1, px.NMAX if px else 0, _stream()), "mvd_bn_stats")
-        count = float(M)
-        if sync:
-            if precomputed and px is not None:            # fused statistics: the exchange is its own (single-CTA) kernel
-                px.allreduce_(sums[:2 * C])
-            elif px is None:                              # no peer memory: NCCL exchanges the sums
-                dist.all_reduce(sums[:2 * C])
-            count *= dist.get_world_size()
-        stats = torch.empty(4 * C, device=x.device, dtype=torch.float32)
-        _lib.check(L.mvd_bn_finalize(_p(sums), count, _p(weight), _p(bias), _p(running_mean), _p(running_var), float(momentum),
-                                     float(eps), _p(stats), C, _p(nbt), _stream()), "mvd_bn_finalize")
-        y = torch.empty_like(xc)
         post = bool(post and residual is not None)         # post: relu(bn(x)) + residual (U-Net skip); else relu(bn(x) + residual)
-        _lib.check(L.mvd_bn_apply(_p(xc), _p(rc_), _p(stats), _p(y), M, C, int(relu) | (2 if post else 0), _stream()), "mvd_bn_apply")
-        _count_launch(4)
+        flags = int(relu) | (2 if post else 0)
+        count = float(M) * (dist.get_world_size() if sync else 1)
+        stats = torch.empty(4 * C, device=x.device, dtype=torch.float32)
+        y = torch.empty_like(xc)
+        fused = (not precomputed) and xc.numel() * 4 <= fuse_bytes and (px is not None or not sync)
+        if fused:                                          # one launch: reduce, barrier (+ exchange), finalize, apply
+            _lib.check(L.mvd_bn_fwd_fused(_p(xc), _p(rc_), _p(weight), _p(bias), _p(running_mean), _p(running_var), _p(nbt),
+                                          float(momentum), float(eps), count, _p(stats), _p(y), M, C, flags,
+                                          _p(workspace(x.device, channel)), _p(px.ptrs) if px else _p(None), px.rank if px else 0,
+                                          px.world if px else 1, px.NMAX if px else 0, _stream()), "mvd_bn_fwd_fused")
+            _count_launch(1)
+        else:
+            if not precomputed:
+                sums = torch.empty(2 * C + 1, device=x.device, dtype=torch.float64)      # [sum x, sum x^2, arrival counter]
+                _lib.check(L.mvd_bn_stats(_p(xc), M, C, _p(sums), _p(px.ptrs) if px else _p(None), px.rank if px else 0,
+                                          px.world if px else 1, px.NMAX if px else 0, _stream()), "mvd_bn_stats")
+            if sync:
+                if precomputed and px is not None:            # fused statistics: the exchange is its own (single-CTA) kernel
+                    px.allreduce_(sums[:2 * C])
+                elif px is None:                              # no peer memory: NCCL exchanges the sums
+                    dist.all_reduce(sums[:2 * C])
+            _lib.check(L.mvd_bn_finalize(_p(sums), count, _p(weight), _p(bias), _p(running_mean), _p(running_var), float(momentum),
+                                         float(eps), _p(stats), C, _p(nbt), _stream()), "mvd_bn_finalize")
+            _lib.check(L.mvd_bn_apply(_p(xc), _p(rc_), _p(stats), _p(y), M, C, flags, _stream()), "mvd_bn_apply")
+            _count_launch(4)
         # the ReLU mask is the sign of bn(x), recomputed from x in the backward, unless a residual was added BEFORE the ReLU
         ctx.save_for_backward(xc, y if (relu and residual is not None and not post) else None, stats, weight)
-        ctx.cfg = (M, C, count, bool(relu), bool(sync), residual is not None, post)
+        ctx.cfg = (M, C, count, bool(relu), bool(sync), residual is not None, post, fused)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         xc, y, stats, weight = ctx.saved_tensors
-        M, C, count, relu, sync, has_res, post = ctx.cfg
+        M, C, count, relu, sync, has_res, post, fused = ctx.cfg
         L = _lib.lib()
         gy = gy.contiguous(memory_format=_fmt(xc))
-        sums2 = torch.empty(2 * C + 1, device=xc.device, dtype=torch.float64)
         px = _peer(xc.device, C, ctx.channel) if sync else None
         local2 = torch.empty(2 * C, device=xc.device, dtype=torch.float64) if px else None
-        _lib.check(L.mvd_bn_bwd_reduce(_p(gy), _p(xc), _p(y), _p(stats), _p(sums2), _p(local2), M, C, int(relu),
-                                       _p(px.ptrs) if px else _p(None), px.rank if px else 0, px.world if px else 1,
-                                       px.NMAX if px else 0, _stream()), "mvd_bn_bwd_reduce")
-        gw = gb = None
-        if sync:                                  # parameter gradients are this rank's own sums (DDP averages them later)
-            if px is None:
-                gb, gw = sums2[:C].float(), sums2[C:2 * C].float()
-                dist.all_reduce(sums2[:2 * C])
-            else:                                 # the reduction kernel exchanged in place and kept the local sums aside
-                gb, gw = local2[:C].float(), local2[C:].float()
-        else:
-            gw = torch.empty(C, device=xc.device, dtype=torch.float32)
-            gb = torch.empty(C, device=xc.device, dtype=torch.float32)
         gx = torch.empty_like(xc)
         gres = torch.empty_like(xc) if (has_res and not post and ctx.needs_input_grad[3]) else None
-        _lib.check(L.mvd_bn_bwd_apply(_p(gy), _p(xc), _p(y), _p(stats), _p(weight), _p(sums2), count, _p(gx), _p(gres),
-                                      _p(None if sync else gw), _p(None if sync else gb), M, C, int(relu), _stream()),
-                   "mvd_bn_bwd_apply")
-        _count_launch(3)
+        gw = gb = None
+        if not sync:
+            gw = torch.empty(C, device=xc.device, dtype=torch.float32)
+            gb = torch.empty(C, device=xc.device, dtype=torch.float32)
+        if fused:
+            _lib.check(L.mvd_bn_bwd_fused(_p(gy), _p(xc), _p(y), _p(stats), _p(weight), count, _p(gx), _p(gres), _p(gw), _p(gb),
+                                          _p(local2), M, C, int(relu), _p(workspace(xc.device, ctx.channel)),
+                                          _p(px.ptrs) if px else _p(None), px.rank if px else 0, px.world if px else 1,
+                                          px.NMAX if px else 0, _stream()), "mvd_bn_bwd_fused")
+            _count_launch(1)
+            if sync:                              # parameter gradients are this rank's own sums (DDP averages them later)
+                gb, gw = local2[:C].float(), local2[C:].float()
+        else:
+            sums2 = torch.empty(2 * C + 1, device=xc.device, dtype=torch.float64)
+            _lib.check(L.mvd_bn_bwd_reduce(_p(gy), _p(xc), _p(y), _p(stats), _p(sums2), _p(local2), M, C, int(relu),
+                                           _p(px.ptrs) if px else _p(None), px.rank if px else 0, px.world if px else 1,
+                                           px.NMAX if px else 0, _stream()), "mvd_bn_bwd_reduce")
+            if sync:
+                if px is None:
+                    gb, gw = sums2[:C].float(), sums2[C:2 * C].float()
+                    dist.all_reduce(sums2[:2 * C])
+                else:                             # the reduction kernel exchanged in place and kept the local sums aside
+                    gb, gw = local2[:C].float(), local2[C:].float()
+            _lib.check(L.mvd_bn_bwd_apply(_p(gy), _p(xc), _p(y), _p(stats), _p(weight), _p(sums2), count, _p(gx), _p(gres),
+                                          _p(None if sync else gw), _p(None if sync else gb), M, C, int(relu), _stream()),
+                       "mvd_bn_bwd_apply")
+            _count_launch(3)
         if post and ctx.needs_input_grad[3]:
             gres = gy                                 # the skip was added after the ReLU: its gradient is gy itself
         if weight is None or not ctx.needs_input_grad[1]:

@@ -291,6 +291,9 @@ class Trainer:
         # noise and a replay never re-uses the noise of the capture
         self._two_streams = not getattr(o, "b200_one_stream", False)
         self._mvs_stream = torch.cuda.Stream() if self._two_streams else None
+        if self.device.type == "cuda":
+            for chan in (0, 1):                            # the one-kernel BatchNorm's workspaces exist before any graph capture
+                NM.workspace(self.device, chan)
         self.noise_generator = torch.Generator(device=self.device)
         self.noise_generator.manual_seed(torch.initial_seed() + self.rank)
         self._noise_buf = None
@@ -819,6 +822,7 @@ class Trainer:
         """movedepth/trainer.py:772-793: scalars per loss plus the colour frames, warped predictions and colour-mapped
         disparities of up to four samples, written as a tensorboard events file under <log_path>/<mode>/ by
         `eventlog.SummaryWriter` (this image has no tensorboardX); the scalars also go to scalars.jsonl."""
+        NM.check_workspaces()
         d = os.path.join(self.log_path, mode)
         if mode not in self.writers:
             self.writers[mode] = eventlog.SummaryWriter(d)

@@ -315,11 +315,13 @@ def test_conv3d_16_to_16_matches_torch_conv3d(ops, shape):
 @pytest.mark.parametrize("shape,relu,res", [((3, 16, 5, 6, 7), True, False), ((4, 64, 9, 11), True, True), ((2, 8, 6, 10), False, False),
                                             ((2, 512, 3, 5), True, True), ((2, 32, 4, 6, 8), True, "post")],
                          ids=["3d-relu", "2d-relu-res", "2d-plain", "c512", "3d-relu-then-skip"])
-def test_fused_batchnorm_matches_torch(shape, relu, res):
-    """csrc/bn.cu (stats / finalize / apply, backward reduce / apply) vs torch's batch_norm + add + relu in fp64:
-    outputs, input / residual / weight / bias gradients and the running statistics."""
+@pytest.mark.parametrize("one_kernel", [False, True], ids=["three-kernels", "one-kernel"])
+def test_fused_batchnorm_matches_torch(shape, relu, res, one_kernel, monkeypatch):
+    """csrc/bn.cu (stats / finalize / apply, backward reduce / apply; and the one-kernel forms with the grid barrier) vs torch's
+    batch_norm + add + relu in fp64: outputs, input / residual / weight / bias gradients and the running statistics."""
     import torch.nn as nn
     from movedepth_b200 import norm as NM
+    monkeypatch.setattr(NM, "fuse_bytes", (1 << 30) if one_kernel else 0)
     gen = torch.Generator().manual_seed(9)
     C = shape[1]
     cls = nn.BatchNorm3d if len(shape) == 5 else nn.BatchNorm2d
@@ -362,6 +364,53 @@ def test_fused_batchnorm_matches_torch(shape, relu, res):
     close(mine.running_mean, ref.running_mean)
     close(mine.running_var, ref.running_var)
     assert int(mine.num_batches_tracked) == 1
+    if one_kernel:                                   # the workspace is handed back zeroed, no timeout was recorded
+        torch.cuda.synchronize()
+        assert int(NM.workspace(DEV, 0).view(torch.int64).abs().sum()) == 0
+
+
+def test_one_kernel_batchnorm_equals_the_three_kernel_form_at_a_full_grid():
+    """A ResNet layer1-sized activation (the barrier runs at its full grid of 2/3 of the SMs, many rows per thread, both
+    unrolled and tail iterations), repeated with different channel counts on one shared workspace: outputs, saved statistics
+    and gradients of the one-kernel BatchNorm vs the stats / finalize / apply kernels (fp64 atomics in a different order:
+    1e-6), running statistics after three steps, workspace zero afterwards."""
+    import torch.nn as nn
+    from movedepth_b200 import norm as NM
+    gen = torch.Generator(device=DEV).manual_seed(77)
+    for shape, relu, res in [((6, 64, 48, 160), True, True), ((3, 8, 95, 161), True, False), ((2, 128, 24, 80), False, False),
+                             ((1, 16, 7, 24, 80), True, "post")]:
+        C = shape[1]
+        fmt = torch.channels_last_3d if len(shape) == 5 else torch.channels_last
+        cls = nn.BatchNorm3d if len(shape) == 5 else nn.BatchNorm2d
+        bns = [cls(C).to(DEV) for _ in range(2)]
+        with torch.no_grad():
+            bns[0].weight.copy_(1 + 0.2 * torch.randn(C, device=DEV, generator=gen))
+            bns[0].bias.copy_(0.1 * torch.randn(C, device=DEV, generator=gen))
+            bns[1].load_state_dict(bns[0].state_dict())
+        for it in range(3):
+            x = (torch.randn(shape, device=DEV, generator=gen) * 2 + 0.5).contiguous(memory_format=fmt)
+            r = torch.randn(shape, device=DEV, generator=gen).contiguous(memory_format=fmt) if res else None
+            gy = torch.randn(shape, device=DEV, generator=gen).contiguous(memory_format=fmt)
+            outs = []
+            for k, limit in enumerate((0, 1 << 30)):
+                NM.fuse_bytes, keep = limit, NM.fuse_bytes
+                try:
+                    xi = x.clone().requires_grad_(True)
+                    ri = r.clone().requires_grad_(True) if res else None
+                    y = NM.bn_act(bns[k], xi, relu=relu, residual=ri, post=(res == "post"))
+                    (y * gy).sum().backward()
+                finally:
+                    NM.fuse_bytes = keep
+                outs.append((y.detach(), xi.grad, ri.grad if res else None, bns[k].weight.grad.clone(), bns[k].bias.grad.clone()))
+                bns[k].zero_grad()
+            for a, b in zip(*outs):
+                if a is not None:
+                    torch.testing.assert_close(b, a, atol=1e-5 * max(1.0, float(a.abs().max())), rtol=1e-5)
+        for name in ("running_mean", "running_var"):
+            torch.testing.assert_close(getattr(bns[1], name), getattr(bns[0], name), atol=1e-6, rtol=1e-6)
+        assert int(bns[1].num_batches_tracked) == 3
+    torch.cuda.synchronize()
+    assert int(NM.workspace(DEV, 0).view(torch.int64).abs().sum()) == 0
 
 
 def _sync_bn_worker(rank, world, port, q):
@@ -771,6 +820,63 @@ def test_batchnorm_reductions_exchange_inside_the_kernel_two_ranks_on_one_gpu(op
         torch.testing.assert_close(sums2[0][:2 * C], mine[0] + mine[1], rtol=1e-5, atol=1e-5)
     for b in bufs:
         assert int(b.view(torch.int64)[1]) == 0 and int(b.view(torch.int64)[0]) == 12
+
+
+def test_one_kernel_batchnorm_exchanges_at_its_grid_barrier_two_ranks_on_one_gpu(ops):
+    """SyncBatchNorm in one launch per direction: the last block to reach the grid barrier of mvd_bn_fwd_fused /
+    mvd_bn_bwd_fused all-reduces the sums over peer memory before it opens the barrier.  Two 'ranks' = two streams on this GPU
+    (their two barrier kernels are resident together and wait for each other): both must normalise with the statistics of
+    BOTH halves of the batch, the backward keeps each rank's own sums aside, and the workspaces come back zeroed."""
+    import ctypes
+    L = ops._lib.lib()
+    world, nmax, C = 2, 2048, 32
+    nbytes = L.mvd_peer_allreduce_buffer_bytes(world, nmax)
+    bufs = [torch.zeros((nbytes + 7) // 8, dtype=torch.float64, device=DEV) for _ in range(world)]
+    ptrs = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=DEV)
+    wss = [torch.zeros(L.mvd_bn_workspace_doubles(), dtype=torch.float64, device=DEV) for _ in range(world)]
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    gen = torch.Generator(device=DEV).manual_seed(36)
+    P = lambda t: ctypes.c_void_p(t.data_ptr() if t is not None else 0)
+    S = lambda r: ctypes.c_void_p(streams[r].cuda_stream)
+    w = 1 + 0.2 * torch.randn(C, device=DEV, generator=gen)
+    b = 0.1 * torch.randn(C, device=DEV, generator=gen)
+    for it, M in enumerate((300, 70000, 5000)):                                   # one block / the full grid / in between
+        Ms = [M, M + 123]
+        xs = [torch.randn(Ms[r], C, device=DEV, generator=gen) * 2 + 0.5 for r in range(world)]
+        gs = [torch.randn(Ms[r], C, device=DEV, generator=gen) for r in range(world)]
+        count = float(sum(Ms))
+        ys = [torch.empty_like(x) for x in xs]
+        stats = [torch.empty(4 * C, device=DEV) for _ in range(world)]
+        rm = [torch.zeros(C, device=DEV) for _ in range(world)]
+        rv = [torch.ones(C, device=DEV) for _ in range(world)]
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert L.mvd_bn_fwd_fused(P(xs[r]), P(None), P(w), P(b), P(rm[r]), P(rv[r]), P(None), 0.1, 1e-5, count, P(stats[r]),
+                                      P(ys[r]), Ms[r], C, 1, P(wss[r]), P(ptrs), r, world, nmax, S(r)) == 0
+        torch.cuda.synchronize()
+        allx = torch.cat(xs).double()
+        mean, var = allx.mean(0), allx.var(0, unbiased=False)
+        assert torch.equal(stats[0], stats[1])
+        torch.testing.assert_close(stats[0][:C], mean.float(), atol=1e-6, rtol=1e-6)
+        torch.testing.assert_close(rv[0], (0.9 + 0.1 * allx.var(0, unbiased=True)).float(), atol=1e-6, rtol=1e-6)
+        for r in range(world):
+            want = torch.relu((xs[r].double() - mean) / torch.sqrt(var + 1e-5) * w.double() + b.double())
+            torch.testing.assert_close(ys[r], want.float(), atol=2e-5, rtol=2e-5)
+        gxs = [torch.empty_like(x) for x in xs]
+        local = [torch.empty(2 * C, dtype=torch.float64, device=DEV) for _ in range(world)]
+        for r in range(world):
+            assert L.mvd_bn_bwd_fused(P(gs[r]), P(xs[r]), P(None), P(stats[r]), P(w), count, P(gxs[r]), P(None), P(None), P(None),
+                                      P(local[r]), Ms[r], C, 1, P(wss[r]), P(ptrs), r, world, nmax, S(r)) == 0
+        torch.cuda.synchronize()
+        xo = torch.cat(xs).double().requires_grad_(True)
+        wo = w.double().requires_grad_(True)
+        yo = torch.relu((xo - xo.mean(0)) / torch.sqrt(xo.var(0, unbiased=False) + 1e-5) * wo + b.double())
+        (yo * torch.cat(gs).double()).sum().backward()
+        got = torch.cat(gxs)
+        torch.testing.assert_close(got, xo.grad.float(), atol=1e-4 * float(xo.grad.abs().max()), rtol=1e-4)
+        torch.testing.assert_close((local[0][C:] + local[1][C:]).float(), wo.grad.float(), atol=1e-3, rtol=1e-4)
+        for r in range(world):
+            assert int(wss[r].view(torch.int64).abs().sum()) == 0
 
 
 # ---------------------------------------------------------------------------------------------- skinny 2-D convolutions
