@@ -80,7 +80,7 @@ def _peer(device, C, chan=0):
     return px
 
 
-fuse_bytes = int(float(os.environ.get("MVD_BN_FUSE_MB", "24")) * (1 << 20))
+fuse_bytes = int(float(os.environ.get("MVD_BN_FUSE_MB", "64")) * (1 << 20))
 """Activations up to this size take the one-kernel forward / backward (csrc/bn.cu: reduce, grid barrier with the SyncBN exchange,
 apply from the L2); larger ones stream through the separate reduction / apply kernels at full-grid bandwidth."""
 _workspaces = {}

@@ -75,6 +75,40 @@ def main():
     t_nccl = e0.elapsed_time(e1) / 200 * 1e3
     print("rank %d/%d: eager max err %.2e, side-stream max err %.2e, graph max err %.2e, peer %.1f us/call, nccl %.1f us/call (eager launches)" % (
         rank, world, worst, serr, gerr, t_peer, t_nccl), flush=True)
+    # nn.SyncBatchNorm through bn_act on real peers: each rank holds a slice of one global batch; outputs / gradients must
+    # equal BatchNorm over the whole batch (fp64), for the one-kernel form (exchange at the grid barrier) and the three-kernel
+    # form (exchange by the last block of the reductions)
+    import torch.nn as nn
+    gen = torch.Generator().manual_seed(5)
+    for shape, one_kernel in [((4 * world, 64, 24, 80), True), ((4 * world, 64, 24, 80), False), ((2 * world, 16, 6, 24, 80), True),
+                              ((2 * world, 512, 6, 20), True)]:
+        NM.fuse_bytes = (1 << 30) if one_kernel else 0
+        C, nb = shape[1], shape[0] // world
+        x = torch.randn(shape, generator=gen) * 1.5 + 0.3
+        gy = torch.randn(shape, generator=gen)
+        ref = (nn.BatchNorm3d if len(shape) == 5 else nn.BatchNorm2d)(C).double()
+        xo = x.double().requires_grad_(True)
+        yo = torch.relu(ref(xo))
+        (yo * gy.double()).sum().backward()
+        bn = nn.SyncBatchNorm(C).to(dev)
+        fmt = torch.channels_last_3d if len(shape) == 5 else torch.channels_last
+        xs = x[rank * nb:(rank + 1) * nb].to(dev).contiguous(memory_format=fmt).requires_grad_(True)
+        for rep in range(3):                                          # repeated: the shared workspace must come back clean
+            bn.zero_grad()
+            xs.grad = None
+            y = NM.bn_act(bn, xs, relu=True)
+            (y * gy[rank * nb:(rank + 1) * nb].to(dev)).sum().backward()
+        sl = slice(rank * nb, (rank + 1) * nb)
+        ey = float((y.detach().cpu() - yo[sl].detach().float()).abs().max())
+        eg = float((xs.grad.cpu() - xo.grad[sl].float()).abs().max()) / float(xo.grad.abs().max())
+        gw = bn.weight.grad.clone()
+        dist.all_reduce(gw)
+        ew = float((gw.cpu() - ref.weight.grad.float()).abs().max()) / float(ref.weight.grad.abs().max())
+        assert ey < 5e-5 and eg < 2e-4 and ew < 2e-4, (shape, one_kernel, ey, eg, ew)
+        NM.check_workspaces()
+        if rank == 0:
+            print("SyncBatchNorm %s %s: y err %.1e, gx err %.1e (rel), sum of rank gw err %.1e (rel)" % (
+                shape, "one-kernel" if one_kernel else "three-kernel", ey, eg, ew), flush=True)
     dist.barrier()
     torch.cuda.synchronize()
     os._exit(0)
