@@ -35,6 +35,8 @@ extern "C" {
 #define MVD_FLAG_NO_TABLE 2 /* forward: no per-pixel tap-correlation table, recompute each bilinear cell directly */
 #define MVD_FLAG_DBG_NO_STORE 4  /* forward, profiling only: compute everything but do not issue the TMA stores */
 #define MVD_FLAG_PLAIN_STORE 16  /* forward: TMA-staged loads, but plain st.global instead of TMA stores */
+#define MVD_FLAG_BWD_V2 32  /* backward: the round-1 kernel (8 short chunks per pixel, one hypothesis in flight per thread), for A/B runs */
+/* backward, tuning: bits 8..11 of flags = number of hypothesis chunks per pixel (0 = default 3) */
 
 int mvd_version(void);
 const char* mvd_last_error_string(void);

@@ -909,6 +909,274 @@ costvol_grouped_bwd_kernel(const __grid_constant__ CUtensorMap map_src, const __
     }
 }
 
+// ---- backward, v5: warp-autonomous ----------------------------------------------------------------
+// No block barriers: a warp owns 16 consecutive pixels of a row and a chunk of hypotheses, a LANE PAIR owns a pixel
+// (lane = 2*pixel + half, half h = groups 8h..8h+7 = the lane's 32 B of every hypothesis' gradient): 32 accumulator registers
+// per thread (v2: 64 + ref + d ref = 253 registers, one 8-warp CTA per SM, one hypothesis in flight per thread).
+//  * In the channels-last layout the gradients of a warp's 16 pixels for one hypothesis are ONE contiguous 1 KB run: each warp
+//    streams them through its own shared-memory ring with bulk async copies (cp.async.bulk + mbarrier, issued by lane 0,
+//    RING hypotheses ahead), so the loads cost no registers and no issue slots and 16 warps keep 100+ KB in flight per SM --
+//    the v2 loop ran at the latency of one 64 B load per thread.  The [B,G,D,h,w] layout loads through registers, four
+//    hypotheses at a time.
+//  * A cell change flushes Q_tap[g] straight to global memory like v2 (vector atomics on d src, d ref partial in registers),
+//    but a thread walks a long chunk of the pixel's epipolar segment, so cells -- and flushes -- per pixel are ~3x fewer than with
+//    v2's 8 chunks; ref / src taps are read at flush time from the L1/L2.
+namespace b5 {
+constexpr int WARPS = 8, THREADS = 32 * WARPS;
+constexpr int PIXW = 16;                              // pixels per warp
+constexpr int GOB = 4;                                // register path: hypotheses loaded before the first is consumed
+constexpr int RING = 8;                               // ring path: stages of 1 KB per warp
+constexpr int SMEM = WARPS * RING * (PIXW * 64) + WARPS * RING * 8;
+
+struct Task {
+    int b, y, x0, d0, d1;
+};
+__device__ __forceinline__ Task task_of(const CvArgs& a, int t, int nch, int xblocks) {
+    Task k;
+    const int ch = t % nch;
+    t /= nch;
+    const int xb = t % xblocks;
+    t /= xblocks;
+    k.y = t % a.h;
+    k.b = t / a.h;
+    k.x0 = xb * PIXW;
+    k.d0 = ch * a.DC;
+    k.d1 = min(a.D, k.d0 + a.DC);
+    return k;
+}
+// 1-D bulk async copy global -> shared::cta with byte-count completion on an mbarrier; 32-bit shared addresses throughout (the
+// generic -> shared conversions stay out of the hypothesis loop)
+__device__ __forceinline__ void bulk_load_s(uint32_t dst_s, const void* src, uint32_t bytes, uint32_t bar_s) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s), "l"(src),
+                 "r"(bytes), "r"(bar_s)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(uint32_t bar_s, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t"
+        "}" ::"r"(bar_s),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void lds_32B(uint32_t addr_s, uint64_t (&v)[4]) {
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v[0]), "=l"(v[1]) : "r"(addr_s) : "memory");
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2+16];" : "=l"(v[2]), "=l"(v[3]) : "r"(addr_s) : "memory");
+}
+}  // namespace b5
+
+template <bool USE_RING, bool HAS_HYPS>
+__global__ void __launch_bounds__(b5::THREADS, 2)
+costvol_grouped_bwd_v5_kernel(const CvArgs a, int nch, int xblocks, int ntasks, float cu, float ru, float cv, float rv) {
+    using namespace b5;
+    using f3::rcp_approx;
+    extern __shared__ __align__(128) unsigned char smem5[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane & 1;
+    constexpr bool use_ring = USE_RING;
+    const uint32_t ring_s = smem_u32(smem5 + warp * (RING * PIXW * 64));
+    const uint32_t bars_s = smem_u32(smem5 + WARPS * RING * PIXW * 64) + warp * RING * 8;
+    if (use_ring) {
+        if (lane == 0) {
+            for (int s0 = 0; s0 < RING; ++s0) mbar_init(reinterpret_cast<uint64_t*>(smem5 + WARPS * RING * PIXW * 64) + warp * RING + s0, 1);
+            mbar_fence_init();
+        }
+        __syncwarp();
+    }
+    uint32_t st = 0, par = 0;                                // ring stage / parity of the next hypothesis to consume
+    const int hw = a.h * a.w;
+    for (int task = blockIdx.x * WARPS + warp; task < ntasks; task += gridDim.x * WARPS) {
+        const Task k = task_of(a, task, nch, xblocks);
+        const int b = k.b, x = k.x0 + (lane >> 1);
+        const bool lane_ok = x < a.w;
+        const int pix = k.y * a.w + (lane_ok ? x : a.w - 1);
+        const int n = k.d1 - k.d0;
+        const float* gbase = a.gout + static_cast<size_t>(b) * CV_G * a.D * hw;
+        // ring: the warp's run of hypothesis d starts at pixel (y, x0): npx pixels of 64 B; lane 0 keeps the issue cursor
+        const uint32_t run_bytes = static_cast<uint32_t>(min(PIXW, a.w - k.x0)) * 64u;
+        const float* run_next = gbase + (static_cast<size_t>(k.d0) * hw + k.y * a.w + k.x0) * CV_G;
+        const size_t run_stride = static_cast<size_t>(hw) * CV_G;
+        int to_issue = n;
+        if (use_ring && lane == 0) {
+            uint32_t s1 = st;
+            for (int j = 0; j < RING && j < n; ++j) {
+                bulk_load_s(ring_s + s1 * (PIXW * 64), run_next, run_bytes, bars_s + s1 * 8);
+                run_next += run_stride;
+                --to_issue;
+                s1 = (s1 + 1 == RING) ? 0 : s1 + 1;
+            }
+        }
+
+        // p(depth) = depth * (K T)[:3,:3] inv_K[:3,:3] (x,y,1) + (K T)[:3,3]   (movedepth/layers.py:581-621), as the forward
+        f3::Geom c;
+        {
+            float P[12];
+            const float* Kb = a.K + b * 16;
+            const float* Tb = a.T + b * 16;
+#pragma unroll
+            for (int q = 0; q < 12; ++q) {
+                const int i = q >> 2, j = q & 3;
+                float v = 0.f;
+#pragma unroll
+                for (int m = 0; m < 4; ++m) v = fmaf(__ldg(Kb + i * 4 + m), __ldg(Tb + m * 4 + j), v);
+                P[q] = v;
+            }
+            const float* iK = a.invK + b * 16;
+            const float xf = static_cast<float>(x), yf = static_cast<float>(k.y);
+            const float rx = fmaf(__ldg(iK + 0), xf, fmaf(__ldg(iK + 1), yf, __ldg(iK + 2)));
+            const float ry = fmaf(__ldg(iK + 4), xf, fmaf(__ldg(iK + 5), yf, __ldg(iK + 6)));
+            const float rz = fmaf(__ldg(iK + 8), xf, fmaf(__ldg(iK + 9), yf, __ldg(iK + 10)));
+            c.mrx = fmaf(P[0], rx, fmaf(P[1], ry, P[2] * rz));
+            c.mry = fmaf(P[4], rx, fmaf(P[5], ry, P[6] * rz));
+            c.mrz = fmaf(P[8], rx, fmaf(P[9], ry, P[10] * rz));
+            c.tx = P[3];
+            c.ty = P[7];
+            c.tz = P[11];
+        }
+        const float prior_v = HAS_HYPS ? 0.f : __ldg(a.prior + static_cast<size_t>(b) * hw + pix);
+        // depth of hypothesis d: hyps[b, d, pixel] or prior * ratio[b, d]; dp walks it with stride dstep
+        const float* dp = HAS_HYPS ? a.hyps + (static_cast<size_t>(b) * a.D + k.d0) * hw + pix : a.ratio + static_cast<size_t>(b) * a.D + k.d0;
+        const int dstep = HAS_HYPS ? hw : 1;
+        const float4* rg = reinterpret_cast<const float4*>(a.ref + (static_cast<size_t>(b) * hw + pix) * CV_C) + 2 * half;
+
+        uint64_t Q2[4][4];
+#pragma unroll
+        for (int tt = 0; tt < 4; ++tt)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) Q2[tt][q] = 0ull;
+        float gr[16];                                        // d ref of channels 8h..8h+7 and 16+8h..16+8h+7 (x2, applied at the end)
+#pragma unroll
+        for (int q = 0; q < 16; ++q) gr[q] = 0.f;
+        int cx = INT_MIN, cy = INT_MIN;
+        auto flush = [&]() {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int px = cx + (t & 1), py = cy + (t >> 1);
+                float Q[8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    unpk2(Q2[t][q], Q[2 * q], Q[2 * q + 1]);
+                    Q2[t][q] = 0ull;
+                }
+                if (px < 0 || px >= a.w || py < 0 || py >= a.h) continue;         // zero padding: no source pixel behind this tap
+                const size_t sp = (static_cast<size_t>(b * a.h + py) * a.w + px) * CV_C;
+                const float4* g = reinterpret_cast<const float4*>(a.src + sp) + 2 * half;
+                float4* gs = reinterpret_cast<float4*>(a.gsrc + sp) + 2 * half;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const float4 rl = __ldg(rg + j), rh = __ldg(rg + j + 4), lo = __ldg(g + j), hi = __ldg(g + j + 4);
+                    const float q0 = Q[4 * j], q1 = Q[4 * j + 1], q2 = Q[4 * j + 2], q3 = Q[4 * j + 3];
+                    gr[4 * j + 0] = fmaf(q0, lo.x, gr[4 * j + 0]);
+                    gr[4 * j + 1] = fmaf(q1, lo.y, gr[4 * j + 1]);
+                    gr[4 * j + 2] = fmaf(q2, lo.z, gr[4 * j + 2]);
+                    gr[4 * j + 3] = fmaf(q3, lo.w, gr[4 * j + 3]);
+                    gr[8 + 4 * j + 0] = fmaf(q0, hi.x, gr[8 + 4 * j + 0]);
+                    gr[8 + 4 * j + 1] = fmaf(q1, hi.y, gr[8 + 4 * j + 1]);
+                    gr[8 + 4 * j + 2] = fmaf(q2, hi.z, gr[8 + 4 * j + 2]);
+                    gr[8 + 4 * j + 3] = fmaf(q3, hi.w, gr[8 + 4 * j + 3]);
+                    const float h0 = 0.5f * q0, h1 = 0.5f * q1, h2 = 0.5f * q2, h3 = 0.5f * q3;
+                    atomicAdd(gs + j, make_float4(h0 * rl.x, h1 * rl.y, h2 * rl.z, h3 * rl.w));
+                    atomicAdd(gs + j + 4, make_float4(h0 * rh.x, h1 * rh.y, h2 * rh.z, h3 * rh.w));
+                }
+            }
+        };
+        // one hypothesis: projection, cell bookkeeping, Q += w (x) gout
+        auto consume = [&](float depth, bool valid, const uint64_t (&go)[4]) {
+            const float inv = rcp_approx(fmaf(depth, c.mrz, c.tz) + 1e-7f);
+            const float uu = fmaf(depth, c.mrx, c.tx) * inv, vv = fmaf(depth, c.mry, c.ty) * inv;
+            const bool ok = lane_ok && valid && (fabsf(uu - cu) < ru) && (fabsf(vv - cv) < rv);
+            if (ok) {
+                const float x0 = floorf(uu), y0 = floorf(vv);
+                const float wx1 = uu - x0, wx0 = (x0 + 1.f) - uu, wy1 = vv - y0, wy0 = (y0 + 1.f) - vv;
+                const int ix = static_cast<int>(x0), iy = static_cast<int>(y0);
+                if (ix != cx || iy != cy) {
+                    if (cx != INT_MIN) flush();
+                    cx = ix;
+                    cy = iy;
+                }
+                const float a00 = wx0 * wy0, a01 = wx1 * wy0, a10 = wx0 * wy1, a11 = wx1 * wy1;
+                const uint64_t w00 = pk2(a00, a00), w01 = pk2(a01, a01), w10 = pk2(a10, a10), w11 = pk2(a11, a11);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    Q2[0][q] = fma2(w00, go[q], Q2[0][q]);
+                    Q2[1][q] = fma2(w01, go[q], Q2[1][q]);
+                    Q2[2][q] = fma2(w10, go[q], Q2[2][q]);
+                    Q2[3][q] = fma2(w11, go[q], Q2[3][q]);
+                }
+            }
+        };
+
+        if constexpr (use_ring) {
+            const uint32_t lane_off = static_cast<uint32_t>(lane) * 32u;
+#pragma unroll 1
+            for (int i = 0; i < n; ++i) {
+                const float dv = __ldg(dp);
+                dp += dstep;
+                const float depth = HAS_HYPS ? dv : prior_v * dv;
+                mbar_wait_s(bars_s + st * 8, par);
+                uint64_t go[4];
+                lds_32B(ring_s + st * (PIXW * 64) + lane_off, go);   // lanes past the row end read stale bytes; never used (lane_ok)
+                // The stage may be refilled only when every lane's loads have RETURNED: a warp barrier alone orders their issue,
+                // not their completion, and a 1 KB copy from the L2 can land first (measured: ~7 % of runs had corrupted pixels in
+                // the L2-resident part of the volume).  The vote consumes one register of each 16 B load, so it cannot execute
+                // before the data is there; the proxy fence orders those generic-proxy reads before the async-proxy write.
+                asm volatile(
+                    "{\n\t"
+                    ".reg .pred p;\n\t"
+                    ".reg .b32 r;\n\t"
+                    ".reg .b64 t;\n\t"
+                    "or.b64 t, %0, %1;\n\t"
+                    "setp.ne.b64 p, t, 0;\n\t"
+                    "vote.sync.ballot.b32 r, p, 0xffffffff;\n\t"
+                    "}" ::"l"(go[0]),
+                    "l"(go[2])
+                    : "memory");
+                if (lane == 0 && to_issue > 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    bulk_load_s(ring_s + st * (PIXW * 64), run_next, run_bytes, bars_s + st * 8);
+                    run_next += run_stride;
+                    --to_issue;
+                }
+                if (++st == RING) {
+                    st = 0;
+                    par ^= 1u;
+                }
+                consume(depth, true, go);
+            }
+        } else {
+#pragma unroll 1
+            for (int i0 = 0; i0 < n; i0 += GOB) {
+                uint64_t go2[GOB][4];
+                float depth[GOB];
+#pragma unroll
+                for (int u = 0; u < GOB; ++u) {
+                    const int du = min(i0 + u, n - 1);
+                    const float* gp = gbase + (static_cast<size_t>(8 * half) * a.D + k.d0 + du) * hw + pix;
+                    const size_t gs = static_cast<size_t>(a.D) * hw;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) go2[u][q] = pk2(__ldg(gp + (2 * q) * gs), __ldg(gp + (2 * q + 1) * gs));
+                    const float dv = __ldg(dp + static_cast<size_t>(du) * dstep);
+                    depth[u] = HAS_HYPS ? dv : prior_v * dv;
+                }
+#pragma unroll
+                for (int u = 0; u < GOB; ++u) consume(depth[u], i0 + u < n, go2[u]);
+            }
+        }
+        if (cx != INT_MIN) flush();
+        if (lane_ok) {                                       // chunks of one pixel meet in global memory
+            float4* grp = reinterpret_cast<float4*>(a.gref + (static_cast<size_t>(b) * hw + pix) * CV_C) + 2 * half;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                atomicAdd(grp + j, make_float4(0.5f * gr[4 * j], 0.5f * gr[4 * j + 1], 0.5f * gr[4 * j + 2], 0.5f * gr[4 * j + 3]));
+                atomicAdd(grp + j + 4, make_float4(0.5f * gr[8 + 4 * j], 0.5f * gr[8 + 4 * j + 1], 0.5f * gr[8 + 4 * j + 2], 0.5f * gr[8 + 4 * j + 3]));
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host
 static int costvol_grouped_launch(bool bwd, CvArgs a, int C, int G, int flags, cudaStream_t st) {
     MVD_REQUIRE(C == CV_C && G == CV_G, "grouped cost volume is built for C=32, G=16 (got C=%d, G=%d)", C, G);
@@ -926,7 +1194,7 @@ static int costvol_grouped_launch(bool bwd, CvArgs a, int C, int G, int flags, c
 
     CUtensorMap map_src, map_ref;
     int rc;
-    if (bwd) {
+    if (bwd && (flags & MVD_FLAG_BWD_V2)) {          // the round-1 kernel (A/B measurements)
         a.tiles_y = (a.h + CV_R - 1) / CV_R;
         a.num_tiles = a.tiles_x * a.tiles_y * a.B;
         a.DC = (a.D + CV_NCH - 1) / CV_NCH;
@@ -939,15 +1207,39 @@ static int costvol_grouped_launch(bool bwd, CvArgs a, int C, int G, int flags, c
         cudaError_t e = cudaMemsetAsync(a.gref, 0, sizeof(float) * a.B * a.h * a.w * CV_C, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(a.gsrc, 0, sizeof(float) * a.B * a.h * a.w * CV_C, st);
         if (e != cudaSuccess) return fail(static_cast<int>(e), "costvol bwd memset: %s", cudaGetErrorString(e));
-        bool attr_done = false;       // per call: the attribute is per device, a process-wide latch is not
-        if (!attr_done) {
-            cudaFuncSetAttribute(costvol_grouped_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            attr_done = true;
-        }
+        cudaFuncSetAttribute(costvol_grouped_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         costvol_grouped_bwd_kernel<<<grid, CV_THREADS, smem, st>>>(map_src, map_ref, a);
         return check_launch("costvol_grouped_bwd");
     }
-
+    if (bwd) {                                       // v5: warp-autonomous
+        const int nch = a.D >= 64 ? ((flags >> 8) & 15 ? (flags >> 8) & 15 : 3) : 1;      // bits 8..11: chunk count override (tuning)
+        a.DC = (a.D + nch - 1) / nch;
+        const int xblocks = (a.w + b5::PIXW - 1) / b5::PIXW;
+        const long long ntasks = static_cast<long long>(a.B) * a.h * xblocks * nch;
+        MVD_REQUIRE(ntasks < (1ll << 31), "too many tiles");
+        cudaError_t e = cudaMemsetAsync(a.gref, 0, sizeof(float) * a.B * a.h * a.w * CV_C, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(a.gsrc, 0, sizeof(float) * a.B * a.h * a.w * CV_C, st);
+        if (e != cudaSuccess) return fail(static_cast<int>(e), "costvol bwd memset: %s", cudaGetErrorString(e));
+        const int blocks = static_cast<int>((ntasks + b5::WARPS - 1) / b5::WARPS);
+        const int grid = min(blocks, sm_count() * 2);
+        // |u - (w-1)/2| < (w+1)/2  <=>  -1 < u < w: the forward's in-image test, constants passed as kernel parameters
+        const float cu = 0.5f * static_cast<float>(a.w - 1), ru = 0.5f * static_cast<float>(a.w + 1);
+        const float cv = 0.5f * static_cast<float>(a.h - 1), rv = 0.5f * static_cast<float>(a.h + 1);
+        const int nt = static_cast<int>(ntasks);
+        const bool ring = a.layout == MVD_LAYOUT_BDHWG;      // channels-last gradient: 1 KB runs through the per-warp bulk-copy ring
+        const size_t smem = ring ? b5::SMEM : 0;
+#define MVD_LAUNCH_V5(R, H)                                                                                                    \
+    do {                                                                                                                       \
+        if (R) cudaFuncSetAttribute(costvol_grouped_bwd_v5_kernel<R, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, b5::SMEM); \
+        costvol_grouped_bwd_v5_kernel<R, H><<<grid, b5::THREADS, smem, st>>>(a, nch, xblocks, nt, cu, ru, cv, rv);             \
+    } while (0)
+        if (ring && a.hyps) MVD_LAUNCH_V5(true, true);
+        else if (ring) MVD_LAUNCH_V5(true, false);
+        else if (a.hyps) MVD_LAUNCH_V5(false, true);
+        else MVD_LAUNCH_V5(false, false);
+#undef MVD_LAUNCH_V5
+        return check_launch("costvol_grouped_bwd_v5");
+    }
     // forward: the kernel keeps the geometry of every batch item in shared memory -> at most MAXB items per launch
     if (a.B > f3::MAXB) {
         for (int b0 = 0; b0 < a.B; b0 += f3::MAXB) {

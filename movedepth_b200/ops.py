@@ -13,6 +13,7 @@ LAYOUT_BGDHW = 0
 LAYOUT_BDHWG = 1
 FLAG_NO_TMA = 1
 FLAG_NO_TABLE = 2
+FLAG_BWD_V2 = 32        # backward: the round-1 kernel (A/B runs)
 
 # counts kernel launches issued through the C ABI (bench.py reports it as `gpu_launches`)
 launch_counter = {"n": 0}

@@ -137,6 +137,44 @@ def test_costvol_grouped_linearity_at_full_size(ops):
     assert lhs.shape == (6, 16, 96, 48, 160)
 
 
+@pytest.mark.parametrize("name,shape", [("forward", (2, 7, 45, 5)), ("sideways", (19, 8, 64, 8)), ("stress", (1, 48, 160, 96)),
+                                        ("forward", (2, 48, 160, 96))], ids=["ragged", "19-items", "stress-full", "config2"])
+def test_costvol_backward_streaming_kernel_agrees_with_the_round1_kernel(ops, name, shape):
+    """K1b v5 (warp-autonomous: lane pair per pixel, long hypothesis chunks, gradients streamed through a per-warp bulk-copy ring
+    in the channels-last layout / four hypotheses in flight through registers otherwise) vs the round-1 kernel (MVD_FLAG_BWD_V2:
+    eight short chunks per pixel, one hypothesis in flight) on the same inputs: same sums in a different order.  Repeated: the
+    ring's refill race showed up in ~7 % of runs before the loads were forced to complete ahead of the refill."""
+    B, h, w, D = shape
+    c = C.case_costvol(name, B=B, h=h, w=w, D=D)
+    gv = g(torch.randn((B, 16, D, h, w), generator=torch.Generator().manual_seed(6)))
+    grads = []
+    for flags in (32, 0, 0x100, 0x400, 0, 0, 0, 0):                    # v2 / v5 (3 chunks) / 1 chunk / 4 chunks / v5 again x4
+        for layout in (0, 1):
+            ref, src = g(c["ref"]).requires_grad_(True), g(c["src"]).requires_grad_(True)
+            got = ops.costvol_grouped(ref, src, g(c["K"]), g(c["invK"]), g(c["pose"][:, 0]), prior=g(c["prior"]), ratio=g(c["ratio"]),
+                                      layout=layout, flags=flags)
+            (got * gv).sum().backward()
+            grads.append((ref.grad, src.grad))
+    for gr, gs in grads[1:]:
+        torch.testing.assert_close(gr, grads[0][0], atol=2e-5 * float(grads[0][0].abs().max()), rtol=1e-4)
+        torch.testing.assert_close(gs, grads[0][1], atol=2e-5 * float(grads[0][1].abs().max()), rtol=1e-4)
+
+
+def test_costvol_backward_euler_identity_at_full_size(ops):
+    """Size-independent property of the adjoint at BASELINE config 2 (B=6, 48x160, D=96): the volume is linear in ref and in
+    src, so <d ref, ref> = <d src, src> = <V, G> for any upstream gradient G (fp64 sums of fp32 products)."""
+    c = C.case_costvol("forward", B=6, h=48, w=160, D=96)
+    ref, src = g(c["ref"]).requires_grad_(True), g(c["src"]).requires_grad_(True)
+    vol = ops.costvol_grouped(ref, src, g(c["K"]), g(c["invK"]), g(c["pose"][:, 0]), prior=g(c["prior"]), ratio=g(c["ratio"]), layout=1)
+    gv = torch.randn(vol.shape, device=DEV, generator=torch.Generator(device=DEV).manual_seed(8))
+    (vol * gv).sum().backward()
+    want = float((vol.detach().double() * gv.double()).sum())
+    a = float((ref.grad.double() * ref.detach().double()).sum())
+    b = float((src.grad.double() * src.detach().double()).sum())
+    scale = float((vol.detach().double() * gv.double()).abs().sum())
+    assert abs(a - want) < 1e-6 * scale and abs(b - want) < 1e-6 * scale, (a, b, want, scale)
+
+
 @pytest.mark.parametrize("name", C.COSTVOL_CASES)
 def test_costvol_full_matches_reference_golden(ops, gold, name):
     """public generate_costvol layout [B,D,C,h,w] against the reference's own output."""
