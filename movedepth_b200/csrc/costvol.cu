@@ -1217,8 +1217,14 @@ static int costvol_grouped_launch(bool bwd, CvArgs a, int C, int G, int flags, c
         const int xblocks = (a.w + b5::PIXW - 1) / b5::PIXW;
         const long long ntasks = static_cast<long long>(a.B) * a.h * xblocks * nch;
         MVD_REQUIRE(ntasks < (1ll << 31), "too many tiles");
-        cudaError_t e = cudaMemsetAsync(a.gref, 0, sizeof(float) * a.B * a.h * a.w * CV_C, st);
-        if (e == cudaSuccess) e = cudaMemsetAsync(a.gsrc, 0, sizeof(float) * a.B * a.h * a.w * CV_C, st);
+        const size_t gcount = static_cast<size_t>(a.B) * a.h * a.w * CV_C;
+        cudaError_t e;
+        if (a.gsrc == a.gref + gcount) {             // adjacent gradient buffers (what ops.py allocates): one memset node
+            e = cudaMemsetAsync(a.gref, 0, sizeof(float) * 2 * gcount, st);
+        } else {
+            e = cudaMemsetAsync(a.gref, 0, sizeof(float) * gcount, st);
+            if (e == cudaSuccess) e = cudaMemsetAsync(a.gsrc, 0, sizeof(float) * gcount, st);
+        }
         if (e != cudaSuccess) return fail(static_cast<int>(e), "costvol bwd memset: %s", cudaGetErrorString(e));
         const int blocks = static_cast<int>((ntasks + b5::WARPS - 1) / b5::WARPS);
         const int grid = min(blocks, sm_count() * 2);

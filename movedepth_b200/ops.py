@@ -109,13 +109,13 @@ class _CostVolumeGrouped(torch.autograd.Function):
         ref_cl, src_cl, prior_c, ratio_c, hyps, K, invK, T = ctx.saved_tensors
         B, C, groups, h, w, D, layout, flags, fmt = ctx.meta
         gout = _f32(gout).contiguous(memory_format=fmt)
-        gref = torch.empty_like(ref_cl)
-        gsrc = torch.empty_like(src_cl)
+        both = torch.empty((2, B, h, w, C), device=ref_cl.device, dtype=ref_cl.dtype).permute(0, 1, 4, 2, 3)
+        gref, gsrc = both[0], both[1]                              # channels-last like ref / src; adjacent: one memset in the library
         rc = _lib.lib().mvd_costvol_grouped_bwd(_p(gout), _p(ref_cl), _p(src_cl), _p(prior_c), _p(ratio_c), _p(hyps),
                                                 _p(K), _p(invK), _p(T), _p(gref), _p(gsrc), B, C, groups, h, w, D,
                                                 layout, flags, _stream())
         _lib.check(rc, "mvd_costvol_grouped_bwd")
-        launch_counter["n"] += 3
+        launch_counter["n"] += 2
         return gref, gsrc, None, None, None, None, None, None, None, None, None
 
 
