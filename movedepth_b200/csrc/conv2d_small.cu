@@ -82,11 +82,11 @@ __global__ void __launch_bounds__(128) small_fwd_kernel(const Args a) {
         }
     }
     __syncthreads();
-    float acc[PR][COUT];
+    uint64_t acc2[PR][COUT / 2];                 // packed output-channel pairs: one FFMA2 = two of the FMAs (Blackwell fp32x2)
 #pragma unroll
     for (int p = 0; p < PR; ++p)
 #pragma unroll
-        for (int co = 0; co < COUT; ++co) acc[p][co] = 0.f;
+        for (int co = 0; co < COUT / 2; ++co) acc2[p][co] = 0ull;
     const float* xt = xs + (q * PR * S) * CF::IWP + lane * S;
 #pragma unroll 1
     for (int ci = 0; ci < CIN; ++ci) {
@@ -100,14 +100,12 @@ __global__ void __launch_bounds__(128) small_fwd_kernel(const Args a) {
                 const float* wp = ws + ((ky * K + kx) * CIN + ci) * COUT;
 #pragma unroll
                 for (int c4 = 0; c4 < COUT; c4 += 4) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(wp + c4);
+                    const ulonglong2 w4 = *reinterpret_cast<const ulonglong2*>(wp + c4);
 #pragma unroll
                     for (int p = 0; p < PR; ++p) {
-                        const float v = xv[p * S + ky];
-                        acc[p][c4 + 0] = fmaf(v, w4.x, acc[p][c4 + 0]);
-                        acc[p][c4 + 1] = fmaf(v, w4.y, acc[p][c4 + 1]);
-                        acc[p][c4 + 2] = fmaf(v, w4.z, acc[p][c4 + 2]);
-                        acc[p][c4 + 3] = fmaf(v, w4.w, acc[p][c4 + 3]);
+                        const uint64_t v = pk2(xv[p * S + ky], xv[p * S + ky]);
+                        acc2[p][c4 / 2] = fma2(v, w4.x, acc2[p][c4 / 2]);
+                        acc2[p][c4 / 2 + 1] = fma2(v, w4.y, acc2[p][c4 / 2 + 1]);
                     }
                 }
             }
@@ -121,7 +119,8 @@ __global__ void __launch_bounds__(128) small_fwd_kernel(const Args a) {
             if (oy < a.Ho) {
                 float4* yp = reinterpret_cast<float4*>(a.y + ((static_cast<size_t>(b) * a.Ho + oy) * a.Wo + ox) * COUT);
 #pragma unroll
-                for (int c4 = 0; c4 < COUT; c4 += 4) yp[c4 >> 2] = make_float4(acc[p][c4], acc[p][c4 + 1], acc[p][c4 + 2], acc[p][c4 + 3]);
+                for (int c4 = 0; c4 < COUT; c4 += 4)
+                    reinterpret_cast<ulonglong2*>(yp)[c4 >> 2] = make_ulonglong2(acc2[p][c4 / 2], acc2[p][c4 / 2 + 1]);
             }
         }
     }
@@ -176,9 +175,9 @@ __global__ void __launch_bounds__(128) small_dgrad_s2_kernel(const Args a) {   /
 #pragma unroll 1
         for (int px = 0; px < 2; ++px) {
             const int ix = ix0 + 2 * lane + px;
-            float acc[CIN];
+            uint64_t acc2[CIN / 2];
 #pragma unroll
-            for (int ci = 0; ci < CIN; ++ci) acc[ci] = 0.f;
+            for (int ci = 0; ci < CIN / 2; ++ci) acc2[ci] = 0ull;
             for (int ky = (iy + P) & 1; ky < K; ky += 2) {
                 const int r = (iy + P - ky) / 2 - oy_base;           // iy + P - ky is even and may be negative only outside the tile
                 if ((iy + P - ky) < 0) continue;
@@ -188,14 +187,13 @@ __global__ void __launch_bounds__(128) small_dgrad_s2_kernel(const Args a) {   /
                     const float* wp = ws + (ky * K + kx) * COUT * CIN;
 #pragma unroll 4
                     for (int co = 0; co < COUT; ++co) {
-                        const float g = gs[(co * CF::GH + r) * CF::GWP + c];
+                        const float g1 = gs[(co * CF::GH + r) * CF::GWP + c];
+                        const uint64_t g = pk2(g1, g1);
 #pragma unroll
                         for (int c4 = 0; c4 < CIN; c4 += 4) {
-                            const float4 w4 = *reinterpret_cast<const float4*>(wp + co * CIN + c4);
-                            acc[c4 + 0] = fmaf(g, w4.x, acc[c4 + 0]);
-                            acc[c4 + 1] = fmaf(g, w4.y, acc[c4 + 1]);
-                            acc[c4 + 2] = fmaf(g, w4.z, acc[c4 + 2]);
-                            acc[c4 + 3] = fmaf(g, w4.w, acc[c4 + 3]);
+                            const ulonglong2 w4 = *reinterpret_cast<const ulonglong2*>(wp + co * CIN + c4);
+                            acc2[c4 / 2] = fma2(g, w4.x, acc2[c4 / 2]);
+                            acc2[c4 / 2 + 1] = fma2(g, w4.y, acc2[c4 / 2 + 1]);
                         }
                     }
                 }
@@ -203,7 +201,7 @@ __global__ void __launch_bounds__(128) small_dgrad_s2_kernel(const Args a) {   /
             if (iy < a.H && ix < a.W) {
                 float4* op = reinterpret_cast<float4*>(a.y + ((static_cast<size_t>(b) * a.H + iy) * a.W + ix) * CIN);
 #pragma unroll
-                for (int c4 = 0; c4 < CIN; c4 += 4) op[c4 >> 2] = make_float4(acc[c4], acc[c4 + 1], acc[c4 + 2], acc[c4 + 3]);
+                for (int c4 = 0; c4 < CIN; c4 += 4) reinterpret_cast<ulonglong2*>(op)[c4 >> 2] = make_ulonglong2(acc2[c4 / 2], acc2[c4 / 2 + 1]);
             }
         }
     }
@@ -242,9 +240,9 @@ __global__ void __launch_bounds__(WgCfg<CIN, COUT, K, S>::THREADS) small_wgrad_k
     const int pair = tid % CF::NT, grp = tid / CF::NT;
     const int ci = pair % CIN, tap = pair / CIN, ky = tap / K, kx = tap % K;
     constexpr int P = K / 2;
-    float acc[COUT];
+    uint64_t acc2[COUT / 2];                     // packed output-channel pairs
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) acc[co] = 0.f;
+    for (int co = 0; co < COUT / 2; ++co) acc2[co] = 0ull;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
         const int tx = tile % a.tiles_x, ty = (tile / a.tiles_x) % a.tiles_y, b = tile / (a.tiles_x * a.tiles_y);
         const int ox0 = tx * CF::TW, oy0 = ty * CF::TH;
@@ -282,21 +280,20 @@ __global__ void __launch_bounds__(WgCfg<CIN, COUT, K, S>::THREADS) small_wgrad_k
         for (int p = grp; p < CF::TH * CF::TW; p += CF::PG) {
             const int r = p / CF::TW, c = p % CF::TW;                           // TW = 32: shift / mask
             const float v = xb[((r * S) * CF::IW + c * S) * CIN];
+            const uint64_t vv = pk2(v, v);
             const float* gp = gs + p * COUT;
 #pragma unroll
             for (int c4 = 0; c4 < COUT; c4 += 4) {
-                const float4 g4 = *reinterpret_cast<const float4*>(gp + c4);
-                acc[c4 + 0] = fmaf(v, g4.x, acc[c4 + 0]);
-                acc[c4 + 1] = fmaf(v, g4.y, acc[c4 + 1]);
-                acc[c4 + 2] = fmaf(v, g4.z, acc[c4 + 2]);
-                acc[c4 + 3] = fmaf(v, g4.w, acc[c4 + 3]);
+                const ulonglong2 g4 = *reinterpret_cast<const ulonglong2*>(gp + c4);
+                acc2[c4 / 2] = fma2(vv, g4.x, acc2[c4 / 2]);
+                acc2[c4 / 2 + 1] = fma2(vv, g4.y, acc2[c4 / 2 + 1]);
             }
         }
     }
     // reduce the pixel groups through shared memory, then one partial per CTA
     __syncthreads();
     float* red = smem;                 // [PG][NT][COUT] <= THREADS * COUT floats; fits: checked by the host
-    for (int co = 0; co < COUT; ++co) red[(grp * CF::NT + pair) * COUT + co] = acc[co];
+    for (int co = 0; co < COUT / 2; ++co) unpk2(acc2[co], red[(grp * CF::NT + pair) * COUT + 2 * co], red[(grp * CF::NT + pair) * COUT + 2 * co + 1]);
     __syncthreads();
     for (int e = tid; e < CF::NT * COUT; e += CF::THREADS) {
         const int co = e % COUT, pr = e / COUT;

@@ -30,6 +30,8 @@ constexpr int THREADS = TH * TW;               // 256
 constexpr int NW = C * 27;                     // 432 weights, index c*27 + kd*9 + kh*3 + kw
 
 __constant__ float c_w[NW];
+__constant__ __align__(16) float c_wt[NW];         // the same weights tap-major, index tap*16 + c: channel pairs for the packed FMAs
+__device__ float g_wt[NW];                          // staging for c_wt (written by transpose_w_kernel)
 
 struct Args {
     const float* x;
@@ -74,6 +76,13 @@ __device__ __forceinline__ float4 lds_x(const unsigned char* buf, int p, int q) 
     return *reinterpret_cast<const float4*>(buf + p * 64 + ((q ^ ((p >> 1) & 3)) << 4));
 }
 
+// the same 16 B as two packed channel pairs, through an explicit shared-window address (a generic pointer costs a generic LD)
+__device__ __forceinline__ ulonglong2 lds_x2(uint32_t buf_s, int p, int q) {
+    ulonglong2 v;
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(buf_s + p * 64 + ((q ^ ((p >> 1) & 3)) << 4)));
+    return v;
+}
+
 __device__ __forceinline__ void issue_slice(const CUtensorMap* map, unsigned char* buf, uint64_t* bar, const Item& it, int s) {
     mbar_expect_tx(bar, SLICE_POS * 64);
     tma_load_5d(buf, map, bar, 0, it.w0 - 1, it.h0 - 1, s, it.b);
@@ -100,10 +109,15 @@ conv3d_c16o1_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const Args a)
     const bool inside = h < a.H && w < a.W;
     float* yp = a.y + (static_cast<size_t>(it.b) * a.D * a.H + h) * a.W + w;       // + d*H*W
     const size_t dstride = static_cast<size_t>(a.H) * a.W;
-    float acc_prev = 0.f, acc_cur = 0.f, acc_next = 0.f;       // outputs d = s-1 (kd=2), s (kd=1), s+1 (kd=0)
+    // Packed fp32 math: an accumulator is the pair (even channels' sum, odd channels' sum); one FFMA2 multiplies a channel pair
+    // of x (a 64-bit half of the 16 B shared-memory load) by the weight pair held in a uniform register (LDCU from c_wt):
+    // 216 FFMA2 + 108 LDCU per output instead of 432 FFMA.
+    const uint64_t* w2 = reinterpret_cast<const uint64_t*>(c_wt);   // [tap][8 channel pairs]
+    const uint32_t smem_s = smem_u32(smem);
+    uint64_t acc_prev = 0ull, acc_cur = 0ull, acc_next = 0ull;      // outputs d = s-1 (kd=2), s (kd=1), s+1 (kd=0)
     for (int i = 0; i < count; ++i) {
         const int s = it.d0 - 1 + i, bi = i % NBUF;
-        const unsigned char* buf = smem + bi * SLICE_BYTES;
+        const uint32_t buf_s = smem_s + bi * SLICE_BYTES;
         mbar_wait(full + bi, (i / NBUF) & 1);
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh)
@@ -112,21 +126,23 @@ conv3d_c16o1_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const Args a)
                 const int p = (hh + kh) * HW + ww + kw, t = kh * 3 + kw;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float4 v = lds_x(buf, p, q);
-                    const float e[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int c = 4 * q + k;
-                        acc_prev = fmaf(e[k], c_w[c * 27 + 18 + t], acc_prev);
-                        acc_cur = fmaf(e[k], c_w[c * 27 + 9 + t], acc_cur);
-                        acc_next = fmaf(e[k], c_w[c * 27 + t], acc_next);
-                    }
+                    const ulonglong2 v = lds_x2(buf_s, p, q);
+                    acc_prev = fma2(v.x, w2[(18 + t) * 8 + 2 * q], acc_prev);
+                    acc_prev = fma2(v.y, w2[(18 + t) * 8 + 2 * q + 1], acc_prev);
+                    acc_cur = fma2(v.x, w2[(9 + t) * 8 + 2 * q], acc_cur);
+                    acc_cur = fma2(v.y, w2[(9 + t) * 8 + 2 * q + 1], acc_cur);
+                    acc_next = fma2(v.x, w2[t * 8 + 2 * q], acc_next);
+                    acc_next = fma2(v.y, w2[t * 8 + 2 * q + 1], acc_next);
                 }
             }
-        if (s - 1 >= it.d0 && inside) yp[(s - 1) * dstride] = acc_prev;
+        if (s - 1 >= it.d0 && inside) {
+            float even, odd;
+            unpk2(acc_prev, even, odd);
+            yp[(s - 1) * dstride] = even + odd;
+        }
         acc_prev = acc_cur;
         acc_cur = acc_next;
-        acc_next = 0.f;
+        acc_next = 0ull;
         __syncthreads();                                       // everyone is done with this buffer
         if (tid == 0 && i + NBUF < count) issue_slice(&map_x, smem + bi * SLICE_BYTES, full + bi, it, s + NBUF);
     }
@@ -161,9 +177,10 @@ conv3d_c16o1_dgrad_kernel(const Args a) {
     for (int d = it.d0; d < it.d1; ++d) {
         load_gy_slice(a, it, d + 1, gys[(d + 2) & 3], tid, 0, a.D);
         __syncthreads();
-        float acc[C];
+        const uint64_t* w2 = reinterpret_cast<const uint64_t*>(c_wt);   // [tap][8 channel pairs]
+        uint64_t acc2[C / 2];                                  // packed channel pairs: 216 FFMA2 per position instead of 432 FFMA
 #pragma unroll
-        for (int c = 0; c < C; ++c) acc[c] = 0.f;
+        for (int c = 0; c < C / 2; ++c) acc2[c] = 0ull;
 #pragma unroll
         for (int kd = 0; kd < 3; ++kd) {
             const float* g = gys[(d - kd + 2) & 3];            // slice d - kd + 1
@@ -172,10 +189,14 @@ conv3d_c16o1_dgrad_kernel(const Args a) {
 #pragma unroll
                 for (int kw = 0; kw < 3; ++kw) {
                     const float v = g[(hh + 2 - kh) * HW + ww + 2 - kw];   // (h - kh + 1, w - kw + 1) in halo coordinates
+                    const uint64_t vv = pk2(v, v);
 #pragma unroll
-                    for (int c = 0; c < C; ++c) acc[c] = fmaf(v, c_w[c * 27 + kd * 9 + kh * 3 + kw], acc[c]);
+                    for (int c = 0; c < C / 2; ++c) acc2[c] = fma2(vv, w2[(kd * 9 + kh * 3 + kw) * 8 + c], acc2[c]);
                 }
         }
+        float acc[C];
+#pragma unroll
+        for (int c = 0; c < C / 2; ++c) unpk2(acc2[c], acc[2 * c], acc[2 * c + 1]);
         // transpose through shared memory so that the warp writes its 2 KB row segment with fully coalesced 16 B stores
         float4* st = reinterpret_cast<float4*>(stage[warp]);
         const int sw = (lane >> 1) & 3;
@@ -236,17 +257,17 @@ conv3d_c16o1_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const Args 
     const int c4 = tid & 3, kd = (tid >> 2) % 3, seg = tid / 12;
     const bool active = seg < NSEG;
     const int hq = seg >> 1, wq0 = (seg & 1) * SEG_LEN;
-    float acc[3][3][4];
+    uint64_t acc2[3][3][2];                                    // packed (x,y) / (z,w) channel pairs of the thread's channel quad
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) acc[i][j][k] = 0.f;
+            for (int k = 0; k < 2; ++k) acc2[i][j][k] = 0ull;
 
     for (int i = 0; i < count; ++i) {
         const int s = it.d0 - 1 + i, bi = i % NBUF;
-        const unsigned char* buf = smem + bi * SLICE_BYTES;
+        const uint32_t buf_s = smem_u32(smem) + bi * SLICE_BYTES;
         load_gy_padded(a, it, s + 1, gys + ((s + 2) & 3) * GP_POS, tid);
         __syncthreads();
         mbar_wait(full + bi, (i / NBUF) & 1);
@@ -259,20 +280,18 @@ conv3d_c16o1_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const Args 
                 win[kh][1] = g[(hq - kh + 2) * GP_W + wq0 - 1 + 2];
                 win[kh][2] = g[(hq - kh + 2) * GP_W + wq0 - 2 + 2];
             }
-#pragma unroll 1
+#pragma unroll 4                                                     // the loads of the next positions overlap this one's FMAs
             for (int j = 0; j < SEG_LEN; ++j) {
                 const int wq = wq0 + j;
-                const float4 xv = lds_x(buf, hq * HW + wq, c4);
+                const ulonglong2 xv = lds_x2(buf_s, hq * HW + wq, c4);
 #pragma unroll
                 for (int kh = 0; kh < 3; ++kh) {
                     win[kh][0] = g[(hq - kh + 2) * GP_W + wq + 2];  // kw = 0: column wq
 #pragma unroll
                     for (int kw = 0; kw < 3; ++kw) {
-                        const float gv = win[kh][kw];
-                        acc[kh][kw][0] = fmaf(gv, xv.x, acc[kh][kw][0]);
-                        acc[kh][kw][1] = fmaf(gv, xv.y, acc[kh][kw][1]);
-                        acc[kh][kw][2] = fmaf(gv, xv.z, acc[kh][kw][2]);
-                        acc[kh][kw][3] = fmaf(gv, xv.w, acc[kh][kw][3]);
+                        const uint64_t gv = pk2(win[kh][kw], win[kh][kw]);
+                        acc2[kh][kw][0] = fma2(gv, xv.x, acc2[kh][kw][0]);
+                        acc2[kh][kw][1] = fma2(gv, xv.y, acc2[kh][kw][1]);
                     }
                     win[kh][2] = win[kh][1];
                     win[kh][1] = win[kh][0];
@@ -288,9 +307,13 @@ conv3d_c16o1_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const Args 
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
-            for (int kw = 0; kw < 3; ++kw)
+            for (int kw = 0; kw < 3; ++kw) {
+                float acc[4];
+                unpk2(acc2[kh][kw][0], acc[0], acc[1]);
+                unpk2(acc2[kh][kw][1], acc[2], acc[3]);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) part[seg * NW + (c4 * 4 + k) * 27 + kd * 9 + kh * 3 + kw] = acc[kh][kw][k];
+                for (int k = 0; k < 4; ++k) part[seg * NW + (c4 * 4 + k) * 27 + kd * 9 + kh * 3 + kw] = acc[k];
+            }
     }
     __syncthreads();
     for (int o = tid; o < NW; o += THREADS) {
@@ -1185,9 +1208,19 @@ static int check_shape(int B, int D, int H, int W) {
     return 0;
 }
 
+__global__ void transpose_w_kernel(const float* __restrict__ w) {           // [c][27] -> [tap][16]
+    const int o = threadIdx.x;
+    if (o < NW) g_wt[o] = w[(o & 15) * 27 + (o >> 4)];
+}
+
 static int upload_weights(const float* w, cudaStream_t st) {
     cudaError_t e = cudaMemcpyToSymbolAsync(c_w, w, sizeof(float) * NW, 0, cudaMemcpyDeviceToDevice, st);
     if (e != cudaSuccess) return fail(static_cast<int>(e), "conv3d_c16o1 weight upload: %s", cudaGetErrorString(e));
+    transpose_w_kernel<<<1, 448, 0, st>>>(w);
+    void* staging = nullptr;
+    e = cudaGetSymbolAddress(&staging, g_wt);
+    if (e == cudaSuccess) e = cudaMemcpyToSymbolAsync(c_wt, staging, sizeof(float) * NW, 0, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return fail(static_cast<int>(e), "conv3d_c16o1 weight upload (tap-major): %s", cudaGetErrorString(e));
     return 0;
 }
 

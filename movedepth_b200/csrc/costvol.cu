@@ -291,25 +291,6 @@ __device__ __forceinline__ bool cell_in_box(const PixelCtx& c, int ix, int iy, i
 }
 
 // ------------------------------------------------------------------------------------------ forward
-// Packed fp32 math (Blackwell FFMA2: two fp32 FMAs per instruction on a 64-bit register pair).
-__device__ __forceinline__ uint64_t pk2(float a, float b) {
-    uint64_t r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
-    return r;
-}
-__device__ __forceinline__ void unpk2(uint64_t v, float& a, float& b) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
-}
-__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
-    uint64_t d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
-    uint64_t d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
 __device__ __forceinline__ ulonglong2 lds128p(const unsigned char* base, int pix, int j) {
     return *reinterpret_cast<const ulonglong2*>(base + pix * 128 + ((j ^ (pix & 7)) << 4));
 }
