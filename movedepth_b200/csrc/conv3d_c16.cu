@@ -152,18 +152,30 @@ conv3d_c16o1_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const Args a)
 // gx[b,d,h,w,c] = sum_{kd,kh,kw} gy[b,d-kd+1,h-kh+1,w-kw+1] * W[c,kd,kh,kw]
 constexpr int GY_POS = HH * HW;                // one halo'd gy slice (floats)
 
-__device__ __forceinline__ void load_gy_slice(const Args& a, const Item& it, int d, float* dst, int tid, int dlo, int dhi) {
-    // rows h0-1 .. h0+8, columns w0-1 .. w0+32; zero outside the image / outside [dlo, dhi)
+// one halo'd gy slice = 340 floats = up to 2 per thread: rows h0-1 .. h0+8, columns w0-1 .. w0+32; zero outside the image /
+// outside [dlo, dhi).  Split into the global loads (issued a whole slice ahead of their use) and the shared-memory stores.
+struct GyRegs {
+    float v[2];
+};
+__device__ __forceinline__ GyRegs fetch_gy_slice(const Args& a, const Item& it, int d, int tid, int dlo, int dhi) {
+    GyRegs g;
     const bool dok = d >= dlo && d < dhi;
-    for (int e = tid; e < GY_POS; e += THREADS) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int e = tid + k * THREADS;
         const int r = e / HW, cc = e - r * HW;
         const int h = it.h0 - 1 + r, w = it.w0 - 1 + cc;
-        float v = 0.f;
-        if (dok && h >= 0 && h < a.H && w >= 0 && w < a.W)
-            v = __ldg(a.gy + ((static_cast<size_t>(it.b) * a.D + d) * a.H + h) * a.W + w);
-        dst[e] = v;
+        g.v[k] = 0.f;
+        if (e < GY_POS && dok && h >= 0 && h < a.H && w >= 0 && w < a.W)
+            g.v[k] = __ldg(a.gy + ((static_cast<size_t>(it.b) * a.D + d) * a.H + h) * a.W + w);
     }
+    return g;
 }
+__device__ __forceinline__ void store_gy_slice(const GyRegs& g, float* dst, int tid) {
+    dst[tid] = g.v[0];
+    if (tid + THREADS < GY_POS) dst[tid + THREADS] = g.v[1];
+}
+static_assert(GY_POS <= 2 * THREADS, "two values per thread cover a gy slice");
 
 __global__ void __launch_bounds__(THREADS, 2)
 conv3d_c16o1_dgrad_kernel(const Args a) {
@@ -171,11 +183,15 @@ conv3d_c16o1_dgrad_kernel(const Args a) {
     __shared__ __align__(16) float stage[THREADS / 32][32 * C];
     const int tid = threadIdx.x, hh = tid >> 5, ww = tid & 31, warp = hh, lane = ww;
     const Item it = decode_item(a, blockIdx.x);
-    load_gy_slice(a, it, it.d0 - 1, gys[(it.d0) & 3], tid, 0, a.D);
-    load_gy_slice(a, it, it.d0, gys[(it.d0 + 1) & 3], tid, 0, a.D);
+    store_gy_slice(fetch_gy_slice(a, it, it.d0 - 1, tid, 0, a.D), gys[(it.d0) & 3], tid);
+    store_gy_slice(fetch_gy_slice(a, it, it.d0, tid, 0, a.D), gys[(it.d0 + 1) & 3], tid);
+    GyRegs ahead = fetch_gy_slice(a, it, it.d0 + 1, tid, 0, a.D);
     const int h = it.h0 + hh;
     for (int d = it.d0; d < it.d1; ++d) {
-        load_gy_slice(a, it, d + 1, gys[(d + 2) & 3], tid, 0, a.D);
+        // slice d+1 (requested during the previous iteration) goes to its slot; slice d+2 is requested now.  One barrier per
+        // slice: the slot written here, (d+2)&3, is read by nobody in iteration d-1 (slots (d-1)&3, d&3, (d+1)&3).
+        store_gy_slice(ahead, gys[(d + 2) & 3], tid);
+        ahead = fetch_gy_slice(a, it, d + 2, tid, 0, a.D);
         __syncthreads();
         const uint64_t* w2 = reinterpret_cast<const uint64_t*>(c_wt);   // [tap][8 channel pairs]
         uint64_t acc2[C / 2];                                  // packed channel pairs: 216 FFMA2 per position instead of 432 FFMA
@@ -212,7 +228,6 @@ conv3d_c16o1_dgrad_kernel(const Args a) {
                 if (chunk < valid) gp[chunk] = st[pos * 4 + (q ^ ((pos >> 1) & 3))];
             }
         }
-        __syncthreads();                                       // gy ring slot (d - 1 + 1) & 3 is rewritten next iteration
     }
 }
 
@@ -224,17 +239,26 @@ constexpr int GP_H = TH + 4, GP_W = TW + 4;    // gy tile zero-padded by 2 on ev
 constexpr int GP_POS = GP_H * GP_W;
 constexpr int NSEG = 20, SEG_LEN = 17;
 
-__device__ __forceinline__ void load_gy_padded(const Args& a, const Item& it, int d, float* dst, int tid) {
+// the zero-padded gy tile of one slice = 432 floats = up to 2 per thread, split into global loads (a slice ahead) and stores
+__device__ __forceinline__ GyRegs fetch_gy_padded(const Args& a, const Item& it, int d, int tid) {
+    GyRegs g;
     const bool dok = d >= it.d0 && d < it.d1;                  // only this work item's own outputs count
-    for (int e = tid; e < GP_POS; e += THREADS) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const int e = tid + k * THREADS;
         const int r = e / GP_W - 2, cc = e % GP_W - 2;
         const int h = it.h0 + r, w = it.w0 + cc;
-        float v = 0.f;
-        if (dok && r >= 0 && r < TH && cc >= 0 && cc < TW && h < a.H && w < a.W)
-            v = __ldg(a.gy + ((static_cast<size_t>(it.b) * a.D + d) * a.H + h) * a.W + w);
-        dst[e] = v;
+        g.v[k] = 0.f;
+        if (e < GP_POS && dok && r >= 0 && r < TH && cc >= 0 && cc < TW && h < a.H && w < a.W)
+            g.v[k] = __ldg(a.gy + ((static_cast<size_t>(it.b) * a.D + d) * a.H + h) * a.W + w);
     }
+    return g;
 }
+__device__ __forceinline__ void store_gy_padded(const GyRegs& g, float* dst, int tid) {
+    dst[tid] = g.v[0];
+    if (tid + THREADS < GP_POS) dst[tid + THREADS] = g.v[1];
+}
+static_assert(GP_POS <= 2 * THREADS, "two values per thread cover a padded gy tile");
 
 __global__ void __launch_bounds__(THREADS, 2)
 conv3d_c16o1_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const Args a) {
@@ -252,8 +276,9 @@ conv3d_c16o1_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const Args 
         for (int i = 0; i < NBUF && i < count; ++i) issue_slice(&map_x, smem + i * SLICE_BYTES, full + i, it, it.d0 - 1 + i);
     }
     // x slice s pairs with gy slices s+1 (kd=0), s (kd=1), s-1 (kd=2)
-    load_gy_padded(a, it, it.d0 - 2, gys + ((it.d0 - 1) & 3) * GP_POS, tid);
-    load_gy_padded(a, it, it.d0 - 1, gys + ((it.d0) & 3) * GP_POS, tid);
+    store_gy_padded(fetch_gy_padded(a, it, it.d0 - 2, tid), gys + ((it.d0 - 1) & 3) * GP_POS, tid);
+    store_gy_padded(fetch_gy_padded(a, it, it.d0 - 1, tid), gys + ((it.d0) & 3) * GP_POS, tid);
+    GyRegs ahead = fetch_gy_padded(a, it, it.d0, tid);
     const int c4 = tid & 3, kd = (tid >> 2) % 3, seg = tid / 12;
     const bool active = seg < NSEG;
     const int hq = seg >> 1, wq0 = (seg & 1) * SEG_LEN;
@@ -268,8 +293,12 @@ conv3d_c16o1_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const Args 
     for (int i = 0; i < count; ++i) {
         const int s = it.d0 - 1 + i, bi = i % NBUF;
         const uint32_t buf_s = smem_u32(smem) + bi * SLICE_BYTES;
-        load_gy_padded(a, it, s + 1, gys + ((s + 2) & 3) * GP_POS, tid);
+        // gy slice s+1 (requested during the previous iteration) goes to its slot, slice s+2 is requested now; after the barrier
+        // everybody has also finished with the x buffer of iteration i-1, which thread 0 refills (one barrier per slice)
+        store_gy_padded(ahead, gys + ((s + 2) & 3) * GP_POS, tid);
+        ahead = fetch_gy_padded(a, it, s + 2, tid);
         __syncthreads();
+        if (tid == 0 && i >= 1 && i - 1 + NBUF < count) issue_slice(&map_x, smem + ((i - 1) % NBUF) * SLICE_BYTES, full + (i - 1) % NBUF, it, s - 1 + NBUF);
         mbar_wait(full + bi, (i / NBUF) & 1);
         if (active) {
             // gy tile-local index for x halo position (hq,wq) and tap (kh,kw): row hq-kh, column wq-kw (+2 padding)
@@ -298,9 +327,8 @@ conv3d_c16o1_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const Args 
                 }
             }
         }
-        __syncthreads();
-        if (tid == 0 && i + NBUF < count) issue_slice(&map_x, smem + bi * SLICE_BYTES, full + bi, it, s + NBUF);
     }
+    __syncthreads();
     // ---- reduce the 20 segment partials of this work item (re-using the x ring as scratch)
     float* part = reinterpret_cast<float*>(smem);              // [NSEG][NW]
     if (active) {
