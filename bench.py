@@ -271,6 +271,8 @@ def run_own(args, cfg):
         argv.append("--ddp")
     if not args.no_graph:
         argv.append("--b200_cuda_graph")
+    if not args.no_cudnn_benchmark:
+        argv.append("--b200_cudnn_benchmark")
     opt = MonodepthOptions().parse(argv)
     torch.manual_seed(0)
     tr = Trainer(opt)
@@ -368,6 +370,8 @@ def run_own(args, cfg):
         "execution": {"precision": {"3xtf32": "convs on tensor cores with a 3-way TF32 operand split in the forward (near-fp32 outputs, "
                                     "movedepth_b200/precision.py); " + grads,
                                     "fp32": "fp32 everywhere (cuDNN SIMT convs)", "tf32": "cuDNN TF32 everywhere"}[args.precision],
+                      "cudnn": "library convs: algorithm per layer shape timed by cuDNN during the warm-up steps (cudnn.benchmark)"
+                               if not args.no_cudnn_benchmark else "library convs: cuDNN heuristics",
                       "launch": "eager launches" if args.no_graph else "forward+backward(+all-reduce) replayed as one CUDA graph; Adam kernels after it",
                       "parallelism": "dp%d, flat-arena gradient all-reduce over NCCL" % world},
         "roofline": {"kernel": "costvol_grouped_fwd_kernel", "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
@@ -407,6 +411,7 @@ def main():
     ap.add_argument("--noise", action="store_true", help="U[0,1) white-noise images (SURVEY 8d) instead of band-limited ones")
     ap.add_argument("--verbose", action="store_true", help="print the pose / prior statistics the cost-volume kernel saw")
     ap.add_argument("--no_graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no_cudnn_benchmark", action="store_true", help="cuDNN heuristics instead of timed algorithm selection for the library convs")
     ap.add_argument("--ncu_range", action="store_true", help="cudaProfilerStart/Stop around the device-timed steps")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]

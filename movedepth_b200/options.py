@@ -66,6 +66,9 @@ class MonodepthOptions:
         p.add_argument("--b200_cuda_graph", action="store_true", help="capture the training step in a CUDA graph")
         p.add_argument("--b200_one_stream", action="store_true",
                        help="issue the mono/pose graph and the cost-volume graph on ONE stream (default: two concurrent streams)")
+        p.add_argument("--b200_cudnn_benchmark", action="store_true",
+                       help="let cuDNN time its algorithms per layer shape during the warm-up steps (torch.backends.cudnn.benchmark; "
+                            "the reference's train.py:19-20 pins deterministic=True, benchmark=False)")
         p.add_argument("--b200_synthetic", action="store_true", help="train on synthetic KITTI-shape tensors")
         self.parser = p
 

@@ -289,6 +289,8 @@ class Trainer:
         # auto-mask tie-break noise (trainer.py:600,641,698 draw it on the CPU and copy it over): a device generator of this
         # trainer fills static buffers OUTSIDE the captured graph, so eager and graph steps with the same seed see the same
         # noise and a replay never re-uses the noise of the capture
+        if getattr(o, "b200_cudnn_benchmark", False) or os.environ.get("MVD_CUDNN_BENCHMARK") == "1":
+            torch.backends.cudnn.benchmark = True
         self._two_streams = not getattr(o, "b200_one_stream", False)
         self._mvs_stream = torch.cuda.Stream() if self._two_streams else None
         if self.device.type == "cuda":
