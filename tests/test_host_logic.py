@@ -241,7 +241,7 @@ def test_workspace_and_buffer_size_queries_need_no_gpu():
     from movedepth_b200.build import build
     build()                                   # no-op when the in-tree library is current
     L = _lib.lib()
-    assert L.mvd_peer_allreduce_buffer_bytes(8, 2048) == 4096 + 2 * 8 * 2048 * 8
+    assert L.mvd_peer_allreduce_buffer_bytes(8, 2048) == 4096 + 2 * 8 * 2048 * 16      # header + 2 epoch slots x 8 ranks x 2048 entries of {lo, tag, hi, tag}
     assert L.mvd_peer_allreduce_buffer_bytes(0, 2048) == 0
     for fn, per_item in ((L.mvd_conv3d_c16o1_wgrad_workspace_bytes, 432 * 4), (L.mvd_conv3d_c16c16_wgrad_workspace_bytes, 6912 * 4),
                          (L.mvd_conv3d_c16c16_wgrad_tc_workspace_bytes, 2 * 6912 * 4)):
