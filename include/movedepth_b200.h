@@ -182,22 +182,25 @@ int mvd_masked_smooth_l1_bwd(const float* gloss, const float* a, const float* b,
                              const double* sums, float* ga, float* gb, long long n, float weight, void* stream);
 
 /* ---------------------------------------------------------------------------------------
- * Skinny 2-D convolutions of the matching-feature network (csrc/conv2d_small.cu): FPN4's conv0 / conv1 stages
- * (movedepth/networks/resnet_encoder.py:325-341, Conv2d 453-475: 3->8, 8->8 at full resolution; 8->16 5x5 stride 2,
- * 16->16 at half resolution) and UncertNet's 8->8 layer (depth_decoder.py:376-381).  Exact fp32 direct convolutions on
- * the CUDA cores, zero padding k/2, no bias.  Replaces cuDNN fprop / dgrad / wgrad for these layers.
+ * Skinny 2-D convolutions (csrc/conv2d_small.cu): FPN4's conv0 / conv1 stages (movedepth/networks/resnet_encoder.py:325-341,
+ * Conv2d 453-475: 3->8, 8->8 at full resolution; 8->16 5x5 stride 2, 16->16 at half resolution), UncertNet's 8->8 layer
+ * (depth_decoder.py:376-381) and the DepthDecoder's finest stage (depth_decoder.py:72-101: upconv(0,1) 16->16 and the
+ * disparity head 16->1, which the caller zero-pads to 4 output channels).  Exact fp32 direct convolutions on the CUDA cores
+ * (packed fp32x2 FMAs), no bias.  Replaces cuDNN fprop / dgrad / wgrad for these layers.
  *   x  : [B,H,W,cin] channels-last;  w : [cout][k][k][cin] (channels-last storage of the OIHW weight);
- *   y, gy : [B,Ho,Wo,cout], Ho = (H + 2*(k/2) - k)/stride + 1;  gx : [B,H,W,cin] OVERWRITTEN;  gw : like w, OVERWRITTEN
- *   supported (cin,cout,k,stride): (3,8,3,1) (8,8,3,1) (8,16,5,2) (16,16,3,1); dgrad: all but (3,8,3,1) (the image).
+ *   pad: zero padding on every side: k/2 ("same"), or 0 for the stride-1 layers ("valid": the decoder's inputs arrive
+ *        reflection-padded from mvd_decoder_prep);
+ *   y, gy : [B,Ho,Wo,cout], Ho = (H + 2*pad - k)/stride + 1;  gx : [B,H,W,cin] OVERWRITTEN;  gw : like w, OVERWRITTEN
+ *   supported (cin,cout,k,stride): (3,8,3,1) (8,8,3,1) (8,16,5,2) (16,16,3,1) (16,4,3,1); dgrad: all but (3,8,3,1) (the image).
  * ------------------------------------------------------------------------------------- */
 int mvd_conv2d_small_supported(int cin, int cout, int k, int stride);
 int mvd_conv2d_small_fwd(const float* x, const float* w, float* y, int B, int H, int W, int cin, int cout, int k,
-                         int stride, void* stream);
+                         int stride, int pad, void* stream);
 int mvd_conv2d_small_dgrad(const float* gy, const float* w, float* gx, int B, int H, int W, int cin, int cout, int k,
-                           int stride, void* stream);
-long long mvd_conv2d_small_wgrad_workspace_bytes(int B, int H, int W, int cin, int cout, int k, int stride);
+                           int stride, int pad, void* stream);
+long long mvd_conv2d_small_wgrad_workspace_bytes(int B, int H, int W, int cin, int cout, int k, int stride, int pad);
 int mvd_conv2d_small_wgrad(const float* x, const float* gy, float* gw, void* workspace, long long workspace_bytes,
-                           int B, int H, int W, int cin, int cout, int k, int stride, void* stream);
+                           int B, int H, int W, int cin, int cout, int k, int stride, int pad, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * DepthDecoder glue (csrc/decoder.cu): everything between two 3x3 convolutions of the U-Net decoder

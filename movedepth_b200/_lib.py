@@ -43,10 +43,10 @@ SIGNATURES = {
     "mvd_masked_smooth_l1_fwd": ([_P] * 6 + [_I] * 7 + [_F, _P], _I),
     "mvd_masked_smooth_l1_bwd": ([_P] * 7 + [_LL, _F, _P], _I),
     "mvd_conv2d_small_supported": ([_I] * 4, _I),
-    "mvd_conv2d_small_fwd": ([_P] * 3 + [_I] * 7 + [_P], _I),
-    "mvd_conv2d_small_dgrad": ([_P] * 3 + [_I] * 7 + [_P], _I),
-    "mvd_conv2d_small_wgrad_workspace_bytes": ([_I] * 7, _LL),
-    "mvd_conv2d_small_wgrad": ([_P] * 4 + [_LL] + [_I] * 7 + [_P], _I),
+    "mvd_conv2d_small_fwd": ([_P] * 3 + [_I] * 8 + [_P], _I),
+    "mvd_conv2d_small_dgrad": ([_P] * 3 + [_I] * 8 + [_P], _I),
+    "mvd_conv2d_small_wgrad_workspace_bytes": ([_I] * 8, _LL),
+    "mvd_conv2d_small_wgrad": ([_P] * 4 + [_LL] + [_I] * 8 + [_P], _I),
     "mvd_decoder_prep_fwd": ([_P] * 5 + [_I] * 7 + [_P], _I),
     "mvd_decoder_prep_bwd": ([_P] * 6 + [_I] * 7 + [_P], _I),
     "mvd_gather_chunk": ([], _I),

@@ -22,6 +22,7 @@ struct Args {
     float* y;           // output            [B,Ho,Wo,COUT]
     int B, H, W, Ho, Wo;
     int flip;           // 1: stage w as the data-gradient filter (flipped taps, channels transposed; w is then [CIN][K][K][COUT])
+    int pad;            // zero padding on every side: K/2 ("same"), 0 ("valid": the DepthDecoder's pre-padded inputs), K-1 (their dgrad)
 };
 
 // ------------------------------------------------------------------------------------------------ forward / dgrad (S = 1)
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(128) small_fwd_kernel(const Args a) {
     float* ws = smem + CF::XS;
     const int tid = threadIdx.x, lane = tid & 31, q = tid >> 5;
     const int ox0 = blockIdx.x * 32, oy0 = blockIdx.y * CF::ROWS, b = blockIdx.z;
-    constexpr int P = K / 2;
+    const int P = a.pad;
     // filter -> ws[tap][ci][co]
     for (int e = tid; e < CF::WS; e += 128) {
         const int co = e % COUT, ci = (e / COUT) % CIN, tap = e / (COUT * CIN);
@@ -228,6 +229,7 @@ struct WArgs {
     const float* gy;    // [B,Ho,Wo,COUT]
     float* part;        // [grid][NW], layout [co][tap][ci]
     int B, H, W, Ho, Wo, tiles_x, tiles_y, num_tiles;
+    int pad;
 };
 
 template <int CIN, int COUT, int K, int S>
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(WgCfg<CIN, COUT, K, S>::THREADS) small_wgrad_k
     const int tid = threadIdx.x;
     const int pair = tid % CF::NT, grp = tid / CF::NT;
     const int ci = pair % CIN, tap = pair / CIN, ky = tap / K, kx = tap % K;
-    constexpr int P = K / 2;
+    const int P = a.pad;
     uint64_t acc2[COUT / 2];                     // packed output-channel pairs
 #pragma unroll
     for (int co = 0; co < COUT / 2; ++co) acc2[co] = 0ull;
@@ -334,10 +336,10 @@ static int wgrad_ctas(int B, int Ho, int Wo) {
 
 template <int CIN, int COUT, int K, int S>
 static int launch_wgrad(const float* x, const float* gy, float* gw, float* ws, long long ws_bytes, int B, int H, int W, int Ho, int Wo,
-                        cudaStream_t st) {
+                        int pad, cudaStream_t st) {
     using CF = WgCfg<CIN, COUT, K, S>;
     static_assert(CF::THREADS * COUT * 4 <= CF::SMEM || CF::THREADS * COUT <= CF::XS + CF::GS, "group reduction scratch fits");
-    WArgs a{x, gy, ws, B, H, W, Ho, Wo, (Wo + CF::TW - 1) / CF::TW, (Ho + CF::TH - 1) / CF::TH, 0};
+    WArgs a{x, gy, ws, B, H, W, Ho, Wo, (Wo + CF::TW - 1) / CF::TW, (Ho + CF::TH - 1) / CF::TH, 0, pad};
     a.num_tiles = a.tiles_x * a.tiles_y * B;
     const int ctas = wgrad_ctas<CIN, COUT, K, S>(B, Ho, Wo);
     MVD_REQUIRE(ws_bytes >= static_cast<long long>(ctas) * CF::NW * 4, "conv2d_small wgrad workspace too small");
@@ -354,14 +356,23 @@ static int launch_wgrad(const float* x, const float* gy, float* gw, float* ws, l
 
 using namespace mvd;
 
-// supported (CIN, COUT, K, S): the skinny FPN4 / UncertNet layers
+// supported (CIN, COUT, K, S): the skinny FPN4 / UncertNet layers and the DepthDecoder's finest stage (16 -> 16, and its
+// 16 -> 1 disparity head zero-padded to 4 output channels by the caller)
 #define C2S_DISPATCH(M)                       \
     M(3, 8, 3, 1)                             \
     M(8, 8, 3, 1)                             \
     M(8, 16, 5, 2)                            \
-    M(16, 16, 3, 1)
+    M(16, 16, 3, 1)                           \
+    M(16, 4, 3, 1)
 
 extern "C" {
+
+// pad: K/2 ("same") for every supported layer; 0 ("valid", pre-padded input) for the stride-1 layers
+static int c2s_check(int cin, int cout, int k, int stride, int pad) {
+    MVD_REQUIRE(mvd_conv2d_small_supported(cin, cout, k, stride), "conv2d_small: unsupported layer %d->%d k%d s%d", cin, cout, k, stride);
+    MVD_REQUIRE(pad == k / 2 || (pad == 0 && stride == 1), "conv2d_small: padding %d not supported for k%d s%d", pad, k, stride);
+    return 0;
+}
 
 int mvd_conv2d_small_supported(int cin, int cout, int k, int stride) {
 #define M(CI, CO, KK, SS) if (cin == CI && cout == CO && k == KK && stride == SS) return 1;
@@ -370,11 +381,14 @@ int mvd_conv2d_small_supported(int cin, int cout, int k, int stride) {
     return 0;
 }
 
-int mvd_conv2d_small_fwd(const float* x, const float* w, float* y, int B, int H, int W, int cin, int cout, int k, int stride, void* stream) {
+int mvd_conv2d_small_fwd(const float* x, const float* w, float* y, int B, int H, int W, int cin, int cout, int k, int stride, int pad,
+                         void* stream) {
     MVD_REQUIRE(x && w && y && B > 0 && H > 0 && W > 0, "bad argument");
     MVD_REQUIRE(aligned16(y), "output must be 16-byte aligned");
-    const int Ho = (H + 2 * (k / 2) - k) / stride + 1, Wo = (W + 2 * (k / 2) - k) / stride + 1;
-    c2s::Args a{x, w, y, B, H, W, Ho, Wo, 0};
+    if (int rc = c2s_check(cin, cout, k, stride, pad)) return rc;
+    const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+    MVD_REQUIRE(Ho > 0 && Wo > 0, "conv2d_small: empty output");
+    c2s::Args a{x, w, y, B, H, W, Ho, Wo, 0, pad};
     cudaStream_t st = as_stream(stream);
 #define M(CI, CO, KK, SS) if (cin == CI && cout == CO && k == KK && stride == SS) return c2s::launch_fwd<CI, CO, KK, SS, (SS == 1 ? 4 : 2)>(a, st);
     C2S_DISPATCH(M)
@@ -382,19 +396,22 @@ int mvd_conv2d_small_fwd(const float* x, const float* w, float* y, int B, int H,
     return fail(-1, "conv2d_small: unsupported layer %d->%d k%d s%d", cin, cout, k, stride);
 }
 
-// gx = d loss / d x given gy = d loss / d y; w as for the forward ([cout][k][k][cin])
-int mvd_conv2d_small_dgrad(const float* gy, const float* w, float* gx, int B, int H, int W, int cin, int cout, int k, int stride, void* stream) {
+// gx = d loss / d x given gy = d loss / d y; w as for the forward ([cout][k][k][cin]); H, W = the INPUT's size
+int mvd_conv2d_small_dgrad(const float* gy, const float* w, float* gx, int B, int H, int W, int cin, int cout, int k, int stride, int pad,
+                           void* stream) {
     MVD_REQUIRE(gy && w && gx && B > 0 && H > 0 && W > 0, "bad argument");
     MVD_REQUIRE(aligned16(gx), "output must be 16-byte aligned");
-    const int Ho = (H + 2 * (k / 2) - k) / stride + 1, Wo = (W + 2 * (k / 2) - k) / stride + 1;
+    if (int rc = c2s_check(cin, cout, k, stride, pad)) return rc;
+    const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
     cudaStream_t st = as_stream(stream);
-    if (stride == 1) {          // a stride-1 convolution of gy with the flipped, transposed filter: forward kernel with roles swapped
-        c2s::Args a{gy, w, gx, B, H, W, H, W, 1};
+    if (stride == 1) {          // a stride-1 convolution of gy (padding k-1-pad) with the flipped, transposed filter: forward kernel, roles swapped
+        c2s::Args a{gy, w, gx, B, Ho, Wo, H, W, 1, k - 1 - pad};
         if (cin == 8 && cout == 8 && k == 3) return c2s::launch_fwd<8, 8, 3, 1, 4>(a, st);
         if (cin == 16 && cout == 16 && k == 3) return c2s::launch_fwd<16, 16, 3, 1, 4>(a, st);
+        if (cin == 16 && cout == 4 && k == 3) return c2s::launch_fwd<4, 16, 3, 1, 4>(a, st);
     } else if (cin == 8 && cout == 16 && k == 5 && stride == 2) {
         using CF = c2s::Dg2Cfg<8, 16, 5>;
-        c2s::Args a{gy, w, gx, B, H, W, Ho, Wo, 0};
+        c2s::Args a{gy, w, gx, B, H, W, Ho, Wo, 0, pad};
         cudaFuncSetAttribute(c2s::small_dgrad_s2_kernel<8, 16, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, CF::SMEM);
         dim3 grid((W + 63) / 64, (H + CF::ROWS - 1) / CF::ROWS, B);
         c2s::small_dgrad_s2_kernel<8, 16, 5><<<grid, 128, CF::SMEM, st>>>(a);
@@ -403,8 +420,8 @@ int mvd_conv2d_small_dgrad(const float* gy, const float* w, float* gx, int B, in
     return fail(-1, "conv2d_small dgrad: unsupported layer %d->%d k%d s%d", cin, cout, k, stride);
 }
 
-long long mvd_conv2d_small_wgrad_workspace_bytes(int B, int H, int W, int cin, int cout, int k, int stride) {
-    const int Ho = (H + 2 * (k / 2) - k) / stride + 1, Wo = (W + 2 * (k / 2) - k) / stride + 1;
+long long mvd_conv2d_small_wgrad_workspace_bytes(int B, int H, int W, int cin, int cout, int k, int stride, int pad) {
+    const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
 #define M(CI, CO, KK, SS) \
     if (cin == CI && cout == CO && k == KK && stride == SS) \
         return static_cast<long long>(c2s::wgrad_ctas<CI, CO, KK, SS>(B, Ho, Wo)) * c2s::WgCfg<CI, CO, KK, SS>::NW * 4;
@@ -414,13 +431,14 @@ long long mvd_conv2d_small_wgrad_workspace_bytes(int B, int H, int W, int cin, i
 }
 
 int mvd_conv2d_small_wgrad(const float* x, const float* gy, float* gw, void* workspace, long long workspace_bytes, int B, int H, int W,
-                           int cin, int cout, int k, int stride, void* stream) {
+                           int cin, int cout, int k, int stride, int pad, void* stream) {
     MVD_REQUIRE(x && gy && gw && workspace && B > 0 && H > 0 && W > 0, "bad argument");
-    const int Ho = (H + 2 * (k / 2) - k) / stride + 1, Wo = (W + 2 * (k / 2) - k) / stride + 1;
+    if (int rc = c2s_check(cin, cout, k, stride, pad)) return rc;
+    const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
     cudaStream_t st = as_stream(stream);
 #define M(CI, CO, KK, SS) \
     if (cin == CI && cout == CO && k == KK && stride == SS) \
-        return c2s::launch_wgrad<CI, CO, KK, SS>(x, gy, gw, static_cast<float*>(workspace), workspace_bytes, B, H, W, Ho, Wo, st);
+        return c2s::launch_wgrad<CI, CO, KK, SS>(x, gy, gw, static_cast<float*>(workspace), workspace_bytes, B, H, W, Ho, Wo, pad, st);
     C2S_DISPATCH(M)
 #undef M
     return fail(-1, "conv2d_small wgrad: unsupported layer %d->%d k%d s%d", cin, cout, k, stride);

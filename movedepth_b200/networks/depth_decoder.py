@@ -56,11 +56,12 @@ class DepthDecoder(nn.Module):
             c0 = self._m("upconv", i, 0).conv.conv
             z = PR.prepared_conv(xp, x3, c0.weight)
             skip = input_features[i - 1] if (self.use_skips and i > 0) else None
-            xp, x3 = ops.decoder_prep(z, c0.bias, skip, act=True, up=2, want_split=want)
             c1 = self._m("upconv", i, 1).conv.conv
+            xp, x3 = ops.decoder_prep(z, c0.bias, skip, act=True, up=2, want_split=want and not PR.prepared_is_small(c1.weight))
             z = PR.prepared_conv(xp, x3, c1.weight)
             if i in self.scales or i > 0:                # this padded activation feeds dispconv(i) and upconv(i-1, 0)
-                xp, x3 = ops.decoder_prep(z, c1.bias, None, act=True, up=1, want_split=want)
+                direct = i == 0 and i in self.scales and PR.prepared_is_small(self._m("dispconv", i).conv.weight)
+                xp, x3 = ops.decoder_prep(z, c1.bias, None, act=True, up=1, want_split=want and not direct)
             if i in self.scales:
                 dc = self._m("dispconv", i).conv
                 self.outputs[("disp", i)] = torch.sigmoid(PR.prepared_conv(xp, x3, dc.weight) + dc.bias.view(1, -1, 1, 1))

@@ -650,45 +650,46 @@ def conv2d_small_supported(cin, cout, k, stride):
 
 class _Conv2dSmall(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, k, stride):
+    def forward(ctx, x, weight, k, stride, pad):
         B, cin, H, W = x.shape
         cout = weight.shape[0]
         x = _nhwc(x)
         w = _f32(weight).contiguous(memory_format=torch.channels_last)           # [cout][k][k][cin] in memory
-        Ho, Wo = (H + 2 * (k // 2) - k) // stride + 1, (W + 2 * (k // 2) - k) // stride + 1
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
         y = torch.empty((B, cout, Ho, Wo), device=x.device, dtype=torch.float32, memory_format=torch.channels_last)
-        rc = _lib.lib().mvd_conv2d_small_fwd(_p(x), _p(w), _p(y), B, H, W, cin, cout, k, stride, _stream())
+        rc = _lib.lib().mvd_conv2d_small_fwd(_p(x), _p(w), _p(y), B, H, W, cin, cout, k, stride, pad, _stream())
         _lib.check(rc, "mvd_conv2d_small_fwd")
         launch_counter["n"] += 1
         ctx.save_for_backward(x, w)
-        ctx.meta = (B, H, W, cin, cout, k, stride)
+        ctx.meta = (B, H, W, cin, cout, k, stride, pad)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
-        B, H, W, cin, cout, k, stride = ctx.meta
+        B, H, W, cin, cout, k, stride, pad = ctx.meta
         gy = _nhwc(gy)
         gx = gw = None
         L = _lib.lib()
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
-            _lib.check(L.mvd_conv2d_small_dgrad(_p(gy), _p(w), _p(gx), B, H, W, cin, cout, k, stride, _stream()), "mvd_conv2d_small_dgrad")
+            _lib.check(L.mvd_conv2d_small_dgrad(_p(gy), _p(w), _p(gx), B, H, W, cin, cout, k, stride, pad, _stream()), "mvd_conv2d_small_dgrad")
             launch_counter["n"] += 1
         if ctx.needs_input_grad[1]:
-            nbytes = L.mvd_conv2d_small_wgrad_workspace_bytes(B, H, W, cin, cout, k, stride)
+            nbytes = L.mvd_conv2d_small_wgrad_workspace_bytes(B, H, W, cin, cout, k, stride, pad)
             ws = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32)
             gw = torch.empty_like(w)                                             # channels-last strides, logical [cout,cin,k,k]
-            _lib.check(L.mvd_conv2d_small_wgrad(_p(x), _p(gy), _p(gw), _p(ws), nbytes, B, H, W, cin, cout, k, stride, _stream()),
+            _lib.check(L.mvd_conv2d_small_wgrad(_p(x), _p(gy), _p(gw), _p(ws), nbytes, B, H, W, cin, cout, k, stride, pad, _stream()),
                        "mvd_conv2d_small_wgrad")
             launch_counter["n"] += 2
-        return gx, gw, None, None
+        return gx, gw, None, None, None
 
 
-def conv2d_small(x, weight, k, stride):
-    """Exact-fp32 direct convolution (zero padding k//2, no bias) for the skinny FPN4 / UncertNet layers; x [B,cin,H,W]
-    (channels-last storage), weight [cout,cin,k,k].  Reference: movedepth/networks/resnet_encoder.py:325-341, 453-475."""
-    return _Conv2dSmall.apply(x, weight, int(k), int(stride))
+def conv2d_small(x, weight, k, stride, pad=None):
+    """Exact-fp32 direct convolution (no bias) for the skinny FPN4 / UncertNet layers (zero padding k//2) and the DepthDecoder's
+    finest stage (pad=0: pre-padded input); x [B,cin,H,W] (channels-last storage), weight [cout,cin,k,k].
+    Reference: movedepth/networks/resnet_encoder.py:325-341, 453-475; depth_decoder.py:72-101."""
+    return _Conv2dSmall.apply(x, weight, int(k), int(stride), int(k) // 2 if pad is None else int(pad))
 
 
 # ------------------------------------------------------------------------------------- ResNet stem max-pool

@@ -166,9 +166,26 @@ class _PreparedConv(torch.autograd.Function):
         return gx, None, gw
 
 
+def prepared_is_small(weight):
+    """True if `prepared_conv` runs this layer on the exact-fp32 direct kernels (csrc/conv2d_small.cu): the DepthDecoder's finest
+    stage, 16 -> 16 and the 16 -> 1 disparity head (no operand split is needed for its input then)."""
+    return (small_direct and weight.is_cuda and weight.dtype == torch.float32 and weight.dim() == 4 and tuple(weight.shape[2:]) == (3, 3)
+            and weight.shape[1] == 16 and weight.shape[0] in (16, 1))
+
+
 def prepared_conv(xp, x3, weight):
     """3x3 (or any) stride-1 convolution, no padding, no bias, of a pre-padded channels-last input following the
     precision policy; `x3` is the pre-split operand the DepthDecoder glue kernel wrote (used under 3xtf32 only)."""
+    if prepared_is_small(weight) and xp.is_cuda:
+        from . import ops
+        w = weight
+        if w.shape[0] == 1:                       # the one-channel head rides the 4-output-channel kernel (zero filters 1..3)
+            w = torch.cat([w, w.new_zeros((3,) + tuple(w.shape[1:]))], 0)
+        y = ops.conv2d_small(xp, w, 3, 1, pad=0)
+        if weight.shape[0] == 1:
+            y = y[:, :1]
+        record_conv(weight, xp, y)
+        return y
     if _policy["mode"] == "3xtf32" and not _policy["split_backward"] and x3.numel():
         y = _PreparedConv.apply(xp, x3, weight)
     elif _policy["mode"] == "3xtf32":

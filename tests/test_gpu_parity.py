@@ -918,14 +918,16 @@ def test_one_kernel_batchnorm_exchanges_at_its_grid_barrier_two_ranks_on_one_gpu
 
 
 # ---------------------------------------------------------------------------------------------- skinny 2-D convolutions
-@pytest.mark.parametrize("cfg", [(3, 8, 3, 1), (8, 8, 3, 1), (8, 16, 5, 2), (16, 16, 3, 1)], ids=["3-8", "8-8", "8-16-k5s2", "16-16"])
+@pytest.mark.parametrize("cfg", [(3, 8, 3, 1), (8, 8, 3, 1), (8, 16, 5, 2), (16, 16, 3, 1), (16, 16, 3, 1, 0), (16, 4, 3, 1), (16, 4, 3, 1, 0)],
+                         ids=["3-8", "8-8", "8-16-k5s2", "16-16", "16-16-valid", "16-4", "16-4-valid"])
 @pytest.mark.parametrize("hw", [(16, 32), (13, 45), (48, 160)], ids=["aligned", "ragged", "multi-tile"])
 def test_conv2d_small_matches_torch_conv2d(ops, cfg, hw):
-    """csrc/conv2d_small.cu (FPN4's conv0 / conv1 stages, UncertNet's 8->8 layer): exact-fp32 direct forward, data gradient
-    (flipped-filter forward kernel for stride 1, parity gather for stride 2) and weight gradient vs torch's CPU conv2d in
-    fp64; 1e-5 of the output scale (fp32 accumulation of <= 400 products)."""
+    """csrc/conv2d_small.cu (FPN4's conv0 / conv1 stages, UncertNet's 8->8 layer, the DepthDecoder's finest stage on pre-padded
+    inputs = "valid"): exact-fp32 direct forward, data gradient (flipped-filter forward kernel for stride 1, parity gather for
+    stride 2) and weight gradient vs torch's CPU conv2d in fp64; 1e-5 of the output scale (fp32 accumulation of <= 400 products)."""
     import torch.nn.functional as F
-    cin, cout, k, s = cfg
+    cin, cout, k, s = cfg[:4]
+    pad = cfg[4] if len(cfg) > 4 else k // 2
     H, W = hw
     if s == 2:
         H, W = H & ~1, W & ~1
@@ -933,14 +935,14 @@ def test_conv2d_small_matches_torch_conv2d(ops, cfg, hw):
     x = torch.randn(2, cin, H, W, generator=gen)
     w = torch.randn(cout, cin, k, k, generator=gen) * 0.2
     xo, wo = x.double().requires_grad_(True), w.double().requires_grad_(True)
-    yo = F.conv2d(xo, wo, stride=s, padding=k // 2)
+    yo = F.conv2d(xo, wo, stride=s, padding=pad)
     gy = torch.randn(yo.shape, generator=gen)
     (yo * gy.double()).sum().backward()
     need_gx = cin > 3
     xg = g(x).contiguous(memory_format=torch.channels_last).requires_grad_(need_gx)
     wg = g(w).requires_grad_(True)
     assert ops.conv2d_small_supported(cin, cout, k, s)
-    y = ops.conv2d_small(xg, wg, k, s)
+    y = ops.conv2d_small(xg, wg, k, s, pad=pad)
     assert y.shape == yo.shape
     (y * g(gy)).sum().backward()
     pairs = [(y, yo), (wg.grad, wo.grad)] + ([(xg.grad, xo.grad)] if need_gx else [])
