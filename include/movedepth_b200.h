@@ -225,6 +225,14 @@ int mvd_decoder_prep_bwd(const float* gxp, const float* z, const float* bias, fl
 int mvd_maxpool3x3s2_fwd(const float* x, float* y, unsigned char* idx, int B, int H, int W, int C, void* stream);
 int mvd_maxpool3x3s2_bwd(const float* gy, const unsigned char* idx, float* gx, int B, int H, int W, int C, void* stream);
 
+/* Pose-net outputs -> 4x4 camera transform: transformation_from_parameters = rot_from_axisangle (Rodrigues, angle + 1e-7) composed
+ * with the translation matrix, optionally inverted (movedepth/layers.py:412-429, 464-518; called at trainer.py:462-466).
+ *   axisangle, translation : [B,3];  M : [B,4,4] row-major, OVERWRITTEN;  invert : M = R^T * T(-t) instead of T(t) * R.
+ *   bwd: g_axisangle, g_translation [B,3] OVERWRITTEN from gM [B,4,4] (forward-mode derivative of the same expression). */
+int mvd_pose_matrix_fwd(const float* axisangle, const float* translation, float* M, int B, int invert, void* stream);
+int mvd_pose_matrix_bwd(const float* axisangle, const float* translation, const float* gM, float* g_axisangle,
+                        float* g_translation, int B, int invert, void* stream);
+
 /* ---------------------------------------------------------------------------------------
  * Device-side image pre-processing (csrc/datapipe.cu): what MonoDataset.preprocess does on the CPU through
  * Pillow / torchvision (movedepth/datasets/mono_dataset.py:104-126 pyramid of `transforms.Resize(..., ANTIALIAS)`,

@@ -53,6 +53,8 @@ SIGNATURES = {
     "mvd_gather_segments": ([_P, _P, _I, _P, _P], _I),
     "mvd_maxpool3x3s2_fwd": ([_P] * 3 + [_I] * 4 + [_P], _I),
     "mvd_maxpool3x3s2_bwd": ([_P] * 3 + [_I] * 4 + [_P], _I),
+    "mvd_pose_matrix_fwd": ([_P] * 3 + [_I] * 2 + [_P], _I),
+    "mvd_pose_matrix_bwd": ([_P] * 5 + [_I] * 2 + [_P], _I),
     "mvd_resample_u8": ([_P] * 4 + [_I, _LL, _I, _I, _I, _P, _LL, _P], _I),
     "mvd_flip_copy_u8": ([_P, _P] + [_I] * 4 + [_P, _P], _I),
     "mvd_u8_to_tensor": ([_P, _P] + [_I] * 3 + [_P], _I),

@@ -400,6 +400,100 @@ maxpool_bwd_kernel(const float4* __restrict__ gy, const uchar4* __restrict__ idx
     }
 }
 
+// ---- pose-net outputs -> 4x4 camera transform (movedepth/layers.py:412-429, 464-518) -----------------------------------
+// transformation_from_parameters = rot_from_axisangle (Rodrigues with the reference's angle + 1e-7 guard) composed with the
+// translation: M = [R t; 0 1], or for invert = [R^T  -R^T t; 0 1].  The reference spends ~50 tiny elementwise launches per call
+// and direction on it; here it is one launch each.  The backward uses forward-mode differentiation of the same expression
+// (a thread per (item, input component) evaluates the 12 outputs with a dual number seeded on its component and contracts
+// them with the upstream gradient), so value and derivative can never drift apart.
+__device__ __forceinline__ float tsqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ float tcos(float x) { return cosf(x); }
+__device__ __forceinline__ float tsin(float x) { return sinf(x); }
+
+struct Dual {
+    float v, d;
+    __device__ __forceinline__ Dual() : v(0.f), d(0.f) {}
+    __device__ __forceinline__ explicit Dual(float v_) : v(v_), d(0.f) {}
+    __device__ __forceinline__ Dual(float v_, float d_) : v(v_), d(d_) {}
+};
+__device__ __forceinline__ Dual operator+(const Dual& a, const Dual& b) { return Dual(a.v + b.v, a.d + b.d); }
+__device__ __forceinline__ Dual operator-(const Dual& a, const Dual& b) { return Dual(a.v - b.v, a.d - b.d); }
+__device__ __forceinline__ Dual operator-(const Dual& a) { return Dual(-a.v, -a.d); }
+__device__ __forceinline__ Dual operator*(const Dual& a, const Dual& b) { return Dual(a.v * b.v, a.d * b.v + a.v * b.d); }
+__device__ __forceinline__ Dual operator/(const Dual& a, const Dual& b) {
+    const float q = a.v / b.v;
+    return Dual(q, (a.d - q * b.d) / b.v);
+}
+__device__ __forceinline__ Dual tsqrt(const Dual& x) {
+    const float r = sqrtf(x.v);
+    return Dual(r, r > 0.f ? 0.5f * x.d / r : 0.f);    // torch's norm backward: zero sub-gradient at the origin
+}
+__device__ __forceinline__ Dual tcos(const Dual& x) { return Dual(cosf(x.v), -sinf(x.v) * x.d); }
+__device__ __forceinline__ Dual tsin(const Dual& x) { return Dual(sinf(x.v), cosf(x.v) * x.d); }
+
+template <typename T>
+struct PoseEval {
+    // out[12]: rows of [R | t] (row-major 3x4)
+    static __device__ __forceinline__ void run(const T (&a)[3], const T (&t)[3], int invert, T (&out)[12]) {
+        const T theta = tsqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+        const T inv = T(1.f) / (theta + T(1e-7f));
+        const T ux = a[0] * inv, uy = a[1] * inv, uz = a[2] * inv;
+        const T ca = tcos(theta), sa = tsin(theta);
+        const T c1 = T(1.f) - ca;
+        const T tx = ux * c1, ty = uy * c1, tz = uz * c1;
+        T R[9] = {ux * tx + ca, ux * ty - uz * sa, uz * tx + uy * sa,
+                  ux * ty + uz * sa, uy * ty + ca, uy * tz - ux * sa,
+                  uz * tx - uy * sa, uy * tz + ux * sa, uz * tz + ca};
+        if (!invert) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) out[i * 4 + j] = R[i * 3 + j];
+                out[i * 4 + 3] = t[i];
+            }
+        } else {                                        // R^T * T(-t)
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) out[i * 4 + j] = R[j * 3 + i];
+                out[i * 4 + 3] = (R[0 * 3 + i] * (-t[0]) + R[1 * 3 + i] * (-t[1])) + R[2 * 3 + i] * (-t[2]);
+            }
+        }
+    }
+};
+__global__ void pose_matrix_fwd_kernel(const float* __restrict__ aa, const float* __restrict__ tr, float* __restrict__ M, int B, int invert) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float a[3] = {aa[3 * b], aa[3 * b + 1], aa[3 * b + 2]}, t[3] = {tr[3 * b], tr[3 * b + 1], tr[3 * b + 2]};
+    float out[12];
+    PoseEval<float>::run(a, t, invert, out);
+    float* m = M + 16 * b;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) m[i] = out[i];
+    m[12] = 0.f; m[13] = 0.f; m[14] = 0.f; m[15] = 1.f;
+}
+
+// thread = (item b, input component j): j < 3 axis-angle, j >= 3 translation
+__global__ void pose_matrix_bwd_kernel(const float* __restrict__ aa, const float* __restrict__ tr, const float* __restrict__ gM,
+                                       float* __restrict__ gaa, float* __restrict__ gtr, int B, int invert) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 6 * B) return;
+    const int b = i / 6, j = i - 6 * b;
+    Dual a[3], t[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        a[k] = Dual(aa[3 * b + k], j == k ? 1.f : 0.f);
+        t[k] = Dual(tr[3 * b + k], j == 3 + k ? 1.f : 0.f);
+    }
+    Dual out[12];
+    PoseEval<Dual>::run(a, t, invert, out);
+    float g = 0.f;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) g = fmaf(gM[16 * b + k], out[k].d, g);
+    if (j < 3) gaa[3 * b + j] = g;
+    else gtr[3 * b + j - 3] = g;
+}
+
 }  // namespace glue
 }  // namespace mvd
 
@@ -421,6 +515,20 @@ int mvd_maxpool3x3s2_bwd(const float* gy, const unsigned char* idx, float* gx, i
     glue::maxpool_bwd_kernel<<<glue::blocks_for(total, 256, 8), 256, 0, as_stream(stream)>>>(
         reinterpret_cast<const float4*>(gy), reinterpret_cast<const uchar4*>(idx), reinterpret_cast<float4*>(gx), B, H, W, C / 4, Ho, Wo);
     return check_launch("maxpool3x3s2_bwd");
+}
+
+int mvd_pose_matrix_fwd(const float* axisangle, const float* translation, float* M, int B, int invert, void* stream) {
+    MVD_REQUIRE(axisangle && translation && M && B > 0, "bad argument");
+    glue::pose_matrix_fwd_kernel<<<(B + 63) / 64, 64, 0, as_stream(stream)>>>(axisangle, translation, M, B, invert ? 1 : 0);
+    return check_launch("pose_matrix_fwd");
+}
+
+int mvd_pose_matrix_bwd(const float* axisangle, const float* translation, const float* gM, float* g_axisangle, float* g_translation,
+                        int B, int invert, void* stream) {
+    MVD_REQUIRE(axisangle && translation && gM && g_axisangle && g_translation && B > 0, "bad argument");
+    glue::pose_matrix_bwd_kernel<<<(6 * B + 63) / 64, 64, 0, as_stream(stream)>>>(axisangle, translation, gM, g_axisangle, g_translation, B,
+                                                                                  invert ? 1 : 0);
+    return check_launch("pose_matrix_bwd");
 }
 
 }

@@ -692,6 +692,38 @@ def conv2d_small(x, weight, k, stride, pad=None):
     return _Conv2dSmall.apply(x, weight, int(k), int(stride), int(k) // 2 if pad is None else int(pad))
 
 
+# ------------------------------------------------------------------------------------- pose-net outputs -> camera transform
+class _PoseMatrix(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, axisangle, translation, invert):
+        B = axisangle.shape[0]
+        aa = _f32(axisangle).reshape(B, 3).contiguous()
+        tr = _f32(translation).reshape(B, 3).contiguous()
+        M = torch.empty((B, 4, 4), device=aa.device, dtype=torch.float32)
+        _lib.check(_lib.lib().mvd_pose_matrix_fwd(_p(aa), _p(tr), _p(M), B, int(invert), _stream()), "mvd_pose_matrix_fwd")
+        launch_counter["n"] += 1
+        ctx.save_for_backward(aa, tr)
+        ctx.meta = (bool(invert), tuple(axisangle.shape), tuple(translation.shape))
+        return M
+
+    @staticmethod
+    def backward(ctx, gM):
+        aa, tr = ctx.saved_tensors
+        invert, sa, st = ctx.meta
+        B = aa.shape[0]
+        gaa, gtr = torch.empty_like(aa), torch.empty_like(tr)
+        _lib.check(_lib.lib().mvd_pose_matrix_bwd(_p(aa), _p(tr), _p(_f32(gM).contiguous()), _p(gaa), _p(gtr), B, int(invert), _stream()),
+                   "mvd_pose_matrix_bwd")
+        launch_counter["n"] += 1
+        return gaa.reshape(sa), gtr.reshape(st), None
+
+
+def pose_matrix(axisangle, translation, invert=False):
+    """transformation_from_parameters (movedepth/layers.py:412-429) in one launch per direction: axis-angle [B,1,3] / [B,3] and
+    translation -> [B,4,4] camera transform (T(t) R, or R^T T(-t) with invert)."""
+    return _PoseMatrix.apply(axisangle, translation, bool(invert))
+
+
 # ------------------------------------------------------------------------------------- ResNet stem max-pool
 class _MaxPool3x3S2(torch.autograd.Function):
     @staticmethod

@@ -917,6 +917,33 @@ def test_one_kernel_batchnorm_exchanges_at_its_grid_barrier_two_ranks_on_one_gpu
             assert int(wss[r].view(torch.int64).abs().sum()) == 0
 
 
+@pytest.mark.parametrize("invert", [False, True], ids=["forward", "inverted"])
+def test_pose_matrix_kernel_matches_the_oracle(ops, invert):
+    """mvd_pose_matrix_fwd/bwd vs oracle.layers.transformation_from_parameters (movedepth/layers.py:412-429) in fp64: the 4x4
+    transform, and the gradients of a random linear functional w.r.t. axis-angle and translation (incl. a zero rotation,
+    where torch's norm backward defines the sub-gradient as 0)."""
+    gen = torch.Generator().manual_seed(51)
+    aa = torch.randn(7, 1, 3, generator=gen) * 0.3
+    tr = torch.randn(7, 1, 3, generator=gen)
+    aa[3] = 0.0
+    aa[5] *= 1e-3
+    gM = torch.randn(7, 4, 4, generator=gen)
+    ao, to = aa.double().requires_grad_(True), tr.double().requires_grad_(True)
+    Mo = OL.transformation_from_parameters(ao, to, invert)
+    (Mo * gM.double()).sum().backward()
+    ag, tg = g(aa).requires_grad_(True), g(tr).requires_grad_(True)
+    M = ops.pose_matrix(ag, tg, invert)
+    (M * g(gM)).sum().backward()
+    torch.testing.assert_close(M.detach().cpu(), Mo.detach().float(), atol=2e-6, rtol=1e-5)
+    keep = [i for i in range(7) if i != 5]
+    torch.testing.assert_close(ag.grad.cpu()[keep], ao.grad.float()[keep], atol=1e-5, rtol=1e-4)
+    # item 5 is a 3e-4 rad rotation: 1 - cos(theta) keeps ~3 significant digits in fp32 (in the reference's arithmetic too)
+    torch.testing.assert_close(ag.grad.cpu()[5], ao.grad.float()[5], atol=5e-4, rtol=5e-3)
+    torch.testing.assert_close(tg.grad.cpu(), to.grad.float(), atol=1e-5, rtol=1e-4)
+    from movedepth_b200 import layers as PL
+    assert torch.equal(PL.transformation_from_parameters(g(aa), g(tr), invert), M.detach())     # the public function takes the kernel
+
+
 # ---------------------------------------------------------------------------------------------- skinny 2-D convolutions
 @pytest.mark.parametrize("cfg", [(3, 8, 3, 1), (8, 8, 3, 1), (8, 16, 5, 2), (16, 16, 3, 1), (16, 16, 3, 1, 0), (16, 4, 3, 1), (16, 4, 3, 1, 0)],
                          ids=["3-8", "8-8", "8-16-k5s2", "16-16", "16-16-valid", "16-4", "16-4-valid"])
