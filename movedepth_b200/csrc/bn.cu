@@ -36,10 +36,23 @@ __device__ __forceinline__ Map make_map(int C) {
     return m;
 }
 
+// Per-thread partial sums are kept in fp64: with fp32 partials the variance E[x^2] - mean^2 of a layer whose mean dominates its
+// spread loses digits that tiny-batch layers then amplify (ResNet50 at batch 1: the gradient norm of the pose encoder moved by
+// 2.7e-3 with the row-to-thread mapping alone).  The kernels are HBM-bound; eight fp64 operations per 16 B load are free.
+__device__ __forceinline__ void add4(double (&s)[4], const float4& v) {
+    s[0] += static_cast<double>(v.x); s[1] += static_cast<double>(v.y); s[2] += static_cast<double>(v.z); s[3] += static_cast<double>(v.w);
+}
+__device__ __forceinline__ void addsq4(double (&s)[4], const float4& v) {
+    s[0] = fma(static_cast<double>(v.x), static_cast<double>(v.x), s[0]);
+    s[1] = fma(static_cast<double>(v.y), static_cast<double>(v.y), s[1]);
+    s[2] = fma(static_cast<double>(v.z), static_cast<double>(v.z), s[2]);
+    s[3] = fma(static_cast<double>(v.w), static_cast<double>(v.w), s[3]);
+}
+
 // reduce 8 per-thread partials over the threads that share a channel quad, then one fp64 atomic per channel per CTA
-template <int T = THREADS>
-__device__ __forceinline__ void block_reduce_to_global(const float (&a)[4], const float (&b)[4], const Map& m, double* out, int C) {
-    __shared__ float red[T][8];
+template <int T = THREADS, typename P = float>
+__device__ __forceinline__ void block_reduce_to_global(const P (&a)[4], const P (&b)[4], const Map& m, double* out, int C) {
+    __shared__ P red[T][8];
     const int t = threadIdx.x;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -81,15 +94,15 @@ __device__ __forceinline__ void exchange_if_last(double* sums, int C, const Peer
 __global__ void __launch_bounds__(THREADS) bn_stats_kernel(const float* __restrict__ x, long long M, int C, double* __restrict__ sums,
                                                            const PeerArgs pa) {
     const Map m = make_map(C);
-    float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+    double s[4] = {0.0, 0.0, 0.0, 0.0}, ss[4] = {0.0, 0.0, 0.0, 0.0};
     const float4* xp = reinterpret_cast<const float4*>(x);
     for (long long r = static_cast<long long>(blockIdx.x) * m.rows_per_iter + m.row0; r < M;
          r += static_cast<long long>(gridDim.x) * m.rows_per_iter) {
         const float4 v = __ldg(xp + r * m.q + m.quad);
         add4(s, v);
-        ss[0] = fmaf(v.x, v.x, ss[0]); ss[1] = fmaf(v.y, v.y, ss[1]); ss[2] = fmaf(v.z, v.z, ss[2]); ss[3] = fmaf(v.w, v.w, ss[3]);
+        addsq4(ss, v);
     }
-    block_reduce_to_global(s, ss, m, sums, C);
+    block_reduce_to_global<THREADS, double>(s, ss, m, sums, C);
     exchange_if_last(sums, C, pa);
 }
 
@@ -318,7 +331,7 @@ __global__ void __launch_bounds__(FT, 2) bn_fwd_fused_kernel(const float* __rest
     const long long step = static_cast<long long>(gridDim.x) * m.rows_per_iter;
     const long long r0 = static_cast<long long>(blockIdx.x) * m.rows_per_iter + m.row0;
     {
-        float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+        double s[4] = {0.0, 0.0, 0.0, 0.0}, ss[4] = {0.0, 0.0, 0.0, 0.0};
         long long r = r0;
         for (; r + 3 * step < M; r += 4 * step) {                                  // four independent loads in flight
             float4 v[4];
@@ -327,16 +340,15 @@ __global__ void __launch_bounds__(FT, 2) bn_fwd_fused_kernel(const float* __rest
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 add4(s, v[u]);
-                ss[0] = fmaf(v[u].x, v[u].x, ss[0]); ss[1] = fmaf(v[u].y, v[u].y, ss[1]);
-                ss[2] = fmaf(v[u].z, v[u].z, ss[2]); ss[3] = fmaf(v[u].w, v[u].w, ss[3]);
+                addsq4(ss, v[u]);
             }
         }
         for (; r < M; r += step) {
             const float4 v = __ldg(xp + r * m.q + m.quad);
             add4(s, v);
-            ss[0] = fmaf(v.x, v.x, ss[0]); ss[1] = fmaf(v.y, v.y, ss[1]); ss[2] = fmaf(v.z, v.z, ss[2]); ss[3] = fmaf(v.w, v.w, ss[3]);
+            addsq4(ss, v);
         }
-        block_reduce_to_global<FT>(s, ss, m, ws, C);
+        block_reduce_to_global<FT, double>(s, ss, m, ws, C);
     }
     grid_barrier_with_exchange(ws, ctl, C, pa, nullptr);
     // the arithmetic of bn_finalize_kernel, once per channel per block; block 0 also publishes it
