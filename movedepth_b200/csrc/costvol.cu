@@ -19,8 +19,10 @@
 // The C-channel volume is never materialised: HBM traffic is ref + src + prior in, the grouped
 // volume out (4*B*h*w*(2C + 1 + D*G) bytes).
 //
-// Backward mirrors it: Q_tap[g] += w_tap * gout[g] is accumulated per cell in registers and
-// flushed with vector atomics when the cell changes.
+// Backward: Q_tap[g] += w_tap * gout[g] is accumulated per bilinear cell in registers and flushed with vector atomics
+// when the cell changes.  The production kernel is costvol_grouped_bwd_v5_kernel (warp-autonomous, a lane pair per pixel,
+// the gradient volume streamed through a per-warp bulk-copy ring; see its header below); the round-1 kernel on the forward's
+// tiles is kept behind MVD_FLAG_BWD_V2 for A/B measurements.
 #include "common.cuh"
 #include "../../include/movedepth_b200.h"
 
