@@ -40,3 +40,22 @@ def test_tma_path_is_in_the_binary(libpath):
     """The cost-volume kernel stages tiles with TMA: the SASS must contain UTMALDG."""
     sass = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", libpath], capture_output=True, text=True).stdout
     assert "UTMALDG" in sass
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Arity and pointer-ness of every ctypes binding in _lib.SIGNATURES against the prototype in include/movedepth_b200.h
+    (an ABI drift -- e.g. a parameter added in the .cu and the header but not in the loader -- would otherwise only show up
+    as garbage arguments on a GPU box)."""
+    import re
+    text = re.sub(r"/\*.*?\*/", "", open(_lib.HEADER).read(), flags=re.S)
+    protos = dict(re.findall(r"\b(mvd_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S))
+    assert set(protos) == set(_lib.declared_symbols())
+    for name, params in protos.items():
+        params = " ".join(params.split())
+        plist = [] if params in ("", "void") else [p.strip() for p in params.split(",")]
+        argtypes = _lib.SIGNATURES[name][0]
+        assert len(plist) == len(argtypes), (name, len(plist), len(argtypes), params)
+        for p, t in zip(plist, argtypes):
+            is_ptr = "*" in p
+            bound_as_ptr = t in (ctypes.c_void_p, ctypes.c_char_p) or (isinstance(t, type) and issubclass(t, ctypes._Pointer))
+            assert is_ptr == bound_as_ptr, (name, p, t)
