@@ -917,6 +917,15 @@ def test_one_kernel_batchnorm_exchanges_at_its_grid_barrier_two_ranks_on_one_gpu
             assert int(wss[r].view(torch.int64).abs().sum()) == 0
 
 
+def test_pose_matrix_kernel_matches_the_reference_golden(ops, gold):
+    """mvd_pose_matrix_fwd vs the reference's own transformation_from_parameters outputs (tests/golden/ops.npz: T_fwd, T_inv,
+    movedepth/layers.py:412-429), incl. the zero rotation that exercises the angle + 1e-7 guard."""
+    c = C.case_pose()
+    for key, invert in (("T_fwd", False), ("T_inv", True)):
+        got = ops.pose_matrix(g(c["aa"]), g(c["tr"]), invert).cpu()
+        torch.testing.assert_close(got, torch.from_numpy(gold[key]), atol=1e-6, rtol=1e-5)
+
+
 @pytest.mark.parametrize("invert", [False, True], ids=["forward", "inverted"])
 def test_pose_matrix_kernel_matches_the_oracle(ops, invert):
     """mvd_pose_matrix_fwd/bwd vs oracle.layers.transformation_from_parameters (movedepth/layers.py:412-429) in fp64: the 4x4
